@@ -1,0 +1,287 @@
+// capi.cu -- extern "C" surface declared in include/clp_b200.h
+#include "../../include/clp_b200.h"
+#include "engine.hpp"
+
+#include <cstring>
+#include <dlfcn.h>
+#include <stdexcept>
+
+struct Clpb_Simplex {
+  clpb::Engine e;
+};
+
+namespace {
+
+// ---- NCCL through dlopen so that single-GPU use has no NCCL dependency -----------------
+typedef int (*ncclGetUniqueId_t)(void *);
+struct NcclId {
+  char internal[128];
+};
+typedef int (*ncclCommInitRankV_t)(void **, int, NcclId, int);
+typedef int (*ncclAllGather_t)(const void *, void *, size_t, int, void *, cudaStream_t);
+
+void *g_nccl = nullptr;
+ncclGetUniqueId_t p_getId = nullptr;
+ncclCommInitRankV_t p_init = nullptr;
+ncclAllGather_t p_allGather = nullptr;
+
+bool loadNccl()
+{
+  if (g_nccl)
+    return true;
+  const char *names[] = {"libnccl.so.2", "libnccl.so", nullptr};
+  for (int i = 0; names[i] && !g_nccl; i++)
+    g_nccl = dlopen(names[i], RTLD_NOW | RTLD_GLOBAL);
+  if (!g_nccl)
+    return false;
+  p_getId = (ncclGetUniqueId_t)dlsym(g_nccl, "ncclGetUniqueId");
+  p_init = (ncclCommInitRankV_t)dlsym(g_nccl, "ncclCommInitRank");
+  p_allGather = (ncclAllGather_t)dlsym(g_nccl, "ncclAllGather");
+  return p_getId && p_init && p_allGather;
+}
+
+struct CommWrap {
+  void *comm;
+  int rank;
+};
+
+int allGatherBytes(void *comm, void *buf, size_t bytesPerRank, void *stream)
+{
+  // in place: rank r's chunk already sits at buf + r*bytesPerRank; ncclChar == 0
+  // sendbuff is resolved by NCCL's in-place convention from the rank stored with the comm
+  CommWrap *w = static_cast<CommWrap *>(comm);
+  const char *send = static_cast<const char *>(buf) + (size_t)w->rank * bytesPerRank;
+  return p_allGather(send, buf, bytesPerRank, 0, w->comm, static_cast<cudaStream_t>(stream));
+}
+
+template <class F> int guarded(F f)
+{
+  try {
+    return f();
+  } catch (const std::exception &ex) {
+    if (std::string(ex.what()) == "no CUDA device")
+      return CLPB_NO_DEVICE;
+    return -99;
+  }
+}
+
+} // namespace
+
+extern "C" {
+
+Clpb_Simplex *Clpb_newModel(void) { return new Clpb_Simplex(); }
+void Clpb_deleteModel(Clpb_Simplex *model) { delete model; }
+
+int Clpb_loadProblem(Clpb_Simplex *model, int numcols, int numrows, const int *start,
+                     const int *index, const double *value, const double *collb,
+                     const double *colub, const double *obj, const double *rowlb,
+                     const double *rowub)
+{
+  return guarded([&] {
+    return model->e.loadProblem(numcols, numrows, start, index, value, collb, colub, obj, rowlb,
+                                rowub);
+  });
+}
+int Clpb_readMps(Clpb_Simplex *model, const char *filename, int, int)
+{
+  return guarded([&] { return model->e.readMps(filename); });
+}
+int Clpb_numberRows(Clpb_Simplex *model) { return model->e.numberRows(); }
+int Clpb_numberColumns(Clpb_Simplex *model) { return model->e.numberColumns(); }
+long long Clpb_getNumElements(Clpb_Simplex *model)
+{
+  return model->e.hColStart.empty() ? 0 : model->e.hColStart[model->e.n];
+}
+void Clpb_getProblem(Clpb_Simplex *model, int *start, int *index, double *value, double *collb,
+                     double *colub, double *obj, double *rowlb, double *rowub)
+{
+  clpb::Engine &e = model->e;
+  const int n = e.n, m = e.m;
+  if (start)
+    std::copy(e.hColStart.begin(), e.hColStart.end(), start);
+  if (index)
+    std::copy(e.hRow.begin(), e.hRow.end(), index);
+  if (value)
+    std::copy(e.hVal.begin(), e.hVal.end(), value);
+  if (collb)
+    std::copy(e.hLower.begin(), e.hLower.begin() + n, collb);
+  if (colub)
+    std::copy(e.hUpper.begin(), e.hUpper.begin() + n, colub);
+  if (obj)
+    std::copy(e.hCost.begin(), e.hCost.begin() + n, obj);
+  if (rowlb)
+    std::copy(e.hLower.begin() + n, e.hLower.begin() + n + m, rowlb);
+  if (rowub)
+    std::copy(e.hUpper.begin() + n, e.hUpper.begin() + n + m, rowub);
+}
+int Clpb_setParameter(Clpb_Simplex *model, const char *key, double value)
+{
+  std::string k(key);
+  clpb::Engine &e = model->e;
+  if (k == "primalTolerance")
+    e.primalTolerance = value;
+  else if (k == "dualTolerance")
+    e.dualTolerance = value;
+  else if (k == "dualBound")
+    e.dualBound = value;
+  else if (k == "maximumIterations")
+    e.maximumIterations = (int)value;
+  else if (k == "maximumSeconds")
+    e.maximumSeconds = value;
+  else if (k == "logLevel")
+    e.logLevel = (int)value;
+  else if (k == "factorizationFrequency")
+    e.factorizationFrequency = (int)value;
+  else if (k == "batch")
+    e.batch = std::max(1, (int)value);
+  else if (k == "timing")
+    e.timing = value != 0.0;
+  else if (k == "objectiveOffset")
+    e.objectiveOffset = value;
+  else
+    return -1;
+  return 0;
+}
+void Clpb_copyinStatus(Clpb_Simplex *model, const unsigned char *statusArray)
+{
+  model->e.setStatus(statusArray);
+}
+int Clpb_dual(Clpb_Simplex *model, int)
+{
+  return guarded([&] { return model->e.dual(); });
+}
+int Clpb_status(Clpb_Simplex *model) { return model->e.problemStatus; }
+double Clpb_objectiveValue(Clpb_Simplex *model) { return model->e.objectiveValue; }
+int Clpb_numberIterations(Clpb_Simplex *model) { return model->e.numberIterations; }
+int Clpb_numberRefactorizations(Clpb_Simplex *model) { return model->e.numberRefactorizations; }
+void Clpb_primalColumnSolution(Clpb_Simplex *model, double *x)
+{
+  if (!model->e.solution.empty())
+    std::copy(model->e.solution.begin(), model->e.solution.begin() + model->e.n, x);
+}
+void Clpb_primalRowSolution(Clpb_Simplex *model, double *y)
+{
+  if (!model->e.solution.empty())
+    std::copy(model->e.solution.begin() + model->e.n, model->e.solution.end(), y);
+}
+void Clpb_dualColumnSolution(Clpb_Simplex *model, double *dj)
+{
+  if (!model->e.reducedCost.empty())
+    std::copy(model->e.reducedCost.begin(), model->e.reducedCost.begin() + model->e.n, dj);
+}
+void Clpb_dualRowSolution(Clpb_Simplex *model, double *pi)
+{
+  if (!model->e.rowPrice.empty())
+    std::copy(model->e.rowPrice.begin(), model->e.rowPrice.end(), pi);
+}
+void Clpb_statusArray(Clpb_Simplex *model, unsigned char *st)
+{
+  if (!model->e.status.empty())
+    std::copy(model->e.status.begin(), model->e.status.end(), st);
+}
+double Clpb_secondsInLoop(Clpb_Simplex *model) { return model->e.secondsInLoop; }
+long long Clpb_kernelLaunches(Clpb_Simplex *model) { return model->e.kernelLaunches; }
+void Clpb_phaseTimes(Clpb_Simplex *model, double *o)
+{
+  const clpb::PhaseTimes &p = model->e.phase;
+  o[0] = p.chuzr;
+  o[1] = p.btran;
+  o[2] = p.price;
+  o[3] = p.chuzc;
+  o[4] = p.dualUpdate;
+  o[5] = p.ftran;
+  o[6] = p.update;
+  o[7] = p.refactor;
+  o[8] = (double)p.samples;
+}
+int Clpb_nucleusSize(Clpb_Simplex *model) { return model->e.lastNucleusSize; }
+
+int Clpb_ncclUniqueId(unsigned char *id128)
+{
+  if (!loadNccl())
+    return -1;
+  return p_getId(id128);
+}
+int Clpb_initSharding(Clpb_Simplex *model, int rank, int worldSize, const unsigned char *id128)
+{
+  if (worldSize <= 1) {
+    model->e.rank = 0;
+    model->e.worldSize = 1;
+    return 0;
+  }
+  if (!loadNccl())
+    return -1;
+  NcclId id;
+  memcpy(id.internal, id128, 128);
+  void *comm = nullptr;
+  int rc = p_init(&comm, worldSize, id, rank);
+  if (rc != 0)
+    return rc;
+  CommWrap *w = new CommWrap{comm, rank};
+  model->e.rank = rank;
+  model->e.worldSize = worldSize;
+  model->e.ncclComm = w;
+  model->e.allGatherFn = allGatherBytes;
+  return 0;
+}
+
+int Clpb_factorize(Clpb_Simplex *model, const int *basicSequence, int *pivotVariable)
+{
+  return guarded([&] { return model->e.factorize(basicSequence, pivotVariable); });
+}
+int Clpb_updateColumn(Clpb_Simplex *model, double *region)
+{
+  return guarded([&] { return model->e.updateColumn(region); });
+}
+int Clpb_updateColumnTranspose(Clpb_Simplex *model, double *region)
+{
+  return guarded([&] { return model->e.updateColumnTranspose(region); });
+}
+int Clpb_replaceColumn(Clpb_Simplex *model, int sequenceIn, int pivotRow)
+{
+  return guarded([&] { return model->e.replaceColumn(sequenceIn, pivotRow); });
+}
+int Clpb_transposeTimes(Clpb_Simplex *model, double scalar, const double *pi, double *z)
+{
+  return guarded([&] {
+    model->e.transposeTimes(scalar, pi, z);
+    return 0;
+  });
+}
+int Clpb_times(Clpb_Simplex *model, double scalar, const double *x, double *y)
+{
+  return guarded([&] {
+    model->e.times(scalar, x, y);
+    return 0;
+  });
+}
+int Clpb_dualColumn(Clpb_Simplex *model, const double *alphaRow, const double *dj,
+                    const unsigned char *status, int direction, double infeasibility,
+                    double *theta)
+{
+  return guarded(
+      [&] { return model->e.dualColumnTest(alphaRow, dj, status, direction, infeasibility, theta); });
+}
+int Clpb_startup(Clpb_Simplex *model)
+{
+  return guarded([&] { return model->e.startup(); });
+}
+int Clpb_iterate(Clpb_Simplex *model, int count)
+{
+  return guarded([&] { return model->e.iterate(count); });
+}
+void Clpb_getWeights(Clpb_Simplex *model, double *weights)
+{
+  guarded([&] {
+    model->e.getWeights(weights);
+    return 0;
+  });
+}
+void Clpb_getDeviceVector(Clpb_Simplex *model, const char *name, double *out)
+{
+  guarded([&] {
+    model->e.getDeviceVector(name, out);
+    return 0;
+  });
+}
+}

@@ -1,0 +1,904 @@
+// engine.cu -- host driver of the device-resident dual simplex (see engine.hpp).
+#include "engine.hpp"
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <stdexcept>
+
+namespace clpb {
+
+#define CUDA_OK(call)                                                                             \
+  do {                                                                                            \
+    cudaError_t e__ = (call);                                                                     \
+    if (e__ != cudaSuccess) {                                                                     \
+      fprintf(stderr, "clp_b200: CUDA error %s at %s:%d\n", cudaGetErrorString(e__), __FILE__,    \
+              __LINE__);                                                                          \
+      throw std::runtime_error("CUDA error");                                                     \
+    }                                                                                             \
+  } while (0)
+
+static inline int roundUp(int v, int a) { return (v + a - 1) / a * a; }
+
+Engine::Engine() {}
+Engine::~Engine()
+{
+  freeAll();
+}
+
+template <class T> T *Engine::dalloc(size_t count)
+{
+  void *p = nullptr;
+  if (count == 0)
+    count = 1;
+  CUDA_OK(cudaMalloc(&p, count * sizeof(T)));
+  allocs.push_back(p);
+  return static_cast<T *>(p);
+}
+
+void Engine::freeAll()
+{
+  for (void *p : allocs)
+    cudaFree(p);
+  allocs.clear();
+  for (cudaEvent_t e : events)
+    cudaEventDestroy(e);
+  events.clear();
+  if (hState)
+    cudaFreeHost(hState);
+  if (hRec)
+    cudaFreeHost(hRec);
+  hState = nullptr;
+  hRec = nullptr;
+  if (stream)
+    cudaStreamDestroy(stream);
+  stream = nullptr;
+  deviceReady = false;
+  nucCap = 0;
+  s1Cap = 0;
+}
+
+int Engine::defaultFactorizationFrequency() const
+{
+  // ClpSimplex::defaultFactorizationFrequency, src/ClpSimplex.cpp:11401-11431
+  const int cutoff1 = 10000, base = 75, freq0 = 50, freq1 = 150, maximum = 10000;
+  int frequency;
+  if (m < cutoff1)
+    frequency = base + m / freq0;
+  else
+    frequency = base + cutoff1 / freq0 + (m - cutoff1) / freq1;
+  return std::min(maximum, frequency);
+}
+
+int Engine::loadProblem(int numberColumns, int numberRows, const int *columnStart, const int *row,
+                        const double *element, const double *columnLower,
+                        const double *columnUpper, const double *objective, const double *rowLower,
+                        const double *rowUpper)
+{
+  freeAll();
+  n = numberColumns;
+  m = numberRows;
+  nm = n + m;
+  if (nm >= (1 << 20) - 1) {
+    fprintf(stderr, "clp_b200: n+m must be below 2^20 (packed argmax keys)\n");
+    return -1;
+  }
+  hColStart.assign(columnStart, columnStart + n + 1);
+  const long long nnz = hColStart[n];
+  hRow.assign(row, row + nnz);
+  hVal.assign(element, element + nnz);
+  hLower.assign(nm, 0.0);
+  hUpper.assign(nm, 0.0);
+  hCost.assign(nm, 0.0);
+  auto lo = [](double v) { return v < -1.0e29 ? -kInf : v; };
+  auto up = [](double v) { return v > 1.0e29 ? kInf : v; };
+  for (int j = 0; j < n; j++) {
+    hCost[j] = objective ? objective[j] : 0.0;
+    hLower[j] = columnLower ? lo(columnLower[j]) : 0.0;
+    hUpper[j] = columnUpper ? up(columnUpper[j]) : kInf;
+  }
+  for (int i = 0; i < m; i++) {
+    hLower[n + i] = rowLower ? lo(rowLower[i]) : -kInf;
+    hUpper[n + i] = rowUpper ? up(rowUpper[i]) : kInf;
+  }
+  haveUserStatus = false;
+  hStatus.assign(nm, atLowerBound);
+  for (int i = 0; i < m; i++)
+    hStatus[n + i] = basic;
+  problemStatus = -1;
+  return 0;
+}
+
+int Engine::readMps(const char *fileName)
+{
+  int mm, nn;
+  std::vector<int> cs, ri;
+  std::vector<double> va, cl, cu, ob, rl, ru;
+  double off = 0.0;
+  int rc = readMpsFile(fileName, mm, nn, cs, ri, va, cl, cu, ob, rl, ru, off, problemName);
+  if (rc != 0)
+    return rc;
+  rc = loadProblem(nn, mm, cs.data(), ri.data(), va.data(), cl.data(), cu.data(), ob.data(),
+                   rl.data(), ru.data());
+  objectiveOffset = off;
+  return rc;
+}
+
+void Engine::setStatus(const unsigned char *st)
+{
+  hStatus.assign(st, st + nm);
+  haveUserStatus = true;
+}
+
+int Engine::setupDevice()
+{
+  if (deviceReady)
+    return 0;
+  int devCount = 0;
+  if (cudaGetDeviceCount(&devCount) != cudaSuccess || devCount == 0) {
+    fprintf(stderr, "clp_b200: no CUDA device -- this engine has no CPU fallback\n");
+    throw std::runtime_error("no CUDA device");
+  }
+  CUDA_OK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+  const long long nnz = hColStart[n];
+  // row copy (CSR) built on the host once
+  std::vector<int> rowStart(m + 1, 0), colIdx(nnz);
+  std::vector<double> rval(nnz);
+  for (long long e = 0; e < nnz; e++)
+    rowStart[hRow[e] + 1]++;
+  for (int i = 0; i < m; i++)
+    rowStart[i + 1] += rowStart[i];
+  {
+    std::vector<int> fill(rowStart.begin(), rowStart.end() - 1);
+    for (int j = 0; j < n; j++)
+      for (int e = hColStart[j]; e < hColStart[j + 1]; e++) {
+        int at = fill[hRow[e]]++;
+        colIdx[at] = j;
+        rval[at] = hVal[e];
+      }
+  }
+  d.m = m;
+  d.n = n;
+  d.nm = nm;
+  d.nnz = nnz;
+  int *p;
+  double *q;
+  p = dalloc<int>(n + 1);
+  CUDA_OK(cudaMemcpy(p, hColStart.data(), sizeof(int) * (n + 1), cudaMemcpyHostToDevice));
+  d.colStart = p;
+  p = dalloc<int>(nnz);
+  CUDA_OK(cudaMemcpy(p, hRow.data(), sizeof(int) * nnz, cudaMemcpyHostToDevice));
+  d.rowIdx = p;
+  q = dalloc<double>(nnz);
+  CUDA_OK(cudaMemcpy(q, hVal.data(), sizeof(double) * nnz, cudaMemcpyHostToDevice));
+  d.val = q;
+  p = dalloc<int>(m + 1);
+  CUDA_OK(cudaMemcpy(p, rowStart.data(), sizeof(int) * (m + 1), cudaMemcpyHostToDevice));
+  d.rowStart = p;
+  p = dalloc<int>(nnz);
+  CUDA_OK(cudaMemcpy(p, colIdx.data(), sizeof(int) * nnz, cudaMemcpyHostToDevice));
+  d.colIdx = p;
+  q = dalloc<double>(nnz);
+  CUDA_OK(cudaMemcpy(q, rval.data(), sizeof(double) * nnz, cudaMemcpyHostToDevice));
+  d.rval = q;
+
+  d.cost = dalloc<double>(nm);
+  d.costTrue = dalloc<double>(nm);
+  d.lower = dalloc<double>(nm);
+  d.upper = dalloc<double>(nm);
+  d.lowerTrue = dalloc<double>(nm);
+  d.upperTrue = dalloc<double>(nm);
+  d.sol = dalloc<double>(nm);
+  d.dj = dalloc<double>(nm);
+  d.status = dalloc<unsigned char>(nm);
+  d.fake = dalloc<unsigned char>(nm);
+  dFlipFlag = dalloc<unsigned char>(nm);
+  d.pivotVariable = dalloc<int>(m);
+  d.weights = dalloc<double>(m);
+  dWeightsTmp = dalloc<double>(m);
+  dSrcPos = dalloc<int>(m);
+  d.posToNuc = dalloc<int>(m);
+  d.nucRow = dalloc<int>(m);
+  d.nucCol = dalloc<int>(m);
+  dS1RowStart = dalloc<int>(m + 1);
+  d.s1RowStart = dS1RowStart;
+  tmax = factorizationFrequency > 0 ? factorizationFrequency : defaultFactorizationFrequency();
+  tmax = std::max(8, std::min(tmax, 2048));
+  d.tmax = roundUp(tmax, 8);
+  d.W = dalloc<double>((size_t)m * d.tmax);
+  d.etaPos = dalloc<int>(d.tmax);
+  d.etaPrevSame = dalloc<int>(d.tmax);
+  d.etaLastOfPos = dalloc<int>(m);
+  d.Ginv = dalloc<double>((size_t)d.tmax * d.tmax);
+  d.rho = dalloc<double>(m);
+  d.alphaRow = dalloc<double>(nm);
+  d.rhs3 = dalloc<double>((size_t)3 * m);
+  d.uwork = dalloc<double>(m);
+  d.ywork = dalloc<double>((size_t)6 * roundUp(m, 8));
+  d.swork = dalloc<double>(roundUp(m, 8));
+  d.mu = dalloc<double>((size_t)3 * d.tmax);
+  d.nu = dalloc<double>(d.tmax);
+  d.histWeight = dalloc<unsigned long long>(kHistBuckets);
+  d.histMin = dalloc<unsigned long long>(kHistBuckets);
+  d.flipList = dalloc<int>(nm);
+  d.st = dalloc<IterState>(1);
+  d.recCap = 64;
+  d.rec = dalloc<IterRecord>(d.recCap);
+  dXn = dalloc<double>(n);
+  dRhs = dalloc<double>(m);
+  dPi = dalloc<double>(m);
+  dZ = dalloc<double>(n);
+  dObj = dalloc<double>(2);
+  dCounters = dalloc<int>(4);
+  dIpiv = dalloc<int>(m);
+  dPerm = dalloc<int>(m);
+  dInfo = dalloc<int>(1);
+  CUDA_OK(cudaMallocHost(&hState, sizeof(IterState)));
+  CUDA_OK(cudaMallocHost(&hRec, sizeof(IterRecord) * d.recCap));
+  d.k = 0;
+  d.ldk = 8;
+  d.Ninv = nullptr;
+  d.NinvT = nullptr;
+  d.primalTolerance = primalTolerance;
+  d.dualTolerance = dualTolerance;
+  d.acceptablePivot = acceptablePivot;
+  d.zeroTolerance = zeroTolerance;
+
+  CUDA_OK(cudaMemcpy(d.costTrue, hCost.data(), sizeof(double) * nm, cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemcpy(d.cost, hCost.data(), sizeof(double) * nm, cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemcpy(d.lowerTrue, hLower.data(), sizeof(double) * nm, cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemcpy(d.upperTrue, hUpper.data(), sizeof(double) * nm, cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemcpy(d.lower, hLower.data(), sizeof(double) * nm, cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemcpy(d.upper, hUpper.data(), sizeof(double) * nm, cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemset(d.fake, 0, nm));
+  CUDA_OK(cudaMemset(d.dj, 0, sizeof(double) * nm));
+  CUDA_OK(cudaMemset(d.histWeight, 0, sizeof(unsigned long long) * kHistBuckets));
+  CUDA_OK(cudaMemset(d.histMin, 0xFF, sizeof(unsigned long long) * kHistBuckets));
+  CUDA_OK(cudaMemset(d.st, 0, sizeof(IterState)));
+  if (timing) {
+    events.resize(16 * 8 + 2);
+    for (auto &e : events)
+      CUDA_OK(cudaEventCreate(&e));
+  }
+  deviceReady = true;
+  return 0;
+}
+
+void Engine::resetStateForRun()
+{
+  // nonbasic variables start at a finite bound; weights 1 (ClpDualRowSteepest::saveWeights mode 1)
+  std::vector<double> sol0(nm, 0.0);
+  int nBasic = 0;
+  for (int j = 0; j < nm; j++)
+    if (hStatus[j] == basic)
+      nBasic++;
+  if (nBasic != m) {
+    hStatus.assign(nm, atLowerBound);
+    for (int i = 0; i < m; i++)
+      hStatus[n + i] = basic;
+  }
+  for (int j = 0; j < nm; j++) {
+    if (hStatus[j] == basic)
+      continue;
+    double lo = hLower[j], up = hUpper[j];
+    if (lo > -kInf && up < kInf) {
+      if (lo == up) {
+        hStatus[j] = isFixed;
+        sol0[j] = lo;
+      } else if (hStatus[j] == atUpperBound)
+        sol0[j] = up;
+      else {
+        hStatus[j] = atLowerBound;
+        sol0[j] = lo;
+      }
+    } else if (lo > -kInf) {
+      hStatus[j] = atLowerBound;
+      sol0[j] = lo;
+    } else if (up < kInf) {
+      hStatus[j] = atUpperBound;
+      sol0[j] = up;
+    } else {
+      hStatus[j] = isFree;
+      sol0[j] = 0.0;
+    }
+  }
+  hPivot.clear();
+  for (int j = 0; j < nm; j++)
+    if (hStatus[j] == basic)
+      hPivot.push_back(j);
+  CUDA_OK(cudaMemcpy(d.sol, sol0.data(), sizeof(double) * nm, cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemcpy(d.status, hStatus.data(), nm, cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemcpy(d.pivotVariable, hPivot.data(), sizeof(int) * m, cudaMemcpyHostToDevice));
+  std::vector<double> w(m, 1.0);
+  CUDA_OK(cudaMemcpy(d.weights, w.data(), sizeof(double) * m, cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemcpy(d.cost, hCost.data(), sizeof(double) * nm, cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemcpy(d.lower, hLower.data(), sizeof(double) * nm, cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemcpy(d.upper, hUpper.data(), sizeof(double) * nm, cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemset(d.fake, 0, nm));
+  CUDA_OK(cudaMemset(d.st, 0, sizeof(IterState)));
+  d.primalTolerance = primalTolerance;
+  d.dualTolerance = dualTolerance;
+  d.acceptablePivot = acceptablePivot;
+  d.zeroTolerance = zeroTolerance;
+  currentDualBound = dualBound;
+}
+
+// ---------------------------------------------------------------------------------------
+// Refactorize the current basis.  Host: canonical positions, nucleus index sets, S1 (symbolic
+// part: ClpFactorization::factorize gather of the basis, ClpFactorization.cpp:2212-2244).
+// Device: dense nucleus gather, LU, inverse, transpose (numerical part).
+int Engine::refactor()
+{
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (timing) {
+    e0 = events[events.size() - 2];
+    e1 = events[events.size() - 1];
+    cudaEventRecord(e0, stream);
+  }
+  CUDA_OK(cudaMemcpyAsync(hStatus.data(), d.status, nm, cudaMemcpyDeviceToHost, stream));
+  hPivot.resize(m);
+  CUDA_OK(cudaMemcpyAsync(hPivot.data(), d.pivotVariable, sizeof(int) * m, cudaMemcpyDeviceToHost,
+                          stream));
+  CUDA_OK(cudaStreamSynchronize(stream));
+  std::vector<int> hostIpiv(m), hostPerm(m);
+  for (int attempt = 0; attempt < 200; attempt++) {
+    // ---- canonical positions: basic slack of row i at position i, structurals elsewhere
+    std::vector<int> newPivot(m, -1), srcPos(m, -1);
+    std::vector<int> queue; // old positions of structurals that must move
+    std::vector<int> oldPosOf;
+    for (int p = 0; p < m; p++) {
+      int seq = hPivot[p];
+      if (seq >= n) {
+        int i = seq - n;
+        newPivot[i] = seq;
+        srcPos[i] = p;
+      }
+    }
+    for (int p = 0; p < m; p++) {
+      int seq = hPivot[p];
+      if (seq < n) {
+        if (newPivot[p] < 0 && hStatus[n + p] != basic) {
+          newPivot[p] = seq;
+          srcPos[p] = p;
+        } else
+          queue.push_back(p);
+      }
+    }
+    {
+      size_t qi = 0;
+      for (int p = 0; p < m && qi < queue.size(); p++)
+        if (newPivot[p] < 0) {
+          newPivot[p] = hPivot[queue[qi]];
+          srcPos[p] = queue[qi];
+          qi++;
+        }
+    }
+    // ---- nucleus index sets
+    std::vector<int> posToNuc(m, -1), nucRow, nucCol;
+    for (int p = 0; p < m; p++)
+      if (newPivot[p] < n) {
+        posToNuc[p] = (int)nucRow.size();
+        nucRow.push_back(p);
+        nucCol.push_back(newPivot[p]);
+      }
+    const int k = (int)nucRow.size();
+    const int ldk = std::max(8, roundUp(k, 8));
+    // ---- S1 = A[C rows, nucleus columns] as CSR over positions
+    std::vector<int> s1Start(m + 1, 0);
+    for (int j = 0; j < k; j++)
+      for (int e = hColStart[nucCol[j]]; e < hColStart[nucCol[j] + 1]; e++)
+        if (posToNuc[hRow[e]] < 0)
+          s1Start[hRow[e] + 1]++;
+    for (int i = 0; i < m; i++)
+      s1Start[i + 1] += s1Start[i];
+    std::vector<int> s1Col(s1Start[m]);
+    std::vector<double> s1Val(s1Start[m]);
+    {
+      std::vector<int> fill(s1Start.begin(), s1Start.end() - 1);
+      for (int j = 0; j < k; j++)
+        for (int e = hColStart[nucCol[j]]; e < hColStart[nucCol[j] + 1]; e++) {
+          int i = hRow[e];
+          if (posToNuc[i] < 0) {
+            int at = fill[i]++;
+            s1Col[at] = j;
+            s1Val[at] = hVal[e];
+          }
+        }
+    }
+    if ((size_t)s1Start[m] > s1Cap) {
+      s1Cap = (size_t)s1Start[m] * 3 / 2 + 1024;
+      dS1Col = dalloc<int>(s1Cap);
+      dS1Val = dalloc<double>(s1Cap);
+    }
+    d.s1Col = dS1Col;
+    d.s1Val = dS1Val;
+    if ((size_t)k * ldk > nucCap) {
+      int kc = std::min(m, std::max(k + k / 4 + 64, 256));
+      int ldc = roundUp(kc, 8);
+      nucCap = (size_t)kc * ldc;
+      d.Ninv = dalloc<double>(nucCap);
+      d.NinvT = dalloc<double>(nucCap);
+    }
+    d.k = k;
+    d.ldk = ldk;
+    CUDA_OK(cudaMemcpyAsync(d.posToNuc, posToNuc.data(), sizeof(int) * m, cudaMemcpyHostToDevice, stream));
+    if (k > 0) {
+      CUDA_OK(cudaMemcpyAsync(d.nucRow, nucRow.data(), sizeof(int) * k, cudaMemcpyHostToDevice, stream));
+      CUDA_OK(cudaMemcpyAsync(d.nucCol, nucCol.data(), sizeof(int) * k, cudaMemcpyHostToDevice, stream));
+    }
+    CUDA_OK(cudaMemcpyAsync(dS1RowStart, s1Start.data(), sizeof(int) * (m + 1), cudaMemcpyHostToDevice, stream));
+    if (s1Start[m] > 0) {
+      CUDA_OK(cudaMemcpyAsync(dS1Col, s1Col.data(), sizeof(int) * s1Start[m], cudaMemcpyHostToDevice, stream));
+      CUDA_OK(cudaMemcpyAsync(dS1Val, s1Val.data(), sizeof(double) * s1Start[m], cudaMemcpyHostToDevice, stream));
+    }
+    int info = 0;
+    if (k > 0) {
+      // row-major nucleus N in NinvT == column-major N^T ; inverse comes out as row-major N^-1
+      CUDA_OK(cudaMemsetAsync(d.NinvT, 0, sizeof(double) * (size_t)k * ldk, stream));
+      launch_gather_nucleus_matrix(d, d.NinvT, ldk, stream);
+      info = dense_invert(d.NinvT, d.Ninv, k, ldk, dIpiv, dPerm, dInfo, hostIpiv.data(),
+                          hostPerm.data(), 1.0e-11, stream);
+      kernelLaunches += 6 * ((k + 31) / 32) * 2;
+    }
+    if (info == 0) {
+      if (k > 0)
+        launch_transpose(d.Ninv, d.NinvT, k, ldk, stream);
+      // weights follow their variables; pivotVariable takes the canonical order
+      CUDA_OK(cudaMemcpyAsync(dSrcPos, srcPos.data(), sizeof(int) * m, cudaMemcpyHostToDevice, stream));
+      launch_permute_weights(d.weights, dWeightsTmp, dSrcPos, m, stream);
+      CUDA_OK(cudaMemcpyAsync(d.weights, dWeightsTmp, sizeof(double) * m, cudaMemcpyDeviceToDevice, stream));
+      CUDA_OK(cudaMemcpyAsync(d.pivotVariable, newPivot.data(), sizeof(int) * m, cudaMemcpyHostToDevice, stream));
+      CUDA_OK(cudaMemsetAsync(d.etaLastOfPos, 0xFF, sizeof(int) * m, stream));
+      // numEtas = 0 (keep the rest of the state)
+      CUDA_OK(cudaMemsetAsync(&d.st->numEtas, 0, sizeof(int), stream));
+      CUDA_OK(cudaStreamSynchronize(stream));
+      hPivot = newPivot;
+      numberRefactorizations++;
+      lastNucleusSize = k;
+      if (timing) {
+        cudaEventRecord(e1, stream);
+        cudaEventSynchronize(e1);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        phase.refactor += ms;
+      }
+      return 0;
+    }
+    // ---- singular: the LU ran on N^T, so the failing column is nucleus ROW info-1 (a
+    // position whose row is dependent); bring its slack in and drop the structural that the
+    // permutation had parked there (ClpFactorization.cpp:2382-2532 does the same repair).
+    const int jbad = info - 1;
+    for (int i = 0; i < k; i++)
+      hostPerm[i] = i;
+    for (int j = 0; j < jbad; j++) {
+      int pp = hostIpiv[j];
+      if (pp != j)
+        std::swap(hostPerm[j], hostPerm[pp]);
+    }
+    const int seqLeave = nucCol[hostPerm[jbad]];
+    const int rowEnter = nucRow[jbad];
+    if (logLevel > 0)
+      fprintf(stderr, "clp_b200: singular basis: structural %d out, slack of row %d in\n",
+              seqLeave, rowEnter);
+    // new basis list (positions are re-canonicalised on the next attempt)
+    for (int p = 0; p < m; p++)
+      if (newPivot[p] == seqLeave)
+        newPivot[p] = n + rowEnter;
+    // make srcPos consistent: treat as a fresh basis for weights of the new slack
+    hPivot = newPivot;
+    hStatus[n + rowEnter] = basic;
+    double lo = hLower[seqLeave], up = hUpper[seqLeave];
+    unsigned char st;
+    double x;
+    if (lo > -kInf) {
+      st = (lo == up) ? isFixed : atLowerBound;
+      x = lo;
+    } else if (up < kInf) {
+      st = atUpperBound;
+      x = up;
+    } else {
+      st = isFree;
+      x = 0.0;
+    }
+    hStatus[seqLeave] = st;
+    CUDA_OK(cudaMemcpy(d.status + seqLeave, &st, 1, cudaMemcpyHostToDevice));
+    unsigned char bs = basic;
+    CUDA_OK(cudaMemcpy(d.status + n + rowEnter, &bs, 1, cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpy(d.sol + seqLeave, &x, sizeof(double), cudaMemcpyHostToDevice));
+    // weights: permute to the (old->new) order first so the next attempt starts from newPivot
+    CUDA_OK(cudaMemcpy(dSrcPos, srcPos.data(), sizeof(int) * m, cudaMemcpyHostToDevice));
+    launch_permute_weights(d.weights, dWeightsTmp, dSrcPos, m, stream);
+    CUDA_OK(cudaMemcpyAsync(d.weights, dWeightsTmp, sizeof(double) * m, cudaMemcpyDeviceToDevice, stream));
+    CUDA_OK(cudaStreamSynchronize(stream));
+  }
+  return -1;
+}
+
+int Engine::refresh()
+{
+  if (refactor() != 0)
+    return -1;
+  launch_compute_duals(d, dPi, dZ, stream);
+  CUDA_OK(cudaMemsetAsync(dCounters, 0, sizeof(int) * 4, stream));
+  launch_make_dual_feasible(d, currentDualBound, dCounters, stream);
+  launch_compute_primals(d, dXn, dRhs, stream);
+  kernelLaunches += 20;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+void Engine::enqueueIteration(bool timed, int slot)
+{
+  cudaEvent_t *ev = timed ? &events[(size_t)slot * 8] : nullptr;
+  if (timed)
+    cudaEventRecord(ev[0], stream);
+  launch_chuzr(d, stream);
+  if (timed)
+    cudaEventRecord(ev[1], stream);
+  launch_btran_unit(d, true, stream);
+  if (timed)
+    cudaEventRecord(ev[2], stream);
+  if (worldSize > 1) {
+    int per = (n + worldSize - 1) / worldSize;
+    int c0 = std::min(n, rank * per), c1 = std::min(n, c0 + per);
+    launch_price(d, c0, c1, false, stream);
+    // one exchange per pricing pass: all-gather of the row shards (padded to 'per' entries;
+    // the padding lands on the slack part, which is written afterwards)
+    allGatherFn(ncclComm, d.alphaRow, sizeof(double) * per, stream);
+    launch_price_slacks(d, false, stream);
+    launch_histogram(d, stream);
+  } else {
+    launch_price(d, 0, n, true, stream);
+    launch_price_slacks(d, true, stream);
+  }
+  if (timed)
+    cudaEventRecord(ev[3], stream);
+  launch_chuzc(d, stream);
+  if (timed)
+    cudaEventRecord(ev[4], stream);
+  launch_dual_update_and_flips(d, dFlipFlag, stream);
+  if (timed)
+    cudaEventRecord(ev[5], stream);
+  launch_ftran(d, 3, true, stream);
+  if (timed)
+    cudaEventRecord(ev[6], stream);
+  launch_pivot_updates(d, stream);
+  if (timed)
+    cudaEventRecord(ev[7], stream);
+  kernelLaunches += 2 + 4 + 2 + 4 + 3 + 5 + 4;
+}
+
+void Engine::fetchState()
+{
+  CUDA_OK(cudaMemcpyAsync(hState, d.st, sizeof(IterState), cudaMemcpyDeviceToHost, stream));
+  CUDA_OK(cudaStreamSynchronize(stream));
+}
+
+void Engine::downloadSolution()
+{
+  solution.resize(nm);
+  reducedCost.resize(nm);
+  rowPrice.resize(m);
+  status.resize(nm);
+  pivotVariable.resize(m);
+  launch_objective(d, dObj, stream);
+  double obj[2];
+  CUDA_OK(cudaMemcpyAsync(solution.data(), d.sol, sizeof(double) * nm, cudaMemcpyDeviceToHost, stream));
+  CUDA_OK(cudaMemcpyAsync(reducedCost.data(), d.dj, sizeof(double) * nm, cudaMemcpyDeviceToHost, stream));
+  CUDA_OK(cudaMemcpyAsync(rowPrice.data(), dPi, sizeof(double) * m, cudaMemcpyDeviceToHost, stream));
+  CUDA_OK(cudaMemcpyAsync(status.data(), d.status, nm, cudaMemcpyDeviceToHost, stream));
+  CUDA_OK(cudaMemcpyAsync(pivotVariable.data(), d.pivotVariable, sizeof(int) * m, cudaMemcpyDeviceToHost, stream));
+  CUDA_OK(cudaMemcpyAsync(obj, dObj, sizeof(double) * 2, cudaMemcpyDeviceToHost, stream));
+  CUDA_OK(cudaStreamSynchronize(stream));
+  objectiveValue = obj[0] + objectiveOffset;
+  sumPrimalInfeasibilities = obj[1];
+  hStatus = status;
+}
+
+int Engine::startup()
+{
+  setupDevice();
+  resetStateForRun();
+  return refresh();
+}
+
+// ClpSimplexDual::dual (src/ClpSimplexDual.cpp:637) : startup, loop, finish.
+int Engine::dual()
+{
+  auto t0 = std::chrono::steady_clock::now();
+  problemStatus = -1;
+  numberIterations = 0;
+  numberRefactorizations = 0;
+  kernelLaunches = 0;
+  phase = PhaseTimes();
+  if (startup() != 0) {
+    problemStatus = 4;
+    return problemStatus;
+  }
+  int dualBoundIncreases = 0;
+  int consecutiveTrouble = 0;
+  const int maxPivots = d.tmax < tmax ? d.tmax : tmax;
+  while (problemStatus < 0) {
+    if (numberIterations >= maximumIterations) {
+      problemStatus = 3;
+      break;
+    }
+    double el = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    if (el > maximumSeconds) {
+      problemStatus = 3;
+      break;
+    }
+    // enqueue a batch of iterations; kernels become no-ops once the device sets a stop reason
+    fetchState();
+    int room = maxPivots - hState->numEtas;
+    if (room <= 0) {
+      if (refresh() != 0) {
+        problemStatus = 4;
+        break;
+      }
+      continue;
+    }
+    int count = std::min(std::min(batch, room), maximumIterations - numberIterations);
+    count = std::min(count, d.recCap);
+    if (timing)
+      count = std::min(count, 16);
+    const int before = hState->iterations;
+    for (int b = 0; b < count; b++)
+      enqueueIteration(timing, b);
+    fetchState();
+    const int done = hState->iterations - before;
+    numberIterations += done;
+    if (timing) {
+      for (int b = 0; b < done; b++) {
+        float ms[7];
+        for (int q = 0; q < 7; q++)
+          cudaEventElapsedTime(&ms[q], events[(size_t)b * 8 + q], events[(size_t)b * 8 + q + 1]);
+        phase.chuzr += ms[0];
+        phase.btran += ms[1];
+        phase.price += ms[2];
+        phase.chuzc += ms[3];
+        phase.dualUpdate += ms[4];
+        phase.ftran += ms[5];
+        phase.update += ms[6];
+        phase.samples++;
+      }
+    }
+    if (logLevel > 1)
+      fprintf(stderr, "clp_b200: it %d etas %d k %d stop %d infeas %.6g theta %.6g\n",
+              numberIterations, hState->numEtas, d.k, hState->stop, hState->infeas,
+              hState->thetaDual);
+    const int stop = hState->stop;
+    if (stop == STOP_NONE) {
+      consecutiveTrouble = 0;
+      continue;
+    }
+    // clear the stop reason for the next batch
+    CUDA_OK(cudaMemsetAsync(&d.st->stop, 0, sizeof(int), stream));
+    const bool fresh = hState->numEtas == 0;
+    switch (stop) {
+    case STOP_ETAS_FULL:
+    case STOP_INACCURATE:
+      if (stop == STOP_INACCURATE && ++consecutiveTrouble > 50) {
+        problemStatus = 4;
+        break;
+      }
+      if (refresh() != 0)
+        problemStatus = 4;
+      break;
+    case STOP_TINY_PIVOT:
+      if (++consecutiveTrouble > 5)
+        problemStatus = 4;
+      else if (refresh() != 0)
+        problemStatus = 4;
+      break;
+    case STOP_NO_ROW: {
+      if (!fresh) {
+        if (refresh() != 0)
+          problemStatus = 4;
+        break;
+      }
+      // primal feasible on fresh factors (statusOfProblemInDual :4996 optimality branch)
+      if (hState->costShifts > 0) {
+        CUDA_OK(cudaMemcpyAsync(d.cost, d.costTrue, sizeof(double) * nm, cudaMemcpyDeviceToDevice, stream));
+        CUDA_OK(cudaMemsetAsync(&d.st->costShifts, 0, sizeof(int), stream));
+        if (refresh() != 0)
+          problemStatus = 4;
+        break;
+      }
+      int atFake = 0;
+      CUDA_OK(cudaMemsetAsync(dCounters, 0, sizeof(int) * 4, stream));
+      launch_count_fake(d, dCounters, stream);
+      CUDA_OK(cudaMemcpyAsync(&atFake, dCounters, sizeof(int), cudaMemcpyDeviceToHost, stream));
+      CUDA_OK(cudaStreamSynchronize(stream));
+      if (atFake > 0) {
+        if (dualBoundIncreases < 2) {
+          dualBoundIncreases++;
+          currentDualBound *= 1000.0;
+          if (refresh() != 0)
+            problemStatus = 4;
+          break;
+        }
+        problemStatus = 2;
+        break;
+      }
+      problemStatus = 0;
+      break;
+    }
+    case STOP_NO_COLUMN: {
+      if (!fresh) {
+        if (refresh() != 0)
+          problemStatus = 4;
+        break;
+      }
+      int atFake = 0;
+      CUDA_OK(cudaMemsetAsync(dCounters, 0, sizeof(int) * 4, stream));
+      launch_count_fake(d, dCounters, stream);
+      CUDA_OK(cudaMemcpyAsync(&atFake, dCounters, sizeof(int), cudaMemcpyDeviceToHost, stream));
+      CUDA_OK(cudaStreamSynchronize(stream));
+      if (atFake > 0 && dualBoundIncreases < 2) {
+        dualBoundIncreases++;
+        currentDualBound *= 1000.0;
+        if (refresh() != 0)
+          problemStatus = 4;
+        break;
+      }
+      problemStatus = 1;
+      break;
+    }
+    default:
+      problemStatus = 4;
+      break;
+    }
+  }
+  downloadSolution();
+  secondsInLoop = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  return problemStatus;
+}
+
+// ---------------------------------------------------------------------------------------
+// plug-in level entry points (host buffers in, host buffers out)
+int Engine::factorize(const int *basicSequence, int *pivotVariableOut)
+{
+  setupDevice();
+  hStatus.assign(nm, atLowerBound);
+  for (int p = 0; p < m; p++)
+    hStatus[basicSequence[p]] = basic;
+  haveUserStatus = true;
+  resetStateForRun();
+  // keep the caller's order where it is canonical
+  std::vector<int> pv(basicSequence, basicSequence + m);
+  CUDA_OK(cudaMemcpy(d.pivotVariable, pv.data(), sizeof(int) * m, cudaMemcpyHostToDevice));
+  int rc = refactor();
+  if (pivotVariableOut)
+    std::copy(hPivot.begin(), hPivot.end(), pivotVariableOut);
+  return rc;
+}
+
+int Engine::updateColumn(double *vec)
+{
+  CUDA_OK(cudaMemcpyAsync(d.rhs3, vec, sizeof(double) * m, cudaMemcpyHostToDevice, stream));
+  launch_ftran_buffer(d, d.rhs3, 1, true, stream);
+  CUDA_OK(cudaMemcpyAsync(vec, d.rhs3, sizeof(double) * m, cudaMemcpyDeviceToHost, stream));
+  CUDA_OK(cudaStreamSynchronize(stream));
+  return 0;
+}
+
+int Engine::updateColumnTranspose(double *vec)
+{
+  CUDA_OK(cudaMemcpyAsync(d.rho, vec, sizeof(double) * m, cudaMemcpyHostToDevice, stream));
+  launch_btran_dense(d, d.rho, true, stream);
+  CUDA_OK(cudaMemcpyAsync(vec, d.rho, sizeof(double) * m, cudaMemcpyDeviceToHost, stream));
+  CUDA_OK(cudaStreamSynchronize(stream));
+  return 0;
+}
+
+int Engine::replaceColumn(int sequenceIn, int pivotRow)
+{
+  fetchState();
+  if (hState->numEtas >= d.tmax)
+    return 5;
+  launch_unpack_column(d, sequenceIn, d.rhs3, stream);
+  launch_ftran_buffer(d, d.rhs3, 1, true, stream);
+  double alpha = 0.0;
+  CUDA_OK(cudaMemcpyAsync(&alpha, d.rhs3 + pivotRow, sizeof(double), cudaMemcpyDeviceToHost, stream));
+  CUDA_OK(cudaStreamSynchronize(stream));
+  if (!(std::fabs(alpha) >= 1.0e-11))
+    return 2;
+  launch_eta_append_test(d, pivotRow, sequenceIn, stream);
+  CUDA_OK(cudaStreamSynchronize(stream));
+  hPivot[pivotRow] = sequenceIn;
+  return 0;
+}
+
+void Engine::transposeTimes(double scalar, const double *pi, double *z)
+{
+  setupDevice();
+  CUDA_OK(cudaMemcpyAsync(dPi, pi, sizeof(double) * m, cudaMemcpyHostToDevice, stream));
+  launch_transpose_times(d, dPi, dZ, scalar, stream);
+  CUDA_OK(cudaMemcpyAsync(z, dZ, sizeof(double) * n, cudaMemcpyDeviceToHost, stream));
+  CUDA_OK(cudaStreamSynchronize(stream));
+}
+
+void Engine::times(double scalar, const double *x, double *y)
+{
+  setupDevice();
+  CUDA_OK(cudaMemcpyAsync(dXn, x, sizeof(double) * n, cudaMemcpyHostToDevice, stream));
+  launch_times_rows(d, dXn, dRhs, scalar, stream);
+  CUDA_OK(cudaMemcpyAsync(y, dRhs, sizeof(double) * m, cudaMemcpyDeviceToHost, stream));
+  CUDA_OK(cudaStreamSynchronize(stream));
+}
+
+int Engine::dualColumnTest(const double *alphaRow, const double *dj, const unsigned char *stat,
+                           int sigma, double infeas, double *theta)
+{
+  setupDevice();
+  resetStateForRun();
+  CUDA_OK(cudaMemcpy(d.alphaRow, alphaRow, sizeof(double) * nm, cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemcpy(d.dj, dj, sizeof(double) * nm, cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemcpy(d.status, stat, nm, cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemset(d.rho, 0, sizeof(double) * m));
+  IterState st;
+  memset(&st, 0, sizeof(st));
+  st.sigma = sigma;
+  st.infeas = infeas;
+  CUDA_OK(cudaMemcpy(d.st, &st, sizeof(st), cudaMemcpyHostToDevice));
+  launch_histogram(d, stream);
+  launch_chuzc(d, stream);
+  fetchState();
+  *theta = hState->thetaDual;
+  if (hState->stop != 0)
+    return -1;
+  return hState->seqIn;
+}
+
+int Engine::iterate(int count)
+{
+  int total = 0;
+  while (count > 0) {
+    int c = std::min(count, d.recCap);
+    fetchState();
+    const int before = hState->iterations;
+    for (int b = 0; b < c; b++)
+      enqueueIteration(false, b);
+    fetchState();
+    total += hState->iterations - before;
+    if (hState->stop != 0)
+      break;
+    count -= c;
+  }
+  return total;
+}
+
+void Engine::getWeights(double *w)
+{
+  CUDA_OK(cudaMemcpy(w, d.weights, sizeof(double) * m, cudaMemcpyDeviceToHost));
+}
+
+void Engine::getDeviceVector(const char *name, double *out)
+{
+  std::string s(name);
+  CUDA_OK(cudaStreamSynchronize(stream));
+  if (s == "sol")
+    CUDA_OK(cudaMemcpy(out, d.sol, sizeof(double) * nm, cudaMemcpyDeviceToHost));
+  else if (s == "dj")
+    CUDA_OK(cudaMemcpy(out, d.dj, sizeof(double) * nm, cudaMemcpyDeviceToHost));
+  else if (s == "rho")
+    CUDA_OK(cudaMemcpy(out, d.rho, sizeof(double) * m, cudaMemcpyDeviceToHost));
+  else if (s == "alphaRow")
+    CUDA_OK(cudaMemcpy(out, d.alphaRow, sizeof(double) * nm, cudaMemcpyDeviceToHost));
+  else if (s == "pivotVariable") {
+    std::vector<int> pv(m);
+    CUDA_OK(cudaMemcpy(pv.data(), d.pivotVariable, sizeof(int) * m, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < m; i++)
+      out[i] = pv[i];
+  } else if (s == "status") {
+    std::vector<unsigned char> st(nm);
+    CUDA_OK(cudaMemcpy(st.data(), d.status, nm, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < nm; i++)
+      out[i] = st[i];
+  }
+}
+
+} // namespace clpb

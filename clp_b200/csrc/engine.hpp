@@ -1,0 +1,135 @@
+// engine.hpp -- host side of the B200 dual simplex engine (C++ interface behind the C ABI).
+//
+// The host keeps what ClpSimplexDual keeps on the host in the reference: the iteration
+// driver (whileIterating / statusOfProblemInDual, src/ClpSimplexDual.cpp:973,4996), the
+// refactorization policy (ClpSimplex.cpp:11401 defaultFactorizationFrequency), fake-bound /
+// cost-shift clean-up decisions and the problem status.  Everything O(m), O(n) or O(nnz) per
+// iteration runs in the CUDA kernels of solve.cu / price.cu / update.cu / factor.cu.
+#pragma once
+#include "engine.cuh"
+
+#include <string>
+#include <vector>
+
+namespace clpb {
+
+struct PhaseTimes { // accumulated device milliseconds per phase (when timing is on)
+  double chuzr = 0, btran = 0, price = 0, chuzc = 0, dualUpdate = 0, ftran = 0, update = 0,
+         refactor = 0;
+  long samples = 0;
+};
+
+class Engine {
+public:
+  Engine();
+  ~Engine();
+
+  // ---- problem (ClpModel::loadProblem / readMps) ----
+  int loadProblem(int numberColumns, int numberRows, const int *columnStart, const int *row,
+                  const double *element, const double *columnLower, const double *columnUpper,
+                  const double *objective, const double *rowLower, const double *rowUpper);
+  int readMps(const char *fileName);
+
+  // ---- parameters ----
+  double primalTolerance = 1.0e-7, dualTolerance = 1.0e-7, dualBound = 1.0e10;
+  double acceptablePivot = 1.0e-7, zeroTolerance = 1.0e-13;
+  int maximumIterations = 2147483647;
+  double maximumSeconds = 1.0e30;
+  int factorizationFrequency = 0; // 0 = default formula
+  int logLevel = 0;
+  int batch = 16;                 // iterations enqueued per host synchronisation
+  bool timing = false;
+  double objectiveOffset = 0.0;
+  // column sharding of the pricing pass (multi-GPU): this rank prices [colBegin,colEnd)
+  int rank = 0, worldSize = 1;
+  void *ncclComm = nullptr; // ncclComm_t when worldSize > 1
+  int (*allGatherFn)(void *comm, void *buf, size_t bytesPerRank, void *stream) = nullptr;
+
+  // ---- solve (ClpSimplex::dual) ----
+  int dual();
+  int problemStatus = -1;
+  int numberIterations = 0, numberRefactorizations = 0;
+  double objectiveValue = 0.0, sumPrimalInfeasibilities = 0.0;
+  double secondsInLoop = 0.0;
+  long kernelLaunches = 0;
+  PhaseTimes phase;
+  int lastNucleusSize = 0;
+
+  // ---- results (host copies, valid after dual()) ----
+  std::vector<double> solution;     // n+m
+  std::vector<double> reducedCost;  // n+m
+  std::vector<double> rowPrice;     // m
+  std::vector<unsigned char> status; // n+m
+  std::vector<int> pivotVariable;   // m
+  void setStatus(const unsigned char *st);
+
+  // ---- plug-in level entry points (parity tests; host buffers) ----
+  int factorize(const int *basicSequence, int *pivotVariableOut);
+  int updateColumn(double *vec);            // FTRAN in place, m doubles
+  int updateColumnTranspose(double *vec);   // BTRAN in place
+  int replaceColumn(int sequenceIn, int pivotRow);
+  void transposeTimes(double scalar, const double *pi, double *z);
+  void times(double scalar, const double *x, double *y);
+  int dualColumnTest(const double *alphaRow, const double *dj, const unsigned char *stat,
+                     int sigma, double infeas, double *theta);
+  int iterate(int count);                   // run 'count' iterations from the current state
+  void getWeights(double *w);
+  void getDeviceVector(const char *name, double *out);
+  int startup();                            // status -> basis, factorize, compute primals/duals
+
+  int numberRows() const { return m; }
+  int numberColumns() const { return n; }
+  long long numberElements() const { return (long long)hColStart.empty() ? 0 : hColStart[n]; }
+  const std::vector<double> &colLower() const { return hLower; }
+
+  // host copy of the problem
+  int m = 0, n = 0, nm = 0;
+  std::vector<int> hColStart, hRow;
+  std::vector<double> hVal;
+  std::vector<double> hLower, hUpper, hCost; // n+m, true bounds/costs
+  std::string problemName;
+
+private:
+  DeviceModel d{};
+  cudaStream_t stream = nullptr;
+  bool deviceReady = false;
+  bool haveUserStatus = false;
+  // device allocations (owned)
+  std::vector<void *> allocs;
+  double *dXn = nullptr, *dRhs = nullptr, *dPi = nullptr, *dZ = nullptr, *dObj = nullptr;
+  double *dWeightsTmp = nullptr;
+  int *dSrcPos = nullptr, *dCounters = nullptr;
+  unsigned char *dFlipFlag = nullptr;
+  int *dIpiv = nullptr, *dPerm = nullptr, *dInfo = nullptr;
+  int *dS1RowStart = nullptr, *dS1Col = nullptr;
+  double *dS1Val = nullptr;
+  size_t s1Cap = 0;
+  size_t nucCap = 0; // capacity (elements) of Ninv / NinvT
+  IterState *hState = nullptr; // pinned
+  IterRecord *hRec = nullptr;
+  std::vector<cudaEvent_t> events;
+  std::vector<unsigned char> hStatus;
+  std::vector<int> hPivot;
+  int tmax = 0;
+  double currentDualBound = 0.0;
+
+  template <class T> T *dalloc(size_t count);
+  void freeAll();
+  int setupDevice();
+  int refactor();          // factorize current basis (repairs singular bases)
+  int refresh();           // refactor + computeDuals + makeDualFeasible + computePrimals
+  void enqueueIteration(bool timed, int slot);
+  void fetchState();
+  void downloadSolution();
+  int defaultFactorizationFrequency() const;
+  void resetStateForRun();
+};
+
+// mps_reader.cpp
+int readMpsFile(const char *fileName, int &m, int &n, std::vector<int> &colStart,
+                std::vector<int> &row, std::vector<double> &val, std::vector<double> &colLower,
+                std::vector<double> &colUpper, std::vector<double> &obj,
+                std::vector<double> &rowLower, std::vector<double> &rowUpper, double &objOffset,
+                std::string &name);
+
+} // namespace clpb

@@ -1,0 +1,428 @@
+// price.cu -- PRICE (tableau row) and CHUZC (bound-flipping ratio test), device resident.
+//
+// Replaces ClpPackedMatrix::transposeTimes (/root/reference/src/ClpPackedMatrix.cpp:706 ->
+// transposeTimesByColumn :961 -> gutsOfTransposeTimesUnscaled :1640/:1799, the variant that
+// skips basic columns by status and fuses the first pass of the ratio test) and
+// ClpSimplexDual::dualColumn0 / dualColumn (src/ClpSimplexDual.cpp:3665 / :4192).
+//
+// PRICE streams the CSC copy of A once (12 B per nonzero) with one warp per column; rho is
+// gathered through L1/L2.  Fused into the same pass: every ratio-test candidate adds its
+// slope contribution |alpha_j|*(u_j-l_j) to a histogram over the (monotone) bit pattern of its
+// ratio d_j/|alpha_j| -- in 2^-40 fixed point relative to the primal infeasibility, with
+// integer atomics, so the result does not depend on the order of the atomics.
+//
+// CHUZC then needs no sort: a single CTA scans the 32768-bucket histogram for the bucket in
+// which the slope of the dual objective is exhausted (theta*), one pass computes the Harris
+// bound beyond theta* (atomicMin) and one pass picks the largest |alpha| inside
+// [theta*, harris] (atomicMax on a packed (|alpha|,sequence) key).  Candidates with a ratio
+// below theta* are "passed": the dual update flips them to their other bound (BFRT).
+#include "engine.cuh"
+
+namespace clpb {
+
+__device__ __forceinline__ bool iter_active(const IterState *st) { return st->stop == 0; }
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+    v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+constexpr unsigned long long kFixOne = 1ull << 40; // fixed-point 1.0 (== infeasibility)
+constexpr unsigned long long kFixCap = 1ull << 41;
+constexpr unsigned long long kSentinel = 0xFFFFFFFFFFFFFFFFull;
+
+__device__ __forceinline__ int ratio_bucket(double r)
+{
+  return (int)((unsigned long long)__double_as_longlong(r) >> 48) & (kHistBuckets - 1);
+}
+
+// Ratio-test candidate test for nonbasic variable j with tableau entry alpha.
+// Returns false if j cannot bound the dual step.  abar = sigma*alpha.
+__device__ __forceinline__ bool candidate(const DeviceModel &d, int j, double alpha, int sigma,
+                                          double &a, double &dtil, bool &boxed, double &range)
+{
+  const unsigned char st = d.status[j];
+  if (st == basic || st == isFixed)
+    return false;
+  const double ab = sigma * alpha;
+  a = fabs(ab);
+  if (a <= 1.0e-12)
+    return false;
+  const double dj = d.dj[j];
+  boxed = false;
+  range = 0.0;
+  if (st == atLowerBound) {
+    if (ab <= 0.0)
+      return false;
+    dtil = dj > 0.0 ? dj : 0.0;
+  } else if (st == atUpperBound) {
+    if (ab >= 0.0)
+      return false;
+    dtil = dj < 0.0 ? -dj : 0.0;
+  } else {
+    dtil = 0.0;
+    return true;
+  }
+  range = d.upper[j] - d.lower[j];
+  boxed = range < 1.0e29;
+  return true;
+}
+
+__device__ __forceinline__ void histogram_add(const DeviceModel &d, double a, double dtil,
+                                              bool boxed, double range, double infeas)
+{
+  const double ratio = dtil / a;
+  const int b = ratio_bucket(ratio);
+  unsigned long long w = kFixCap;
+  if (boxed) {
+    double v = a * range / infeas * 1099511627776.0;
+    w = v >= 2199023255552.0 ? kFixCap : (unsigned long long)v;
+  }
+  atomicAdd(d.histWeight + b, w);
+  atomicMin(d.histMin + b, (unsigned long long)__double_as_longlong(ratio));
+}
+
+// alphaRow[j] = rho^T a_j for nonbasic, non-fixed columns j in [colBegin,colEnd) + histogram
+__global__ void __launch_bounds__(256) price_kernel(DeviceModel d, int colBegin, int colEnd, bool fuseHist)
+{
+  if (!iter_active(d.st))
+    return;
+  const int lane = threadIdx.x & 31;
+  const int warpsPerBlock = blockDim.x >> 5;
+  const int sigma = d.st->sigma;
+  const double infeas = d.st->infeas;
+  const double *__restrict__ rho = d.rho;
+  for (int j = colBegin + blockIdx.x * warpsPerBlock + (threadIdx.x >> 5); j < colEnd;
+       j += gridDim.x * warpsPerBlock) {
+    const unsigned char st = d.status[j];
+    if (st == basic || st == isFixed) {
+      if (lane == 0)
+        d.alphaRow[j] = 0.0;
+      continue;
+    }
+    const int e0 = d.colStart[j], e1 = d.colStart[j + 1];
+    double acc = 0.0;
+    for (int e = e0 + lane; e < e1; e += 32)
+      acc = fma(__ldg(d.val + e), __ldg(rho + __ldg(d.rowIdx + e)), acc);
+    acc = warp_sum(acc);
+    if (lane == 0) {
+      if (fabs(acc) < d.zeroTolerance)
+        acc = 0.0;
+      d.alphaRow[j] = acc;
+      double a, dtil, range;
+      bool boxed;
+      if (fuseHist && acc != 0.0 && candidate(d, j, acc, sigma, a, dtil, boxed, range))
+        histogram_add(d, a, dtil, boxed, range, infeas);
+    }
+  }
+}
+
+// slack part of the row: alpha_{n+i} = -rho_i for nonbasic rows
+__global__ void price_slack_kernel(DeviceModel d, bool fuseHist)
+{
+  if (!iter_active(d.st))
+    return;
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= d.m)
+    return;
+  const int j = d.n + i;
+  const unsigned char st = d.status[j];
+  double alpha = 0.0;
+  if (st != basic && st != isFixed) {
+    alpha = -d.rho[i];
+    if (fabs(alpha) < d.zeroTolerance)
+      alpha = 0.0;
+  }
+  d.alphaRow[j] = alpha;
+  double a, dtil, range;
+  bool boxed;
+  if (fuseHist && alpha != 0.0 && candidate(d, j, alpha, d.st->sigma, a, dtil, boxed, range))
+    histogram_add(d, a, dtil, boxed, range, d.st->infeas);
+}
+
+// stand-alone histogram pass over a complete tableau row (column-sharded runs: after the
+// all-gather of the row; also used by the ratio-test parity tests)
+__global__ void histogram_kernel(DeviceModel d)
+{
+  if (!iter_active(d.st))
+    return;
+  const int sigma = d.st->sigma;
+  const double infeas = d.st->infeas;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < d.nm; j += gridDim.x * blockDim.x) {
+    const double alpha = d.alphaRow[j];
+    if (alpha == 0.0)
+      continue;
+    double a, dtil, range;
+    bool boxed;
+    if (candidate(d, j, alpha, sigma, a, dtil, boxed, range))
+      histogram_add(d, a, dtil, boxed, range, infeas);
+  }
+}
+void launch_histogram(const DeviceModel &d, cudaStream_t s)
+{
+  int blocks = (d.nm + 255) / 256;
+  if (blocks > 148 * 4)
+    blocks = 148 * 4;
+  histogram_kernel<<<blocks, 256, 0, s>>>(d);
+}
+
+void launch_price(const DeviceModel &d, int colBegin, int colEnd, bool fuseHist, cudaStream_t s)
+{
+  int ncol = colEnd - colBegin;
+  if (ncol > 0) {
+    int blocks = (ncol + 7) / 8;
+    int cap = 148 * 16;
+    if (blocks > cap)
+      blocks = cap;
+    price_kernel<<<blocks, 256, 0, s>>>(d, colBegin, colEnd, fuseHist);
+  }
+}
+void launch_price_slacks(const DeviceModel &d, bool fuseHist, cudaStream_t s)
+{
+  price_slack_kernel<<<(d.m + 255) / 256, 256, 0, s>>>(d, fuseHist);
+}
+
+// ---------------------------------------------------------------------------------------
+// single CTA: find theta* from the histogram, reset it, compute ||rho||^2
+__global__ void __launch_bounds__(1024) chuzc_scan_kernel(DeviceModel d)
+{
+  if (!iter_active(d.st))
+    return;
+  constexpr int PER = kHistBuckets / 1024;
+  const int tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5;
+  __shared__ unsigned long long warpTot[32];
+  __shared__ int sLast[32];
+  __shared__ int sCross;
+  __shared__ double sNorm[32];
+  unsigned long long w[PER];
+  unsigned long long mn[PER];
+  unsigned long long tot = 0;
+  int last = -1;
+#pragma unroll
+  for (int q = 0; q < PER; q++) {
+    int b = tid * PER + q;
+    w[q] = d.histWeight[b];
+    mn[q] = d.histMin[b];
+    tot += w[q];
+    if (mn[q] != kSentinel)
+      last = b;
+    d.histWeight[b] = 0ull;
+    d.histMin[b] = kSentinel;
+  }
+  // inclusive scan of per-thread totals
+  unsigned long long inc = tot;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    unsigned long long t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o)
+      inc += t;
+  }
+  int wl = last;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+    wl = max(wl, __shfl_xor_sync(0xffffffffu, wl, o));
+  if (lane == 31)
+    warpTot[warp] = inc;
+  if (lane == 0)
+    sLast[warp] = wl;
+  if (tid == 0)
+    sCross = -1;
+  // ||rho||^2
+  double nrm = 0.0;
+  for (int i = tid; i < d.m; i += 1024) {
+    double r = d.rho[i];
+    nrm = fma(r, r, nrm);
+  }
+  nrm = warp_sum(nrm);
+  if (lane == 0)
+    sNorm[warp] = nrm;
+  __syncthreads();
+  unsigned long long base = 0;
+  for (int q = 0; q < warp; q++)
+    base += warpTot[q];
+  unsigned long long excl = base + inc - tot;
+  if (excl < kFixOne && excl + tot >= kFixOne) {
+    unsigned long long c = excl;
+    int found = -1;
+#pragma unroll
+    for (int q = 0; q < PER; q++) {
+      c += w[q];
+      if (found < 0 && c >= kFixOne)
+        found = tid * PER + q;
+    }
+    sCross = found; // exactly one thread crosses
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int lastAll = -1;
+    for (int q = 0; q < 32; q++)
+      lastAll = max(lastAll, sLast[q]);
+    double nsum = 0.0;
+    for (int q = 0; q < 32; q++)
+      nsum += sNorm[q];
+    d.st->rhoNorm2 = nsum;
+    d.st->harrisBits = 0x7FF0000000000000ull; // +inf
+    d.st->chuzcKey = 0ull;
+    if (lastAll < 0) {
+      d.st->stop = STOP_NO_COLUMN;
+      d.st->thetaStar = 0.0;
+      sCross = -2;
+    } else if (sCross < 0) {
+      sCross = lastAll; // slope never exhausted: stop at the last breakpoint group
+    }
+  }
+  __syncthreads();
+  const int b = sCross;
+  if (b >= 0 && tid == (b / PER))
+    d.st->thetaStar = __longlong_as_double((long long)mn[b % PER]);
+}
+
+// Harris bound over candidates with ratio >= theta*  (ClpSimplexDual.cpp:4331-4395 upperTheta)
+__global__ void chuzc_harris_kernel(DeviceModel d)
+{
+  if (!iter_active(d.st))
+    return;
+  const int sigma = d.st->sigma;
+  const double thetaStar = d.st->thetaStar;
+  const double tol = d.dualTolerance;
+  unsigned long long best = 0x7FF0000000000000ull;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < d.nm; j += gridDim.x * blockDim.x) {
+    const double alpha = d.alphaRow[j];
+    if (alpha == 0.0)
+      continue;
+    double a, dtil, range;
+    bool boxed;
+    if (!candidate(d, j, alpha, sigma, a, dtil, boxed, range))
+      continue;
+    if (a < d.acceptablePivot || dtil / a < thetaStar)
+      continue;
+    unsigned long long h = (unsigned long long)__double_as_longlong((dtil + tol) / a);
+    best = min(best, h);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+    best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
+  if ((threadIdx.x & 31) == 0 && best != 0x7FF0000000000000ull)
+    atomicMin(&d.st->harrisBits, best);
+}
+
+// largest |alpha| with theta* <= ratio <= harris  (ClpSimplexDual.cpp:4531-4573)
+__global__ void chuzc_select_kernel(DeviceModel d)
+{
+  if (!iter_active(d.st))
+    return;
+  const int sigma = d.st->sigma;
+  const double thetaStar = d.st->thetaStar;
+  const double harris = __longlong_as_double((long long)d.st->harrisBits);
+  unsigned long long best = 0ull;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < d.nm; j += gridDim.x * blockDim.x) {
+    const double alpha = d.alphaRow[j];
+    if (alpha == 0.0)
+      continue;
+    double a, dtil, range;
+    bool boxed;
+    if (!candidate(d, j, alpha, sigma, a, dtil, boxed, range))
+      continue;
+    const double ratio = dtil / a;
+    if (a < d.acceptablePivot || ratio < thetaStar || ratio > harris)
+      continue;
+    unsigned long long key = ((unsigned long long)__double_as_longlong(a) & ~0xFFFFFull) |
+                             (unsigned long long)(0xFFFFF - j);
+    best = max(best, key);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+    best = max(best, __shfl_xor_sync(0xffffffffu, best, o));
+  if ((threadIdx.x & 31) == 0 && best != 0ull)
+    atomicMax(&d.st->chuzcKey, best);
+}
+
+__global__ void chuzc_finish_kernel(DeviceModel d)
+{
+  IterState *st = d.st;
+  if (!iter_active(st))
+    return;
+  const unsigned long long key = st->chuzcKey;
+  if (key == 0ull) {
+    st->stop = STOP_NO_COLUMN;
+    return;
+  }
+  const int q = 0xFFFFF - (int)(key & 0xFFFFFull);
+  st->seqIn = q;
+  const double alpha = d.alphaRow[q];
+  st->alphaRow = alpha;
+  const double t = d.dj[q] / (st->sigma * alpha);
+  st->thetaDual = t > 0.0 ? t : 0.0;
+  st->harrisTheta = __longlong_as_double((long long)st->harrisBits);
+}
+
+void launch_chuzc(const DeviceModel &d, cudaStream_t s)
+{
+  chuzc_scan_kernel<<<1, 1024, 0, s>>>(d);
+  int blocks = (d.nm + 255) / 256;
+  if (blocks > 148 * 4)
+    blocks = 148 * 4;
+  chuzc_harris_kernel<<<blocks, 256, 0, s>>>(d);
+  chuzc_select_kernel<<<blocks, 256, 0, s>>>(d);
+  chuzc_finish_kernel<<<1, 1, 0, s>>>(d);
+}
+
+// ---------------------------------------------------------------------------------------
+// z[j] = scalar * pi^T a_j for all columns (ClpPackedMatrix::transposeTimes, plain variant :1484)
+__global__ void __launch_bounds__(256)
+    transpose_times_kernel(DeviceModel d, const double *__restrict__ pi, double *__restrict__ z,
+                           double scalar)
+{
+  const int lane = threadIdx.x & 31;
+  const int warpsPerBlock = blockDim.x >> 5;
+  for (int j = blockIdx.x * warpsPerBlock + (threadIdx.x >> 5); j < d.n;
+       j += gridDim.x * warpsPerBlock) {
+    double acc = 0.0;
+    for (int e = d.colStart[j] + lane; e < d.colStart[j + 1]; e += 32)
+      acc = fma(__ldg(d.val + e), __ldg(pi + __ldg(d.rowIdx + e)), acc);
+    acc = warp_sum(acc);
+    if (lane == 0)
+      z[j] = scalar * acc;
+  }
+}
+void launch_transpose_times(const DeviceModel &d, const double *pi, double *z, double scalar,
+                            cudaStream_t s)
+{
+  int blocks = (d.n + 7) / 8;
+  if (blocks > 148 * 16)
+    blocks = 148 * 16;
+  if (d.n > 0)
+    transpose_times_kernel<<<blocks, 256, 0, s>>>(d, pi, z, scalar);
+}
+
+// y[i] = scalar * sum_j A_ij x_j  via the row copy (ClpPackedMatrix::times :296)
+__global__ void __launch_bounds__(256)
+    times_rows_kernel(DeviceModel d, const double *__restrict__ x, double *__restrict__ y,
+                      double scalar)
+{
+  const int lane = threadIdx.x & 31;
+  const int warpsPerBlock = blockDim.x >> 5;
+  for (int i = blockIdx.x * warpsPerBlock + (threadIdx.x >> 5); i < d.m;
+       i += gridDim.x * warpsPerBlock) {
+    double acc = 0.0;
+    for (int e = d.rowStart[i] + lane; e < d.rowStart[i + 1]; e += 32)
+      acc = fma(__ldg(d.rval + e), __ldg(x + __ldg(d.colIdx + e)), acc);
+    acc = warp_sum(acc);
+    if (lane == 0)
+      y[i] = scalar * acc;
+  }
+}
+void launch_times_rows(const DeviceModel &d, const double *x, double *y, double scalar,
+                       cudaStream_t s)
+{
+  int blocks = (d.m + 7) / 8;
+  if (blocks > 148 * 16)
+    blocks = 148 * 16;
+  times_rows_kernel<<<blocks, 256, 0, s>>>(d, x, y, scalar);
+}
+
+} // namespace clpb

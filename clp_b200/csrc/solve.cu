@@ -1,0 +1,405 @@
+// solve.cu -- FTRAN / BTRAN through the basis factors (device resident).
+//
+// Replaces ClpFactorization::updateColumn / updateColumnFT / updateTwoColumnsFT
+// (/root/reference/src/ClpFactorization.cpp:2803,2723,2889 -> CoinAbcBaseFactorization3.cpp
+// updateColumnL/R/U) and ClpFactorization::updateColumnTranspose (ClpFactorization.cpp:2993 ->
+// CoinAbcBaseFactorization4.cpp:3216).  See engine.cuh for the factor layout.
+//
+//   FTRAN  x = B_t^-1 b :   yN = Ninv * b_N                      (GEMV, HBM stream of Ninv)
+//                           x_N = yN ; x_C = S1*yN - b_C          (CSR SpMV)
+//                           mu = Ginv * x[P] ; x -= W * mu        (eta panel GEMV)
+//   BTRAN  rho = B_t^-T e_r: nu = Ginv^T * W[r,:] ; u = e_r - sum_j e_{p_j} nu_j
+//                           rho_C = -u_C ; s = u_N + S1^T u_C
+//                           rho_N = Ninv^T * s                    (GEMV, HBM stream of NinvT)
+// Up to three right-hand sides share one pass over Ninv / W (the reference's
+// updateTwoColumnsFT fusion, plus the bound-flip column of ClpSimplexDual.cpp:1533).
+#include "engine.cuh"
+
+namespace clpb {
+
+__device__ __forceinline__ int decode_row(unsigned long long key) { return (int)(key & 0xFFFFFull); }
+
+__device__ __forceinline__ bool iter_active(const IterState *st)
+{
+  return st->stop == 0;
+}
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+    v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ---------------------------------------------------------------------------------------
+// gather b_N : xg[c][j] = b_c[nucRow[j]]
+__global__ void gather_nucleus_kernel(DeviceModel d, const double *__restrict__ b, int bstride,
+                                      double *__restrict__ xg, int nrhs, bool checkState)
+{
+  if (checkState && !iter_active(d.st))
+    return;
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= d.ldk)
+    return;
+  if (j >= d.k) { // zero padding so the GEMV can run over the padded row length
+    for (int c = 0; c < nrhs; c++)
+      xg[(size_t)c * d.ldk + j] = 0.0;
+    return;
+  }
+  int p = d.nucRow[j];
+  for (int c = 0; c < nrhs; c++)
+    xg[(size_t)c * d.ldk + j] = b[(size_t)c * bstride + p];
+}
+
+// y[c][i] = sum_j M[i][j] * x[c][j]   (M row-major k x ldk, one warp per row)
+// if outIndex != nullptr the result is scattered: out[c*ostride + outIndex[i]]
+template <int NRHS>
+__global__ void __launch_bounds__(256)
+    gemv_rows_kernel(const double *__restrict__ M, int k, int ldk, const double *__restrict__ x,
+                     double *__restrict__ out, int ostride, const int *__restrict__ outIndex,
+                     const IterState *st, bool checkState)
+{
+  if (checkState && !iter_active(st))
+    return;
+  const int warpsPerBlock = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  for (int i = blockIdx.x * warpsPerBlock + warp; i < k; i += gridDim.x * warpsPerBlock) {
+    const double2 *row = reinterpret_cast<const double2 *>(M + (size_t)i * ldk);
+    double acc[NRHS];
+#pragma unroll
+    for (int c = 0; c < NRHS; c++)
+      acc[c] = 0.0;
+    const int half = ldk >> 1; // ldk is a multiple of 8, padding is zero
+#pragma unroll 4
+    for (int j = lane; j < half; j += 32) {
+      double2 a = __ldg(row + j);
+#pragma unroll
+      for (int c = 0; c < NRHS; c++) {
+        const double2 xv = __ldg(reinterpret_cast<const double2 *>(x + (size_t)c * ldk) + j);
+        acc[c] = fma(a.x, xv.x, acc[c]);
+        acc[c] = fma(a.y, xv.y, acc[c]);
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < NRHS; c++)
+      acc[c] = warp_sum(acc[c]);
+    if (lane == 0) {
+      int o = outIndex ? outIndex[i] : i;
+#pragma unroll
+      for (int c = 0; c < NRHS; c++)
+        out[(size_t)c * ostride + o] = acc[c];
+    }
+  }
+}
+
+// x_N = yN ; x_C = S1*yN - b_C   (in place on b, 8 lanes per position)
+template <int NRHS>
+__global__ void ftran_spread_kernel(DeviceModel d, double *__restrict__ b, int bstride,
+                                    const double *__restrict__ y, bool checkState)
+{
+  if (checkState && !iter_active(d.st))
+    return;
+  const int sub = threadIdx.x & 7;
+  int p = (blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+  if (p >= d.m)
+    return; // whole 8-lane group exits together
+  const unsigned gmask = 0xFFu << ((threadIdx.x & 31) & ~7);
+  int ni = d.posToNuc[p];
+  if (ni >= 0) {
+    if (sub == 0)
+      for (int c = 0; c < NRHS; c++)
+        b[(size_t)c * bstride + p] = y[(size_t)c * d.ldk + ni];
+    return;
+  }
+  double acc[NRHS];
+#pragma unroll
+  for (int c = 0; c < NRHS; c++)
+    acc[c] = 0.0;
+  if (d.k > 0) {
+    int e0 = d.s1RowStart[p], e1 = d.s1RowStart[p + 1];
+    for (int e = e0 + sub; e < e1; e += 8) {
+      double v = d.s1Val[e];
+      int j = d.s1Col[e];
+#pragma unroll
+      for (int c = 0; c < NRHS; c++)
+        acc[c] = fma(v, y[(size_t)c * d.ldk + j], acc[c]);
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < NRHS; c++) {
+    acc[c] += __shfl_xor_sync(gmask, acc[c], 4);
+    acc[c] += __shfl_xor_sync(gmask, acc[c], 2);
+    acc[c] += __shfl_xor_sync(gmask, acc[c], 1);
+  }
+  if (sub == 0)
+    for (int c = 0; c < NRHS; c++)
+      b[(size_t)c * bstride + p] = acc[c] - b[(size_t)c * bstride + p];
+}
+
+// mu[c][i] = sum_{j<=i} Ginv[i][j] * x_c[etaPos[j]]   (one warp per eta i)
+template <int NRHS>
+__global__ void pfi_mu_kernel(DeviceModel d, const double *__restrict__ x, int xstride,
+                              bool checkState)
+{
+  if (checkState && !iter_active(d.st))
+    return;
+  const int t = d.st->numEtas;
+  const int lane = threadIdx.x & 31;
+  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (i >= t)
+    return;
+  const double *grow = d.Ginv + (size_t)i * d.tmax;
+  double acc[NRHS];
+#pragma unroll
+  for (int c = 0; c < NRHS; c++)
+    acc[c] = 0.0;
+  for (int j = lane; j <= i; j += 32) {
+    double g = grow[j];
+    int p = d.etaPos[j];
+#pragma unroll
+    for (int c = 0; c < NRHS; c++)
+      acc[c] = fma(g, x[(size_t)c * xstride + p], acc[c]);
+  }
+#pragma unroll
+  for (int c = 0; c < NRHS; c++)
+    acc[c] = warp_sum(acc[c]);
+  if (lane == 0)
+    for (int c = 0; c < NRHS; c++)
+      d.mu[(size_t)c * d.tmax + i] = acc[c];
+}
+
+// x_c[p] -= sum_{i<t} W[p][i] * mu_c[i]   (one warp per position)
+template <int NRHS>
+__global__ void pfi_apply_kernel(DeviceModel d, double *__restrict__ x, int xstride,
+                                 bool checkState)
+{
+  if (checkState && !iter_active(d.st))
+    return;
+  const int t = d.st->numEtas;
+  if (t == 0)
+    return;
+  const int lane = threadIdx.x & 31;
+  const int warpsPerBlock = blockDim.x >> 5;
+  for (int p = blockIdx.x * warpsPerBlock + (threadIdx.x >> 5); p < d.m;
+       p += gridDim.x * warpsPerBlock) {
+    const double *wrow = d.W + (size_t)p * d.tmax;
+    double acc[NRHS];
+#pragma unroll
+    for (int c = 0; c < NRHS; c++)
+      acc[c] = 0.0;
+    for (int i = lane; i < t; i += 32) {
+      double w = wrow[i];
+#pragma unroll
+      for (int c = 0; c < NRHS; c++)
+        acc[c] = fma(w, d.mu[(size_t)c * d.tmax + i], acc[c]);
+    }
+#pragma unroll
+    for (int c = 0; c < NRHS; c++)
+      acc[c] = warp_sum(acc[c]);
+    if (lane == 0)
+      for (int c = 0; c < NRHS; c++)
+        x[(size_t)c * xstride + p] -= acc[c];
+  }
+}
+
+template <int NRHS>
+static void ftran_impl(const DeviceModel &d, double *b, bool applyEtas, bool checkState,
+                       cudaStream_t s)
+{
+  const int m = d.m, k = d.k;
+  if (k > 0) {
+    gather_nucleus_kernel<<<(d.ldk + 255) / 256, 256, 0, s>>>(d, b, m, d.ywork + (size_t)3 * d.ldk,
+                                                          NRHS, checkState);
+    int blocks = (k + 7) / 8;
+    gemv_rows_kernel<NRHS><<<blocks, 256, 0, s>>>(d.Ninv, k, d.ldk, d.ywork + (size_t)3 * d.ldk,
+                                                  d.ywork, d.ldk, nullptr, d.st, checkState);
+  }
+  ftran_spread_kernel<NRHS><<<(m * 8 + 255) / 256, 256, 0, s>>>(d, b, m, d.ywork, checkState);
+  if (applyEtas) {
+    pfi_mu_kernel<NRHS><<<(d.tmax + 7) / 8, 256, 0, s>>>(d, b, m, checkState);
+    int blocks = (m + 7) / 8;
+    if (blocks > 148 * 8)
+      blocks = 148 * 8;
+    pfi_apply_kernel<NRHS><<<blocks, 256, 0, s>>>(d, b, m, checkState);
+  }
+}
+
+// FTRAN of the first nrhs vectors of d.rhs3 (in place).
+void launch_ftran(const DeviceModel &d, int nrhs, bool applyEtas, cudaStream_t s)
+{
+  if (nrhs == 1)
+    ftran_impl<1>(d, d.rhs3, applyEtas, applyEtas, s);
+  else if (nrhs == 2)
+    ftran_impl<2>(d, d.rhs3, applyEtas, applyEtas, s);
+  else
+    ftran_impl<3>(d, d.rhs3, applyEtas, applyEtas, s);
+}
+
+// ---------------------------------------------------------------------------------------
+// out[j] = scale * sum_{i>=j, i<t} Ginv[i][j] * W[row][i]   for j < t
+//   mode 0 : nu (BTRAN eta transposes), vec = W[pivot row][:]
+//   mode 1 : new row t of Ginv = -out / alphaCol, diagonal 1/alphaCol, vec = W[pivot row][:]
+//   mode 2 : nu for a general BTRAN, vec = d.mu (the t dot products W_i . v)
+__global__ void __launch_bounds__(256) eta_rowvec_kernel(DeviceModel d, int mode, bool checkState)
+{
+  if (checkState && !iter_active(d.st))
+    return;
+  const int t = d.st->numEtas;
+  const int j0 = blockIdx.x * 32;
+  if (j0 >= t && !(mode == 1 && blockIdx.x == 0))
+    return;
+  const int r = d.st->pivotRow;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int j = j0 + lane;
+  __shared__ double part[8][33];
+  const double *wrow = mode == 2 ? d.mu : d.W + (size_t)r * d.tmax;
+  double acc = 0.0;
+  if (j < t)
+    for (int i = j0 + warp; i < t; i += 8) // rows below j0 contribute nothing (lower triangular)
+      if (i >= j)
+        acc = fma(d.Ginv[(size_t)i * d.tmax + j], wrow[i], acc);
+  part[warp][lane] = acc;
+  __syncthreads();
+  if (warp == 0) {
+    double s = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; w++)
+      s += part[w][lane];
+    if (mode != 1) {
+      if (j < t)
+        d.nu[j] = s;
+    } else {
+      const double dinv = 1.0 / d.st->alphaCol;
+      if (j < t)
+        d.Ginv[(size_t)t * d.tmax + j] = -s * dinv;
+      if (blockIdx.x == 0 && lane == 0)
+        d.Ginv[(size_t)t * d.tmax + t] = dinv;
+    }
+  }
+}
+void launch_eta_rowvec(const DeviceModel &d, int mode, bool checkState, cudaStream_t s)
+{
+  eta_rowvec_kernel<<<(d.tmax + 31) / 32, 256, 0, s>>>(d, mode, checkState);
+}
+
+// u = e_r - sum_j e_{p_j} nu_j ; rho_C = -u_C    (thread per position)
+__global__ void btran_build_u_kernel(DeviceModel d, double *rhoOut, bool checkState,
+                                     const double *vin)
+{
+  if (checkState && !iter_active(d.st))
+    return;
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= d.m)
+    return;
+  const int r = d.st->pivotRow;
+  double u = vin ? vin[p] : ((p == r) ? 1.0 : 0.0);
+  if (d.st->numEtas > 0) {
+    // etas that pivoted on this position, newest first (fixed order => deterministic sum)
+    double sum = 0.0;
+    for (int e = d.etaLastOfPos[p]; e >= 0; e = d.etaPrevSame[e])
+      sum += d.nu[e];
+    u -= sum;
+  }
+  d.uwork[p] = u;
+  if (d.posToNuc[p] < 0)
+    rhoOut[p] = -u;
+}
+
+// rho_C = -u_C for a dense input u (already in d.uwork)
+__global__ void btran_dense_c_kernel(DeviceModel d, double *__restrict__ rhoOut)
+{
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= d.m)
+    return;
+  if (d.posToNuc[p] < 0)
+    rhoOut[p] = -d.uwork[p];
+}
+
+// s_j = u[nucRow[j]] + sum_{rows i in C of column nucCol[j]} a_ij u[i]   (warp per nucleus col)
+__global__ void btran_s_kernel(DeviceModel d, bool checkState)
+{
+  if (checkState && !iter_active(d.st))
+    return;
+  const int lane = threadIdx.x & 31;
+  const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (j >= d.k)
+    return;
+  const int col = d.nucCol[j];
+  double acc = 0.0;
+  for (int e = d.colStart[col] + lane; e < d.colStart[col + 1]; e += 32) {
+    int i = d.rowIdx[e];
+    if (d.posToNuc[i] < 0)
+      acc = fma(d.val[e], d.uwork[i], acc);
+  }
+  acc = warp_sum(acc);
+  if (lane == 0)
+    d.swork[j] = acc + d.uwork[d.nucRow[j]];
+  // zero the padding once so the GEMV can run over ldk
+  if (j == 0 && lane == 0)
+    for (int q = d.k; q < d.ldk; q++)
+      d.swork[q] = 0.0;
+}
+
+static void btran_tail(const DeviceModel &d, double *rhoOut, bool checkState, cudaStream_t s)
+{
+  if (d.k > 0) {
+    btran_s_kernel<<<(d.k + 7) / 8, 256, 0, s>>>(d, checkState);
+    gemv_rows_kernel<1><<<(d.k + 7) / 8, 256, 0, s>>>(d.NinvT, d.k, d.ldk, d.swork, rhoOut, d.m,
+                                                      d.nucRow, d.st, checkState);
+  }
+}
+
+// rho = B_t^-T e_r with r = st->pivotRow ; result in d.rho
+void launch_btran_unit(const DeviceModel &d, bool checkState, cudaStream_t s)
+{
+  launch_eta_rowvec(d, 0, checkState, s); // no-op when numEtas == 0
+  btran_build_u_kernel<<<(d.m + 255) / 256, 256, 0, s>>>(d, d.rho, checkState, nullptr);
+  btran_tail(d, d.rho, checkState, s);
+}
+
+// s_i = W[:,i] . v   (one warp per eta; general BTRAN only -- the simplex BTRAN starts from a
+// unit vector and reads a row of W instead)
+__global__ void eta_dot_kernel(DeviceModel d, const double *__restrict__ v)
+{
+  const int t = d.st->numEtas;
+  const int lane = threadIdx.x & 31;
+  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (i >= t)
+    return;
+  double acc = 0.0;
+  for (int p = lane; p < d.m; p += 32)
+    acc = fma(d.W[(size_t)p * d.tmax + i], v[p], acc);
+  acc = warp_sum(acc);
+  if (lane == 0)
+    d.mu[i] = acc;
+}
+
+// vec = B_t^-T vec for a dense vector (computeDuals right after a refactorization uses
+// applyEtas=false; the general form backs the updateColumnTranspose entry point)
+void launch_btran_dense(const DeviceModel &d, double *vec, bool applyEtas, cudaStream_t s)
+{
+  if (applyEtas) {
+    eta_dot_kernel<<<(d.tmax + 7) / 8, 256, 0, s>>>(d, vec);
+    launch_eta_rowvec(d, 2, false, s);
+    btran_build_u_kernel<<<(d.m + 255) / 256, 256, 0, s>>>(d, vec, false, vec);
+  } else {
+    cudaMemcpyAsync(d.uwork, vec, sizeof(double) * d.m, cudaMemcpyDeviceToDevice, s);
+    btran_dense_c_kernel<<<(d.m + 255) / 256, 256, 0, s>>>(d, vec);
+  }
+  btran_tail(d, vec, false, s);
+}
+
+// FTRAN on an arbitrary device buffer of nrhs vectors (stride m), optional etas, no state check
+void launch_ftran_buffer(const DeviceModel &d, double *buf, int nrhs, bool applyEtas, cudaStream_t s)
+{
+  if (nrhs == 1)
+    ftran_impl<1>(d, buf, applyEtas, false, s);
+  else if (nrhs == 2)
+    ftran_impl<2>(d, buf, applyEtas, false, s);
+  else
+    ftran_impl<3>(d, buf, applyEtas, false, s);
+}
+
+} // namespace clpb

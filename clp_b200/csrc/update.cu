@@ -1,0 +1,652 @@
+// update.cu -- CHUZR, dual/primal/weight updates and the refresh (recompute-from-scratch) kernels.
+//
+// Replaces, with device-resident state,
+//   ClpDualRowSteepest::pivotRow            /root/reference/src/ClpDualRowSteepest.cpp:179
+//   ClpSimplexDual::updateDualsInDual       src/ClpSimplexDual.cpp:2430   (+ flipBounds :6345)
+//   ClpDualRowSteepest::updateWeights       src/ClpDualRowSteepest.cpp:375 (recurrence :501-538)
+//   ClpDualRowSteepest::updatePrimalSolution src/ClpDualRowSteepest.cpp:630
+//   ClpSimplex::housekeeping                src/ClpSimplex.cpp:2065 (status / pivotVariable swap)
+//   ClpSimplexDual::changeBounds            src/ClpSimplexDual.cpp:3148 (fake bounds)
+//   ClpSimplex::computePrimals / computeDuals  src/ClpSimplex.cpp:914 / :1164
+// All reductions are order independent (packed-key atomicMax/Min, integer atomics) or done
+// in a fixed order, so replicated ranks of a column-sharded run stay bit-identical.
+#include "engine.cuh"
+
+namespace clpb {
+
+__device__ __forceinline__ bool iter_active(const IterState *st) { return st->stop == 0; }
+
+// ------------------------------------------------------------------ CHUZR
+__global__ void chuzr_kernel(DeviceModel d)
+{
+  if (!iter_active(d.st))
+    return;
+  const double tol = d.primalTolerance;
+  unsigned long long best = 0ull;
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < d.m; p += gridDim.x * blockDim.x) {
+    const int seq = d.pivotVariable[p];
+    const double v = d.sol[seq];
+    double inf = 0.0;
+    const double lo = d.lower[seq], up = d.upper[seq];
+    if (v < lo - tol)
+      inf = lo - v;
+    else if (v > up + tol)
+      inf = v - up;
+    if (inf > 0.0) {
+      double w = d.weights[p];
+      double score = inf * inf / w;
+      unsigned long long key =
+          ((unsigned long long)__double_as_longlong(score) & ~0xFFFFFull) | (unsigned long long)(0xFFFFF - p);
+      best = max(best, key);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+    best = max(best, __shfl_xor_sync(0xffffffffu, best, o));
+  if ((threadIdx.x & 31) == 0 && best != 0ull)
+    atomicMax(&d.st->chuzrKey, best);
+}
+
+__global__ void chuzr_finish_kernel(DeviceModel d)
+{
+  IterState *st = d.st;
+  if (!iter_active(st))
+    return;
+  if (st->numEtas >= d.tmax) {
+    st->stop = STOP_ETAS_FULL;
+    return;
+  }
+  const unsigned long long key = st->chuzrKey;
+  st->chuzrKey = 0ull;
+  if (key == 0ull) {
+    st->stop = STOP_NO_ROW;
+    return;
+  }
+  const int r = 0xFFFFF - (int)(key & 0xFFFFFull);
+  const int seq = d.pivotVariable[r];
+  const double v = d.sol[seq];
+  st->pivotRow = r;
+  st->seqOut = seq;
+  if (v < d.lower[seq]) {
+    st->sigma = -1;
+    st->infeas = d.lower[seq] - v;
+  } else {
+    st->sigma = +1;
+    st->infeas = v - d.upper[seq];
+  }
+  st->numFlips = 0;
+  st->seqIn = -1;
+}
+
+void launch_chuzr(const DeviceModel &d, cudaStream_t s)
+{
+  int blocks = (d.m + 255) / 256;
+  if (blocks > 148 * 4)
+    blocks = 148 * 4;
+  chuzr_kernel<<<blocks, 256, 0, s>>>(d);
+  chuzr_finish_kernel<<<1, 1, 0, s>>>(d);
+}
+
+// ------------------------------------------------------------------ dual update + flips
+// dj -= thetaDual * sigma * alpha over the pivot row; variables whose dj changes sign flip to
+// the other bound when boxed, otherwise their cost is shifted (ClpSimplexDual.cpp:4705-4772).
+// flipFlag[j] (stored in d.fake's neighbour array, see engine.cu) marks flipped variables.
+__global__ void dual_update_kernel(DeviceModel d, unsigned char *__restrict__ flipFlag)
+{
+  if (!iter_active(d.st))
+    return;
+  const double theta = d.st->thetaDual;
+  const int sigma = d.st->sigma;
+  const int seqIn = d.st->seqIn;
+  const double tol = d.dualTolerance;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < d.nm; j += gridDim.x * blockDim.x) {
+    unsigned char flag = 0;
+    const double alpha = d.alphaRow[j];
+    if (alpha != 0.0 && j != seqIn) {
+      const unsigned char st = d.status[j];
+      if (st != basic && st != isFixed) {
+        double dnew = d.dj[j] - theta * (sigma * alpha);
+        bool wrong = (st == atLowerBound && dnew < -tol) || (st == atUpperBound && dnew > tol);
+        if (wrong) {
+          const double lo = d.lower[j], up = d.upper[j];
+          if (up - lo < 1.0e29) {
+            if (st == atLowerBound) {
+              d.status[j] = atUpperBound;
+              d.sol[j] = up;
+            } else {
+              d.status[j] = atLowerBound;
+              d.sol[j] = lo;
+            }
+            flag = 1;
+          } else {
+            d.cost[j] -= dnew;
+            dnew = 0.0;
+            atomicAdd(&d.st->costShifts, 1);
+          }
+        } else if ((st == isFree || st == superBasic) && fabs(dnew) > tol) {
+          d.cost[j] -= dnew;
+          dnew = 0.0;
+          atomicAdd(&d.st->costShifts, 1);
+        }
+        d.dj[j] = dnew;
+      }
+    }
+    flipFlag[j] = flag;
+  }
+}
+
+// single CTA: ordered compaction of flipFlag into flipList (ascending sequence => fixed order)
+__global__ void __launch_bounds__(1024) flip_collect_kernel(DeviceModel d,
+                                                           const unsigned char *__restrict__ flipFlag)
+{
+  if (!iter_active(d.st))
+    return;
+  __shared__ int warpCount[32];
+  __shared__ int base;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0)
+    base = 0;
+  __syncthreads();
+  for (int start = 0; start < d.nm; start += 1024 * 8) {
+    // each thread owns 8 consecutive flags
+    const int j0 = start + tid * 8;
+    int cnt = 0;
+    unsigned char f[8];
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+      f[q] = (j0 + q < d.nm) ? flipFlag[j0 + q] : 0;
+      cnt += f[q];
+    }
+    int inc = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o)
+        inc += t;
+    }
+    if (lane == 31)
+      warpCount[warp] = inc;
+    __syncthreads();
+    int off = base + inc - cnt;
+    for (int w = 0; w < warp; w++)
+      off += warpCount[w];
+#pragma unroll
+    for (int q = 0; q < 8; q++)
+      if (f[q])
+        d.flipList[off++] = j0 + q;
+    __syncthreads();
+    if (tid == 1023) {
+      int tot = 0;
+      for (int w = 0; w < 32; w++)
+        tot += warpCount[w];
+      base += tot;
+    }
+    __syncthreads();
+  }
+  if (tid == 0)
+    d.st->numFlips = base;
+}
+
+// rhs3[0] = a_q (entering column of [A|-I]); rhs3[1] = rho; rhs3[2] = -sum_flips a_j * delta_j.
+// Each thread owns one row and scans the (few) columns involved in ascending flip order, so
+// the sums are formed in a fixed order without atomics.
+__global__ void __launch_bounds__(256) build_rhs3_kernel(DeviceModel d)
+{
+  if (!iter_active(d.st))
+    return;
+  __shared__ int sRow[256];
+  __shared__ double sVal[256];
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = row < d.m;
+  const int q = d.st->seqIn;
+  double aq = 0.0, fl = 0.0;
+  // entering column
+  if (q >= d.n) {
+    if (live && row == q - d.n)
+      aq = -1.0;
+  } else {
+    const int e0 = d.colStart[q], e1 = d.colStart[q + 1];
+    for (int c0 = e0; c0 < e1; c0 += 256) {
+      int e = c0 + threadIdx.x;
+      sRow[threadIdx.x] = e < e1 ? d.rowIdx[e] : -1;
+      sVal[threadIdx.x] = e < e1 ? d.val[e] : 0.0;
+      __syncthreads();
+      int cnt = min(256, e1 - c0);
+      for (int t = 0; t < cnt; t++)
+        if (sRow[t] == row)
+          aq = sVal[t];
+      __syncthreads();
+    }
+  }
+  // flipped columns
+  const int nf = d.st->numFlips;
+  for (int f = 0; f < nf; f++) {
+    const int j = d.flipList[f];
+    const double range = d.upper[j] - d.lower[j];
+    const double delta = d.status[j] == atUpperBound ? range : -range;
+    if (j >= d.n) {
+      if (live && row == j - d.n)
+        fl += delta;
+      continue;
+    }
+    const int e0 = d.colStart[j], e1 = d.colStart[j + 1];
+    for (int c0 = e0; c0 < e1; c0 += 256) {
+      int e = c0 + threadIdx.x;
+      sRow[threadIdx.x] = e < e1 ? d.rowIdx[e] : -1;
+      sVal[threadIdx.x] = e < e1 ? d.val[e] : 0.0;
+      __syncthreads();
+      int cnt = min(256, e1 - c0);
+      for (int t = 0; t < cnt; t++)
+        if (sRow[t] == row)
+          fl -= delta * sVal[t];
+      __syncthreads();
+    }
+  }
+  if (live) {
+    d.rhs3[row] = aq;
+    d.rhs3[(size_t)d.m + row] = d.rho[row];
+    d.rhs3[(size_t)2 * d.m + row] = fl;
+  }
+}
+
+void launch_dual_update_and_flips(const DeviceModel &d, unsigned char *flipFlag, cudaStream_t s)
+{
+  int blocks = (d.nm + 255) / 256;
+  if (blocks > 148 * 8)
+    blocks = 148 * 8;
+  dual_update_kernel<<<blocks, 256, 0, s>>>(d, flipFlag);
+  flip_collect_kernel<<<1, 1024, 0, s>>>(d, flipFlag);
+  build_rhs3_kernel<<<(d.m + 255) / 256, 256, 0, s>>>(d);
+}
+
+// ------------------------------------------------------------------ after the FTRANs
+// accuracy gate (ClpSimplexDual.cpp:1447-1501) and primal step length
+__global__ void pivot_scalars_kernel(DeviceModel d)
+{
+  IterState *st = d.st;
+  if (!iter_active(st))
+    return;
+  const int r = st->pivotRow;
+  const double ac = d.rhs3[r];
+  st->alphaCol = ac;
+  const double ar = st->alphaRow;
+  const double err = fabs(ar - ac) / (1.0 + fabs(ac));
+  const bool bad = !(fabs(ac) >= 1.0e-9) || !(err <= 1.0e-6);
+  if (bad) {
+    if (st->numEtas > 0) {
+      st->stop = STOP_INACCURATE; // the host refactorizes, recomputes and retries
+      return;
+    }
+    if (!(fabs(ac) >= 1.0e-11) || !(err <= 1.0e-3)) {
+      st->stop = STOP_TINY_PIVOT; // fresh factors and still no usable pivot
+      return;
+    }
+  }
+  const int seqOut = st->seqOut;
+  double valueOut = d.sol[seqOut];
+  if (st->numFlips > 0)
+    valueOut += d.rhs3[(size_t)2 * d.m + r];
+  const double bound = st->sigma < 0 ? d.lower[seqOut] : d.upper[seqOut];
+  st->thetaPrimal = (valueOut - bound) / ac;
+}
+
+// x_B, DSE weights and the new eta column, one thread per position
+__global__ void pivot_update_kernel(DeviceModel d)
+{
+  const IterState *st = d.st;
+  if (!iter_active(st))
+    return;
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= d.m)
+    return;
+  const int r = st->pivotRow;
+  const int t = st->numEtas;
+  const double a = d.rhs3[p];
+  const double alphaR = st->alphaCol;
+  // eta column W_t = alpha_q with (alpha_r - 1) on the pivot position
+  d.W[(size_t)p * d.tmax + t] = (p == r) ? a - 1.0 : a;
+  const int seq = d.pivotVariable[p];
+  if (p != r) {
+    double x = d.sol[seq];
+    if (st->numFlips > 0)
+      x += d.rhs3[(size_t)2 * d.m + p];
+    x -= st->thetaPrimal * a;
+    d.sol[seq] = x;
+    if (a != 0.0) {
+      // w_i += (a_i/a_r) * ((a_i/a_r) * w_r - 2 tau_i)   clipped at DEVEX_TRY_NORM
+      const double ratio = a / alphaR;
+      double w = d.weights[p] + ratio * (ratio * st->rhoNorm2 - 2.0 * d.rhs3[(size_t)d.m + p]);
+      d.weights[p] = w < kDevexTryNorm ? kDevexTryNorm : w;
+    }
+  } else {
+    double w = st->rhoNorm2 / (alphaR * alphaR);
+    d.weights[p] = w < kDevexTryNorm ? kDevexTryNorm : w;
+  }
+}
+
+// status / pivotVariable swap and per-iteration record (ClpSimplex::housekeeping)
+__global__ void pivot_fixup_kernel(DeviceModel d)
+{
+  IterState *st = d.st;
+  IterRecord &rec = d.rec[st->iterations % d.recCap];
+  if (!iter_active(st)) {
+    rec.stop = st->stop;
+    return;
+  }
+  const int r = st->pivotRow, q = st->seqIn, out = st->seqOut;
+  const double bound = st->sigma < 0 ? d.lower[out] : d.upper[out];
+  d.sol[q] += st->thetaPrimal;
+  d.sol[out] = bound;
+  d.dj[q] = 0.0;
+  d.dj[out] = -st->sigma * st->thetaDual;
+  d.status[q] = basic;
+  d.lower[q] = d.lowerTrue[q];
+  d.upper[q] = d.upperTrue[q];
+  d.fake[q] = 0;
+  d.status[out] = (d.lower[out] == d.upper[out]) ? isFixed
+                  : (st->sigma < 0 ? atLowerBound : atUpperBound);
+  d.pivotVariable[r] = q;
+  const int t = st->numEtas;
+  d.etaPos[t] = r;
+  d.etaPrevSame[t] = d.etaLastOfPos[r];
+  d.etaLastOfPos[r] = t;
+  st->numEtas = t + 1;
+  rec.stop = 0;
+  rec.pivotRow = r;
+  rec.seqIn = q;
+  rec.seqOut = out;
+  rec.sigma = st->sigma;
+  rec.numFlips = st->numFlips;
+  rec.thetaDual = st->thetaDual;
+  rec.thetaPrimal = st->thetaPrimal;
+  rec.alphaRow = st->alphaRow;
+  rec.alphaCol = st->alphaCol;
+  rec.infeas = st->infeas;
+  st->iterations += 1;
+}
+
+void launch_pivot_updates(const DeviceModel &d, cudaStream_t s)
+{
+  pivot_scalars_kernel<<<1, 1, 0, s>>>(d);
+  launch_eta_rowvec(d, 1, true, s); // new row of Ginv (reads old W[r][:], alphaCol)
+  pivot_update_kernel<<<(d.m + 255) / 256, 256, 0, s>>>(d);
+  pivot_fixup_kernel<<<1, 1, 0, s>>>(d);
+}
+
+// ------------------------------------------------------------------ refresh kernels
+// choose a dual feasible bound for every nonbasic variable, fake bounds of width dualBound
+// where the needed bound is infinite (ClpSimplexDual::changeBounds :3148)
+__global__ void make_dual_feasible_kernel(DeviceModel d, double dualBound, int *counters)
+{
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= d.nm)
+    return;
+  double lo = d.lowerTrue[j], up = d.upperTrue[j];
+  unsigned char st = d.status[j];
+  if (st == basic) {
+    d.lower[j] = lo;
+    d.upper[j] = up;
+    d.fake[j] = 0;
+    return;
+  }
+  const double dj = d.dj[j];
+  const double tol = d.dualTolerance;
+  const double old = d.sol[j];
+  unsigned char f = 0;
+  double x;
+  if (lo == up) {
+    st = isFixed;
+    x = lo;
+  } else if (dj > tol) {
+    if (lo <= -kInf) {
+      lo = (up < kInf ? up : 0.0) - dualBound;
+      f = 1;
+    }
+    st = atLowerBound;
+    x = lo;
+  } else if (dj < -tol) {
+    if (up >= kInf) {
+      up = (lo > -kInf ? lo : 0.0) + dualBound;
+      f = 2;
+    }
+    st = atUpperBound;
+    x = up;
+  } else {
+    if (st == atUpperBound && up < kInf && !(d.fake[j] & 2)) {
+      x = up;
+    } else if (lo > -kInf) {
+      st = atLowerBound;
+      x = lo;
+    } else if (up < kInf) {
+      st = atUpperBound;
+      x = up;
+    } else {
+      st = isFree;
+      x = 0.0;
+    }
+  }
+  d.lower[j] = lo;
+  d.upper[j] = up;
+  d.fake[j] = f;
+  d.status[j] = st;
+  d.sol[j] = x;
+  if (f)
+    atomicAdd(counters + 0, 1);
+  if (x != old)
+    atomicAdd(counters + 1, 1);
+}
+
+// xn[j] = nonbasic structural value (0 for basic)
+__global__ void nonbasic_x_kernel(DeviceModel d, double *__restrict__ xn)
+{
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < d.n)
+    xn[j] = d.status[j] == basic ? 0.0 : d.sol[j];
+}
+// rhs[i] += value of nonbasic row variable
+__global__ void primal_rhs_slack_kernel(DeviceModel d, double *__restrict__ rhs)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < d.m && d.status[d.n + i] != basic)
+    rhs[i] += d.sol[d.n + i];
+}
+// sol[pivotVariable[p]] = x[p]
+__global__ void scatter_basic_kernel(DeviceModel d, const double *__restrict__ x)
+{
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < d.m)
+    d.sol[d.pivotVariable[p]] = x[p];
+}
+// cB[p] = cost[pivotVariable[p]]
+__global__ void gather_basic_cost_kernel(DeviceModel d, double *__restrict__ cb)
+{
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < d.m)
+    cb[p] = d.cost[d.pivotVariable[p]];
+}
+// dj = cost - z for columns, cost + pi for rows; 0 for basics
+__global__ void reduced_cost_kernel(DeviceModel d, const double *__restrict__ z,
+                                    const double *__restrict__ pi)
+{
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= d.nm)
+    return;
+  double v = 0.0;
+  if (d.status[j] != basic)
+    v = j < d.n ? d.cost[j] - z[j] : d.cost[j] + pi[j - d.n];
+  d.dj[j] = v;
+}
+
+// out[0] = sum costTrue*sol (fixed order, single CTA) ; out[1] = sum primal infeasibility of basics
+__global__ void __launch_bounds__(1024) objective_kernel(DeviceModel d, double *out)
+{
+  __shared__ double s1[32], s2[32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  double a = 0.0, b = 0.0;
+  for (int j = tid; j < d.nm; j += 1024)
+    a = fma(d.costTrue[j], d.sol[j], a);
+  for (int p = tid; p < d.m; p += 1024) {
+    int seq = d.pivotVariable[p];
+    double v = d.sol[seq];
+    if (v < d.lower[seq] - d.primalTolerance)
+      b += d.lower[seq] - v;
+    else if (v > d.upper[seq] + d.primalTolerance)
+      b += v - d.upper[seq];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, o);
+    b += __shfl_xor_sync(0xffffffffu, b, o);
+  }
+  if (lane == 0) {
+    s1[warp] = a;
+    s2[warp] = b;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    double x = 0.0, y = 0.0;
+    for (int w = 0; w < 32; w++) {
+      x += s1[w];
+      y += s2[w];
+    }
+    out[0] = x;
+    out[1] = y;
+  }
+}
+
+// weightsNew[p] = srcPos[p] >= 0 ? weightsOld[srcPos[p]] : 1
+__global__ void permute_weights_kernel(const double *__restrict__ wOld, double *__restrict__ wNew,
+                                       const int *__restrict__ srcPos, int m)
+{
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < m)
+    wNew[p] = srcPos[p] >= 0 ? wOld[srcPos[p]] : 1.0;
+}
+
+// dense nucleus gather: N[i][j] (row-major k x ld) = A[nucRow[i], nucCol[j]]
+__global__ void gather_nucleus_matrix_kernel(DeviceModel d, double *__restrict__ N, int ld)
+{
+  const int lane = threadIdx.x & 31;
+  const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (j >= d.k)
+    return;
+  const int col = d.nucCol[j];
+  for (int e = d.colStart[col] + lane; e < d.colStart[col + 1]; e += 32) {
+    int ni = d.posToNuc[d.rowIdx[e]];
+    if (ni >= 0)
+      N[(size_t)ni * ld + j] = d.val[e];
+  }
+}
+
+__global__ void count_fake_kernel(DeviceModel d, int *counter)
+{
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < d.nm && d.fake[j] && d.status[j] != basic)
+    atomicAdd(counter, 1);
+}
+void launch_count_fake(const DeviceModel &d, int *counter, cudaStream_t s)
+{
+  count_fake_kernel<<<(d.nm + 255) / 256, 256, 0, s>>>(d, counter);
+}
+
+// out[m] = column seq of [A | -I]   (ClpPackedMatrix::unpack :4803)
+__global__ void unpack_column_kernel(DeviceModel d, int seq, double *__restrict__ out)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (seq >= d.n) {
+    if (i < d.m)
+      out[i] = (i == seq - d.n) ? -1.0 : 0.0;
+    return;
+  }
+  // zero fill then scatter by the first block (columns are short)
+  if (i < d.m)
+    out[i] = 0.0;
+}
+__global__ void unpack_scatter_kernel(DeviceModel d, int seq, double *__restrict__ out)
+{
+  int e = d.colStart[seq] + blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < d.colStart[seq + 1])
+    out[d.rowIdx[e]] = d.val[e];
+}
+void launch_unpack_column(const DeviceModel &d, int seq, double *out, cudaStream_t s)
+{
+  unpack_column_kernel<<<(d.m + 255) / 256, 256, 0, s>>>(d, seq, out);
+  if (seq < d.n)
+    unpack_scatter_kernel<<<64, 256, 0, s>>>(d, seq, out); // columns up to 16384 entries
+}
+
+// Product-form update outside the simplex loop (replaceColumn entry point / parity tests):
+// rhs3[0] holds B^-1 a_q ; append it as eta for position pivotRow.
+__global__ void eta_append_prepare_kernel(DeviceModel d, int pivotRow)
+{
+  d.st->pivotRow = pivotRow;
+  d.st->alphaCol = d.rhs3[pivotRow];
+}
+__global__ void eta_append_column_kernel(DeviceModel d)
+{
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= d.m)
+    return;
+  const int r = d.st->pivotRow, t = d.st->numEtas;
+  const double a = d.rhs3[p];
+  d.W[(size_t)p * d.tmax + t] = (p == r) ? a - 1.0 : a;
+}
+__global__ void eta_append_finish_kernel(DeviceModel d, int seqIn)
+{
+  IterState *st = d.st;
+  const int r = st->pivotRow, t = st->numEtas;
+  d.etaPos[t] = r;
+  d.etaPrevSame[t] = d.etaLastOfPos[r];
+  d.etaLastOfPos[r] = t;
+  st->numEtas = t + 1;
+  const int out = d.pivotVariable[r];
+  d.status[out] = atLowerBound;
+  d.status[seqIn] = basic;
+  d.pivotVariable[r] = seqIn;
+}
+void launch_eta_append_test(const DeviceModel &d, int pivotRow, int seqIn, cudaStream_t s)
+{
+  eta_append_prepare_kernel<<<1, 1, 0, s>>>(d, pivotRow);
+  launch_eta_rowvec(d, 1, false, s);
+  eta_append_column_kernel<<<(d.m + 255) / 256, 256, 0, s>>>(d);
+  eta_append_finish_kernel<<<1, 1, 0, s>>>(d, seqIn);
+}
+
+// ---- host wrappers used by engine.cu
+void launch_make_dual_feasible(const DeviceModel &d, double dualBound, int *counters, cudaStream_t s)
+{
+  make_dual_feasible_kernel<<<(d.nm + 255) / 256, 256, 0, s>>>(d, dualBound, counters);
+}
+void launch_compute_primals(const DeviceModel &d, double *xn, double *rhs, cudaStream_t s)
+{
+  // rhs = -A x_N + (nonbasic row values) ; x_B = B0^-1 rhs   (no etas: fresh factorization)
+  if (d.n > 0)
+    nonbasic_x_kernel<<<(d.n + 255) / 256, 256, 0, s>>>(d, xn);
+  launch_times_rows(d, xn, rhs, -1.0, s);
+  primal_rhs_slack_kernel<<<(d.m + 255) / 256, 256, 0, s>>>(d, rhs);
+  launch_ftran_buffer(d, rhs, 1, false, s);
+  scatter_basic_kernel<<<(d.m + 255) / 256, 256, 0, s>>>(d, rhs);
+}
+void launch_compute_duals(const DeviceModel &d, double *pi, double *z, cudaStream_t s)
+{
+  gather_basic_cost_kernel<<<(d.m + 255) / 256, 256, 0, s>>>(d, pi);
+  launch_btran_dense(d, pi, false, s);
+  launch_transpose_times(d, pi, z, 1.0, s);
+  reduced_cost_kernel<<<(d.nm + 255) / 256, 256, 0, s>>>(d, z, pi);
+}
+void launch_objective(const DeviceModel &d, double *out, cudaStream_t s)
+{
+  objective_kernel<<<1, 1024, 0, s>>>(d, out);
+}
+void launch_permute_weights(const double *wOld, double *wNew, const int *srcPos, int m,
+                            cudaStream_t s)
+{
+  permute_weights_kernel<<<(m + 255) / 256, 256, 0, s>>>(wOld, wNew, srcPos, m);
+}
+void launch_gather_nucleus_matrix(const DeviceModel &d, double *N, int ld, cudaStream_t s)
+{
+  if (d.k > 0)
+    gather_nucleus_matrix_kernel<<<(d.k + 7) / 8, 256, 0, s>>>(d, N, ld);
+}
+
+} // namespace clpb

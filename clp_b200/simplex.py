@@ -1,0 +1,224 @@
+"""Host-side mirror of the reference's ClpSimplex interface for the dual path.
+
+Method names, argument meaning and status codes follow ClpSimplex / ClpModel
+(/root/reference/src/ClpSimplex.hpp, ClpModel.hpp): ``loadProblem``, ``readMps``, ``dual``,
+``status`` (0 optimal, 1 primal infeasible, 2 dual infeasible, 3 stopped, 4 errors),
+``objectiveValue``, ``primalColumnSolution`` ... Everything computational happens behind the
+C ABI of include/clp_b200.h in hand-written sm_100a CUDA; this module only marshals arrays.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+
+from . import _capi
+from ._capi import c_double_p, c_int_p, c_ubyte_p
+
+
+def _dp(a):
+    return a.ctypes.data_as(c_double_p)
+
+
+def _ip(a):
+    return a.ctypes.data_as(c_int_p)
+
+
+def _up(a):
+    return a.ctypes.data_as(c_ubyte_p)
+
+
+class NoDeviceError(RuntimeError):
+    pass
+
+
+class ClpSimplex:
+    # ClpSimplex::Status (ClpSimplex.hpp:119-126)
+    isFree, basic, atUpperBound, atLowerBound, superBasic, isFixed = range(6)
+
+    def __init__(self):
+        self._L = _capi.lib()
+        self._h = self._L.Clpb_newModel()
+        self._keep = None
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            self._L.Clpb_deleteModel(h)
+            self._h = None
+
+    # ---- ClpModel::loadProblem (column-major matrix without gaps) ----
+    def loadProblem(self, numberColumns, numberRows, start, index, value, collb=None, colub=None,
+                    obj=None, rowlb=None, rowub=None):
+        c = lambda a, t: None if a is None else np.ascontiguousarray(a, dtype=t)
+        keep = [c(start, np.int32), c(index, np.int32), c(value, np.float64), c(collb, np.float64),
+                c(colub, np.float64), c(obj, np.float64), c(rowlb, np.float64), c(rowub, np.float64)]
+        p = lambda a, f: None if a is None else f(a)
+        rc = self._L.Clpb_loadProblem(self._h, int(numberColumns), int(numberRows), _ip(keep[0]),
+                                      _ip(keep[1]), _dp(keep[2]), p(keep[3], _dp), p(keep[4], _dp),
+                                      p(keep[5], _dp), p(keep[6], _dp), p(keep[7], _dp))
+        if rc != 0:
+            raise ValueError(f"loadProblem failed ({rc})")
+        return rc
+
+    def loadLP(self, lp):
+        return self.loadProblem(lp.n, lp.m, lp.col_start, lp.row_index, lp.element, lp.col_lower,
+                                lp.col_upper, lp.objective, lp.row_lower, lp.row_upper)
+
+    # ---- ClpModel::readMps ----
+    def readMps(self, fileName, keepNames=False, ignoreErrors=False):
+        return self._L.Clpb_readMps(self._h, str(fileName).encode(), int(keepNames), int(ignoreErrors))
+
+    def numberRows(self):
+        return self._L.Clpb_numberRows(self._h)
+
+    def numberColumns(self):
+        return self._L.Clpb_numberColumns(self._h)
+
+    def getNumElements(self):
+        return self._L.Clpb_getNumElements(self._h)
+
+    def getProblem(self):
+        """Returns the loaded problem as a generators.LP (what readMps parsed)."""
+        from .generators import LP
+
+        n, m, nnz = self.numberColumns(), self.numberRows(), self.getNumElements()
+        st = np.zeros(n + 1, np.int32); ix = np.zeros(nnz, np.int32); va = np.zeros(nnz)
+        cl = np.zeros(n); cu = np.zeros(n); ob = np.zeros(n); rl = np.zeros(m); ru = np.zeros(m)
+        self._L.Clpb_getProblem(self._h, _ip(st), _ip(ix), _dp(va), _dp(cl), _dp(cu), _dp(ob),
+                                _dp(rl), _dp(ru))
+        return LP("from-engine", m, n, st, ix, va, cl, cu, ob, rl, ru)
+
+    # ---- parameters ----
+    def _set(self, key, value):
+        if self._L.Clpb_setParameter(self._h, key.encode(), float(value)) != 0:
+            raise KeyError(key)
+
+    def setPrimalTolerance(self, v): self._set("primalTolerance", v)
+    def setDualTolerance(self, v): self._set("dualTolerance", v)
+    def setDualBound(self, v): self._set("dualBound", v)
+    def setMaximumIterations(self, v): self._set("maximumIterations", v)
+    def setMaximumSeconds(self, v): self._set("maximumSeconds", v)
+    def setLogLevel(self, v): self._set("logLevel", v)
+    def setFactorizationFrequency(self, v): self._set("factorizationFrequency", v)
+    def setParameter(self, key, v): self._set(key, v)
+
+    def copyinStatus(self, status):
+        st = np.ascontiguousarray(status, dtype=np.uint8)
+        self._L.Clpb_copyinStatus(self._h, _up(st))
+
+    # ---- ClpSimplex::dual ----
+    def dual(self, ifValuesPass=0):
+        rc = self._L.Clpb_dual(self._h, int(ifValuesPass))
+        if rc == _capi.NO_DEVICE:
+            raise NoDeviceError("clp_b200 needs a CUDA device (no CPU fallback)")
+        if rc == -99:
+            raise RuntimeError("clp_b200: CUDA failure inside dual()")
+        return rc
+
+    def status(self): return self._L.Clpb_status(self._h)
+    def isProvenOptimal(self): return self.status() == 0
+    def isProvenPrimalInfeasible(self): return self.status() == 1
+    def isProvenDualInfeasible(self): return self.status() == 2
+    def objectiveValue(self): return self._L.Clpb_objectiveValue(self._h)
+    def numberIterations(self): return self._L.Clpb_numberIterations(self._h)
+    def numberRefactorizations(self): return self._L.Clpb_numberRefactorizations(self._h)
+    def secondsInLoop(self): return self._L.Clpb_secondsInLoop(self._h)
+    def kernelLaunches(self): return self._L.Clpb_kernelLaunches(self._h)
+    def nucleusSize(self): return self._L.Clpb_nucleusSize(self._h)
+
+    def phaseTimes(self):
+        o = np.zeros(9)
+        self._L.Clpb_phaseTimes(self._h, _dp(o))
+        keys = ["chuzr", "btran", "price", "chuzc", "dualUpdate", "ftran", "update", "refactor", "samples"]
+        return dict(zip(keys, o.tolist()))
+
+    def _vec(self, fn, size, dtype=np.float64):
+        out = np.zeros(size, dtype=dtype)
+        fn(self._h, _dp(out) if dtype == np.float64 else _up(out))
+        return out
+
+    def primalColumnSolution(self): return self._vec(self._L.Clpb_primalColumnSolution, self.numberColumns())
+    def primalRowSolution(self): return self._vec(self._L.Clpb_primalRowSolution, self.numberRows())
+    def dualColumnSolution(self): return self._vec(self._L.Clpb_dualColumnSolution, self.numberColumns())
+    def dualRowSolution(self): return self._vec(self._L.Clpb_dualRowSolution, self.numberRows())
+    def statusArray(self): return self._vec(self._L.Clpb_statusArray, self.numberColumns() + self.numberRows(), np.uint8)
+
+    # ---- column sharding ----
+    def initSharding(self, rank, world_size, unique_id):
+        uid = np.ascontiguousarray(unique_id, dtype=np.uint8)
+        rc = self._L.Clpb_initSharding(self._h, int(rank), int(world_size), _up(uid))
+        if rc != 0:
+            raise RuntimeError(f"NCCL communicator init failed ({rc})")
+
+    @staticmethod
+    def ncclUniqueId():
+        uid = np.zeros(128, dtype=np.uint8)
+        rc = _capi.lib().Clpb_ncclUniqueId(_up(uid))
+        if rc != 0:
+            raise RuntimeError(f"ncclGetUniqueId failed ({rc})")
+        return uid
+
+    # ---- plug-in level (ClpFactorization / ClpMatrixBase / ClpDualRowPivot interfaces) ----
+    def _chk(self, rc):
+        if rc == _capi.NO_DEVICE:
+            raise NoDeviceError("clp_b200 needs a CUDA device (no CPU fallback)")
+        if rc == -99:
+            raise RuntimeError("clp_b200: CUDA failure")
+        return rc
+
+    def factorize(self, basicSequence):
+        b = np.ascontiguousarray(basicSequence, dtype=np.int32)
+        pv = np.zeros(self.numberRows(), dtype=np.int32)
+        rc = self._chk(self._L.Clpb_factorize(self._h, _ip(b), _ip(pv)))
+        return rc, pv
+
+    def updateColumn(self, region):
+        v = np.array(region, dtype=np.float64)
+        self._chk(self._L.Clpb_updateColumn(self._h, _dp(v)))
+        return v
+
+    def updateColumnTranspose(self, region):
+        v = np.array(region, dtype=np.float64)
+        self._chk(self._L.Clpb_updateColumnTranspose(self._h, _dp(v)))
+        return v
+
+    def replaceColumn(self, sequenceIn, pivotRow):
+        return self._chk(self._L.Clpb_replaceColumn(self._h, int(sequenceIn), int(pivotRow)))
+
+    def transposeTimes(self, scalar, pi):
+        pi = np.ascontiguousarray(pi, dtype=np.float64)
+        z = np.zeros(self.numberColumns())
+        self._chk(self._L.Clpb_transposeTimes(self._h, float(scalar), _dp(pi), _dp(z)))
+        return z
+
+    def times(self, scalar, x):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        y = np.zeros(self.numberRows())
+        self._chk(self._L.Clpb_times(self._h, float(scalar), _dp(x), _dp(y)))
+        return y
+
+    def dualColumn(self, alphaRow, dj, status, direction, infeasibility):
+        a = np.ascontiguousarray(alphaRow, dtype=np.float64)
+        d = np.ascontiguousarray(dj, dtype=np.float64)
+        s = np.ascontiguousarray(status, dtype=np.uint8)
+        theta = ctypes.c_double(0.0)
+        q = self._chk(self._L.Clpb_dualColumn(self._h, _dp(a), _dp(d), _up(s), int(direction),
+                                              float(infeasibility), ctypes.byref(theta)))
+        return q, theta.value
+
+    def startup(self): return self._chk(self._L.Clpb_startup(self._h))
+    def iterate(self, count): return self._chk(self._L.Clpb_iterate(self._h, int(count)))
+
+    def weights(self):
+        w = np.zeros(self.numberRows())
+        self._L.Clpb_getWeights(self._h, _dp(w))
+        return w
+
+    def deviceVector(self, name):
+        n, m = self.numberColumns(), self.numberRows()
+        size = {"sol": n + m, "dj": n + m, "rho": m, "alphaRow": n + m, "pivotVariable": m,
+                "status": n + m}[name]
+        out = np.zeros(size)
+        self._L.Clpb_getDeviceVector(self._h, name.encode(), _dp(out))
+        return out

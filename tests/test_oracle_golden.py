@@ -1,0 +1,239 @@
+"""CPU suite (-m "not gpu"): the oracle against the reference's golden vectors, the C ABI
+surface, the host-side MPS reader and the multi-rank host logic (gloo)."""
+import json
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, load_golden
+
+from clp_b200 import generators as G
+from oracle import oracle as O
+
+MANIFEST = json.load(open(os.path.join(ROOT, "tests", "golden", "manifest.json")))
+SMALL = [k for k, v in MANIFEST.items() if v["m"] * v["n"] < 4_000_000 and k != "NQueens-100"]
+
+
+def test_unit_test_3x5_factorize_ftran():
+    """src/unitTest.cpp:1415-1482: basis {c0,c1,c4} -> colsol = {20/7, 3, 0, 0, 23/7}."""
+    lp = load_golden("unitTest-3x5")
+    o = O.OracleSimplex(lp)
+    rc, pv = o.factorize([0, 1, 4])
+    assert rc == 0
+    # rows are equalities 14,3,3 and are nonbasic at that value: B x_B = +rowvalue (slack col -e_i)
+    x = o.ftran(lp.row_lower.copy())
+    col = np.zeros(5)
+    for p, seq in enumerate(pv):
+        col[seq] = x[p]
+    np.testing.assert_allclose(col, [20.0 / 7.0, 3.0, 0.0, 0.0, 23.0 / 7.0], rtol=1e-12, atol=1e-12)
+
+
+@pytest.mark.parametrize("name", SMALL)
+def test_oracle_matches_reference_values(name):
+    lp = load_golden(name)
+    o = O.OracleSimplex(lp)
+    st = o.dual()
+    assert st == lp.expect_status
+    if st == 0:
+        tol = 1e-4 if MANIFEST[name]["objective_source"] == "reference" else 1e-8
+        assert abs(o.objective_value - lp.known_objective) <= tol * (1 + abs(lp.known_objective))
+        assert O.kkt_violations(lp, o.column_solution(), o.row_activity(), o.reduced_cost()) == 0
+
+
+def test_oracle_planted_random_lp():
+    lp = G.random_sparse_lp(300, 3000, 0.02, 7)
+    o = O.OracleSimplex(lp)
+    assert o.dual() == 0
+    assert abs(o.objective_value - lp.known_objective) <= 1e-8 * (1 + abs(lp.known_objective))
+
+
+def test_oracle_ft_update_consistency():
+    """FTRAN/BTRAN after Forrest-Tomlin updates == FTRAN/BTRAN after refactorizing the same basis."""
+    lp = G.random_sparse_lp(120, 600, 0.05, 3)
+    rng = np.random.default_rng(0)
+    o = O.OracleSimplex(lp)
+    basis = list(range(lp.n, lp.n + lp.m))
+    rc, pv = o.factorize(basis)
+    assert rc == 0
+    entering = rng.choice(lp.n, size=40, replace=False)
+    for q in entering:
+        col = np.zeros(lp.m)
+        col[lp.row_index[lp.col_start[q]:lp.col_start[q + 1]]] = lp.element[lp.col_start[q]:lp.col_start[q + 1]]
+        a = o.ftran(col)
+        r = int(np.argmax(np.abs(a)))
+        assert o.replace_column(int(q), r) in (0, 1)
+        pv[r] = q
+    b = rng.standard_normal(lp.m)
+    x1, y1 = o.ftran(b), o.btran(b)
+    o2 = O.OracleSimplex(lp)
+    rc, pv2 = o2.factorize(pv)
+    assert rc == 0
+    x2, y2 = o2.ftran(b), o2.btran(b)
+    # same basis, possibly different pivot-row labels: compare per variable
+    xv1 = {int(s): x1[p] for p, s in enumerate(pv)}
+    xv2 = {int(s): x2[p] for p, s in enumerate(pv2)}
+    for s in xv1:
+        assert abs(xv1[s] - xv2[s]) <= 1e-8 * (1 + abs(xv2[s]))
+    cb = rng.standard_normal(lp.n + lp.m)
+    y1 = o.btran(np.array([cb[s] for s in pv]))
+    y2 = o2.btran(np.array([cb[s] for s in pv2]))
+    np.testing.assert_allclose(y1, y2, rtol=1e-8, atol=1e-8)
+
+
+def test_generators_are_frozen():
+    """the libc-rand generators reproduce the committed fixtures bit for bit"""
+    for lp in (G.tsp_mtz(20, 42), G.ufl(10, 30, 99), G.set_cover(30, 100, 0.15, 11)):
+        ref = load_golden(lp.name)
+        assert np.array_equal(ref.col_start, lp.col_start)
+        assert np.array_equal(ref.row_index, lp.row_index)
+        assert np.array_equal(ref.element, lp.element)
+        assert np.array_equal(ref.objective, lp.objective)
+
+
+def test_cabi_exports_every_declared_symbol():
+    from clp_b200 import _capi
+
+    header = open(os.path.join(ROOT, "include", "clp_b200.h")).read()
+    declared = set(re.findall(r"\b(Clpb_[A-Za-z0-9]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    L = _capi.lib()
+    for name in sorted(declared):
+        assert hasattr(L, name), f"{name} declared in include/clp_b200.h but not exported"
+    assert declared == set(_capi.SIGNATURES), declared ^ set(_capi.SIGNATURES)
+
+
+def test_product_does_not_reference_oracle():
+    """the product path must not include, link or call anything under oracle/"""
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "clp_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".hpp", ".cpp", ".h")) or f == "Makefile":
+                txt = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert "oracle" not in txt.lower() or f == "generators.py", os.path.join(dirpath, f)
+    out = subprocess.run(["ldd", os.path.join(ROOT, "clp_b200", "_lib", "libclp_b200.so")],
+                         capture_output=True, text=True).stdout
+    assert "oracle" not in out
+
+
+def _write_mps(lp, path):
+    """tiny MPS writer (test side) for the reader round trip"""
+    inf = 1e29
+    with open(path, "w") as f:
+        f.write("NAME          RT\nROWS\n N  COST\n")
+        kinds = []
+        for i in range(lp.m):
+            lo, up = lp.row_lower[i], lp.row_upper[i]
+            k = "E" if lo == up else ("G" if up >= inf else ("L" if lo <= -inf else "R"))
+            kinds.append(k)
+            f.write(f" {'L' if k == 'R' else k}  R{i}\n")
+        f.write("COLUMNS\n")
+        for j in range(lp.n):
+            if lp.objective[j] != 0.0:
+                f.write(f"    C{j}  COST  {float(lp.objective[j])!r}\n")
+            for e in range(lp.col_start[j], lp.col_start[j + 1]):
+                f.write(f"    C{j}  R{lp.row_index[e]}  {float(lp.element[e])!r}\n")
+        f.write("RHS\n")
+        for i in range(lp.m):
+            v = lp.row_lower[i] if kinds[i] in "EG" else lp.row_upper[i]
+            if v != 0.0:
+                f.write(f"    RHS  R{i}  {float(v)!r}\n")
+        f.write("RANGES\n")
+        for i in range(lp.m):
+            if kinds[i] == "R":
+                f.write(f"    RNG  R{i}  {float(lp.row_upper[i] - lp.row_lower[i])!r}\n")
+        f.write("BOUNDS\n")
+        for j in range(lp.n):
+            lo, up = lp.col_lower[j], lp.col_upper[j]
+            if lo <= -inf and up >= inf:
+                f.write(f" FR BND  C{j}\n")
+                continue
+            if lo <= -inf:
+                f.write(f" MI BND  C{j}\n")
+            elif lo != 0.0:
+                f.write(f" LO BND  C{j}  {float(lo)!r}\n")
+            if up < inf:
+                f.write(f" UP BND  C{j}  {float(up)!r}\n")
+        f.write("ENDATA\n")
+
+
+@pytest.mark.parametrize("name", ["TSP-MTZ-20", "hello", "modified_afiro", "SetPack-40x120"])
+def test_mps_reader_round_trip(tmp_path, name):
+    import clp_b200
+
+    lp = load_golden(name)
+    path = tmp_path / "rt.mps"
+    _write_mps(lp, path)
+    s = clp_b200.ClpSimplex()
+    assert s.readMps(path) == 0
+    got = s.getProblem()
+    assert (got.m, got.n) == (lp.m, lp.n)
+    A0, A1 = lp.to_scipy(), got.to_scipy()
+    assert abs(A0 - A1).max() == 0
+    for a, b in ((lp.col_lower, got.col_lower), (lp.col_upper, got.col_upper),
+                 (lp.row_lower, got.row_lower), (lp.row_upper, got.row_upper),
+                 (lp.objective, got.objective)):
+        np.testing.assert_allclose(np.clip(a, -1e30, 1e30), np.clip(b, -1e30, 1e30), rtol=1e-15)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/examples"), reason="reference tree absent")
+def test_mps_reader_on_reference_files():
+    import clp_b200
+
+    for fn, name in (("modified_afiro.mps", "modified_afiro"), ("hello.mps", "hello")):
+        s = clp_b200.ClpSimplex()
+        assert s.readMps(os.path.join("/root/reference/examples", fn)) == 0
+        got, ref = s.getProblem(), load_golden(name)
+        assert abs(got.to_scipy() - ref.to_scipy()).max() == 0
+        np.testing.assert_array_equal(got.row_lower, ref.row_lower)
+
+
+def test_no_device_fails_loudly():
+    import clp_b200
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    s = clp_b200.ClpSimplex()
+    s.loadLP(load_golden("NQueens-8"))
+    with pytest.raises(clp_b200.NoDeviceError):
+        s.dual()
+
+
+def test_two_rank_sharding_host_logic():
+    """world_size=2 over gloo: unique-id broadcast and column shard ranges (the host logic of
+    the column-sharded pricing pass; the NCCL exchange itself is exercised on the GPU box)."""
+    code = r"""
+import os, sys
+sys.path.insert(0, %r)
+import numpy as np, torch, torch.distributed as dist
+from clp_b200.sharding import shard_range, broadcast_unique_id
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%%s" %% os.environ["PORT"],
+                        rank=int(os.environ["RANK"]), world_size=2)
+rank = dist.get_rank()
+uid = np.arange(128, dtype=np.uint8) if rank == 0 else np.zeros(128, dtype=np.uint8)
+uid = broadcast_unique_id(uid, src=0)
+assert np.array_equal(uid, np.arange(128, dtype=np.uint8))
+n = 1001
+lo, hi = shard_range(n, rank, 2)
+t = torch.tensor([lo, hi])
+out = [torch.zeros(2, dtype=torch.long) for _ in range(2)]
+dist.all_gather(out, t)
+assert out[0][0] == 0 and out[0][1] == out[1][0] and out[1][1] == n
+dist.destroy_process_group()
+print("ok", rank)
+""" % ROOT
+    import socket
+
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), PORT=str(port))
+        procs.append(subprocess.Popen([sys.executable, "-c", code], env=env, stdout=subprocess.PIPE,
+                                      stderr=subprocess.PIPE, text=True))
+    for p in procs:
+        out, err = p.communicate(timeout=120)
+        assert p.returncode == 0, err
+        assert "ok" in out
