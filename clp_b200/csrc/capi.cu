@@ -136,6 +136,8 @@ int Clpb_setParameter(Clpb_Simplex *model, const char *key, double value)
     e.batch = std::max(1, (int)value);
   else if (k == "timing")
     e.timing = value != 0.0;
+  else if (k == "useGraph")
+    e.useGraph = value != 0.0;
   else if (k == "objectiveOffset")
     e.objectiveOffset = value;
   else

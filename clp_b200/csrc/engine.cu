@@ -46,6 +46,9 @@ void Engine::freeAll()
   for (cudaEvent_t e : events)
     cudaEventDestroy(e);
   events.clear();
+  if (iterGraph)
+    cudaGraphExecDestroy(iterGraph);
+  iterGraph = nullptr;
   if (hState)
     cudaFreeHost(hState);
   if (hRec)
@@ -222,8 +225,18 @@ int Engine::setupDevice()
   d.nu = dalloc<double>(d.tmax);
   d.histWeight = dalloc<unsigned long long>(kHistBuckets);
   d.histMin = dalloc<unsigned long long>(kHistBuckets);
+  d.hist2Weight = dalloc<unsigned long long>(kHist2Buckets);
+  d.hist2Min = dalloc<unsigned long long>(kHist2Buckets);
+  d.segTotal = dalloc<unsigned long long>(kHistBuckets / 1024);
+  d.segLast = dalloc<int>(kHistBuckets / 1024);
+  d.scanCounter = dalloc<unsigned int>(1);
+  CUDA_OK(cudaMemset(d.scanCounter, 0, sizeof(unsigned int)));
+  CUDA_OK(cudaMemset(d.hist2Weight, 0, sizeof(unsigned long long) * kHist2Buckets));
+  CUDA_OK(cudaMemset(d.hist2Min, 0xFF, sizeof(unsigned long long) * kHist2Buckets));
   d.flipList = dalloc<int>(nm);
   d.st = dalloc<IterState>(1);
+  d.fd = dalloc<FactorDesc>(1);
+  CUDA_OK(cudaMemset(d.fd, 0, sizeof(FactorDesc)));
   d.recCap = 64;
   d.rec = dalloc<IterRecord>(d.recCap);
   dXn = dalloc<double>(n);
@@ -423,6 +436,17 @@ int Engine::refactor()
     }
     d.k = k;
     d.ldk = ldk;
+    {
+      FactorDesc hfd;
+      hfd.k = k;
+      hfd.ldk = ldk;
+      hfd.Ninv = d.Ninv;
+      hfd.NinvT = d.NinvT;
+      hfd.s1Col = dS1Col;
+      hfd.s1Val = dS1Val;
+      CUDA_OK(cudaMemcpyAsync(d.fd, &hfd, sizeof(FactorDesc), cudaMemcpyHostToDevice, stream));
+      CUDA_OK(cudaStreamSynchronize(stream)); // hfd is a stack object
+    }
     CUDA_OK(cudaMemcpyAsync(d.posToNuc, posToNuc.data(), sizeof(int) * m, cudaMemcpyHostToDevice, stream));
     if (k > 0) {
       CUDA_OK(cudaMemcpyAsync(d.nucRow, nucRow.data(), sizeof(int) * k, cudaMemcpyHostToDevice, stream));
@@ -570,6 +594,23 @@ void Engine::enqueueIteration(bool timed, int slot)
   kernelLaunches += 2 + 4 + 2 + 4 + 3 + 5 + 4;
 }
 
+void Engine::buildIterationGraph()
+{
+  if (iterGraph)
+    return;
+  cudaGraph_t graph = nullptr;
+  const long before = kernelLaunches;
+  CUDA_OK(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+  enqueueIteration(false, 0);
+  CUDA_OK(cudaStreamEndCapture(stream, &graph));
+  kernelLaunches = before;
+  size_t numNodes = 0;
+  CUDA_OK(cudaGraphGetNodes(graph, nullptr, &numNodes));
+  kernelsPerIteration = (int)numNodes;
+  CUDA_OK(cudaGraphInstantiate(&iterGraph, graph, 0));
+  cudaGraphDestroy(graph);
+}
+
 void Engine::fetchState()
 {
   CUDA_OK(cudaMemcpyAsync(hState, d.st, sizeof(IterState), cudaMemcpyDeviceToHost, stream));
@@ -645,8 +686,15 @@ int Engine::dual()
     if (timing)
       count = std::min(count, 16);
     const int before = hState->iterations;
-    for (int b = 0; b < count; b++)
-      enqueueIteration(timing, b);
+    if (useGraph && !timing) {
+      buildIterationGraph();
+      for (int b = 0; b < count; b++)
+        CUDA_OK(cudaGraphLaunch(iterGraph, stream));
+      kernelLaunches += (long)count * kernelsPerIteration;
+    } else {
+      for (int b = 0; b < count; b++)
+        enqueueIteration(timing, b);
+    }
     fetchState();
     const int done = hState->iterations - before;
     numberIterations += done;
@@ -663,6 +711,15 @@ int Engine::dual()
         phase.ftran += ms[5];
         phase.update += ms[6];
         phase.samples++;
+      }
+    }
+    if (logLevel > 2) {
+      CUDA_OK(cudaMemcpy(hRec, d.rec, sizeof(IterRecord) * d.recCap, cudaMemcpyDeviceToHost));
+      for (int b = 0; b < done; b++) {
+        const IterRecord &r = hRec[(before + b) % d.recCap];
+        fprintf(stderr, "TRACE %d out=%d in=%d sigma=%d thetaD=%.12g thetaP=%.12g alpha=%.12g infeas=%.12g flips=%d\n",
+                numberIterations - done + b, r.seqOut, r.seqIn, r.sigma, r.thetaDual, r.thetaPrimal,
+                r.alphaCol, r.infeas, r.numFlips);
       }
     }
     if (logLevel > 1)
@@ -844,6 +901,10 @@ int Engine::dualColumnTest(const double *alphaRow, const double *dj, const unsig
   st.sigma = sigma;
   st.infeas = infeas;
   CUDA_OK(cudaMemcpy(d.st, &st, sizeof(st), cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemsetAsync(d.histWeight, 0, sizeof(unsigned long long) * kHistBuckets, stream));
+  CUDA_OK(cudaMemsetAsync(d.histMin, 0xFF, sizeof(unsigned long long) * kHistBuckets, stream));
+  CUDA_OK(cudaMemsetAsync(d.hist2Weight, 0, sizeof(unsigned long long) * kHist2Buckets, stream));
+  CUDA_OK(cudaMemsetAsync(d.hist2Min, 0xFF, sizeof(unsigned long long) * kHist2Buckets, stream));
   launch_histogram(d, stream);
   launch_chuzc(d, stream);
   fetchState();

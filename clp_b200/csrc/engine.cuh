@@ -30,7 +30,8 @@ enum : unsigned char { isFree = 0, basic = 1, atUpperBound = 2, atLowerBound = 3
 
 constexpr double kInf = 1.0e30;
 constexpr double kDevexTryNorm = 1.0e-4; // DEVEX_TRY_NORM ClpSimplex.hpp:2056
-constexpr int kHistBuckets = 32768;       // ratio-test histogram: 11 exponent + 4 mantissa bits
+constexpr int kHistBuckets = 32768;       // ratio-test histogram level 1: 11 exponent + 4 mantissa bits
+constexpr int kHist2Buckets = 4096;       // level 2: the next 12 mantissa bits inside the crossing bucket
 constexpr int kMaxFlips = 8192;
 
 // stop reasons written by the device into IterState.stop
@@ -60,12 +61,25 @@ struct IterState {
   unsigned long long harrisBits; // atomicMin target (double bits, positive)
   double objectiveChange;
   int costShifts;        // number of cost shifts since they were last removed
-  int pad;
+  int bucket1;           // level-1 ratio bucket in which the BFRT slope is exhausted (-1: none)
+  unsigned long long residual; // fixed-point slope still to absorb inside bucket1
 };
 
 struct IterRecord { // what the host reads back per iteration
   int stop, pivotRow, seqIn, seqOut, sigma, numFlips;
   double thetaDual, thetaPrimal, alphaRow, alphaCol, infeas;
+};
+
+// Things that change at a refactorization.  Lives in device memory and is read by the kernels,
+// so that the kernel arguments (and hence a captured CUDA graph of one iteration) stay valid
+// across refactorizations.
+struct FactorDesc {
+  int k;               // nucleus size
+  int ldk;             // row pitch of Ninv / NinvT (multiple of 8)
+  const double *Ninv;  // [k x ldk] row-major                 (FTRAN  y = Ninv b)
+  const double *NinvT; // [k x ldk] row-major of the transpose (BTRAN  y = Ninv^T b)
+  const int *s1Col;    // CSR of S1 = A[C rows, nucleus columns]: nucleus index
+  const double *s1Val;
 };
 
 // All device pointers of one model.  Plain struct passed by value to kernels.
@@ -92,6 +106,7 @@ struct DeviceModel {
   int *nucCol;        // [k] structural sequence of nucleus index
   double *Ninv;       // [k x ldk] row-major : row i contiguous  (FTRAN  y = Ninv b)
   double *NinvT;      // [k x ldk] row-major of the transpose     (BTRAN  y = Ninv^T b)
+  FactorDesc *fd;        // device copy of {k, ldk, Ninv, NinvT, s1Col, s1Val} (read by kernels)
   const int *s1RowStart; // CSR of S1 = A[C rows, nucleus columns], rows indexed by position
   const int *s1Col;      // nucleus index
   const double *s1Val;
@@ -114,6 +129,10 @@ struct DeviceModel {
   // ratio test
   unsigned long long *histWeight; // [kHistBuckets] fixed-point slope per ratio bucket
   unsigned long long *histMin;    // [kHistBuckets] min ratio bits per bucket
+  unsigned long long *hist2Weight, *hist2Min; // [kHist2Buckets] second level
+  unsigned long long *segTotal;   // [kHistBuckets/1024] per-segment totals of the level-1 scan
+  int *segLast;                   // last non-empty bucket per segment
+  unsigned int *scanCounter;      // last-block-done ticket
   int *flipList;      // [kMaxFlips]
   IterState *st;
   IterRecord *rec;    // ring of records (device)

@@ -39,6 +39,7 @@ public:
   int logLevel = 0;
   int batch = 16;                 // iterations enqueued per host synchronisation
   bool timing = false;
+  bool useGraph = true;
   double objectiveOffset = 0.0;
   // column sharding of the pricing pass (multi-GPU): this rank prices [colBegin,colEnd)
   int rank = 0, worldSize = 1;
@@ -112,6 +113,9 @@ private:
   std::vector<int> hPivot;
   int tmax = 0;
   double currentDualBound = 0.0;
+  cudaGraphExec_t iterGraph = nullptr; // one captured iteration (replayed 'batch' times per sync)
+  int kernelsPerIteration = 0;
+  void buildIterationGraph();
 
   template <class T> T *dalloc(size_t count);
   void freeAll();

@@ -186,34 +186,169 @@ void launch_price_slacks(const DeviceModel &d, bool fuseHist, cudaStream_t s)
 }
 
 // ---------------------------------------------------------------------------------------
-// single CTA: find theta* from the histogram, reset it, compute ||rho||^2
-__global__ void __launch_bounds__(1024) chuzc_scan_kernel(DeviceModel d)
+// Level-1 scan: 32 CTAs x 1024 buckets.  Each CTA reduces its segment; the last CTA to finish
+// locates the segment and then the bucket in which the cumulative slope reaches the primal
+// infeasibility (fixed point 2^40).  Outputs st->bucket1 and st->residual (slope still to be
+// absorbed inside that bucket).  The histograms are cleared by next iteration's CHUZR kernel.
+__global__ void __launch_bounds__(1024) chuzc_scan1_kernel(DeviceModel d)
 {
   if (!iter_active(d.st))
     return;
-  constexpr int PER = kHistBuckets / 1024;
-  const int tid = threadIdx.x;
-  const int lane = tid & 31, warp = tid >> 5;
-  __shared__ unsigned long long warpTot[32];
+  __shared__ unsigned long long sTot[32];
   __shared__ int sLast[32];
-  __shared__ int sCross;
+  __shared__ unsigned long long segPrefix[32];
+  __shared__ int sIsLast, sSeg, sLastAll;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nseg = gridDim.x; // kHistBuckets / 1024
+  {
+    const int b = blockIdx.x * 1024 + tid;
+    unsigned long long w = d.histWeight[b];
+    int last = d.histMin[b] != kSentinel ? b : -1;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      w += __shfl_xor_sync(0xffffffffu, w, o);
+      last = max(last, __shfl_xor_sync(0xffffffffu, last, o));
+    }
+    if (lane == 0) {
+      sTot[warp] = w;
+      sLast[warp] = last;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      unsigned long long t = 0;
+      int l = -1;
+      for (int q = 0; q < 32; q++) {
+        t += sTot[q];
+        l = max(l, sLast[q]);
+      }
+      d.segTotal[blockIdx.x] = t;
+      d.segLast[blockIdx.x] = l;
+      __threadfence();
+      unsigned int ticket = atomicAdd(d.scanCounter, 1u);
+      sIsLast = (ticket == (unsigned)nseg - 1);
+      if (sIsLast)
+        *d.scanCounter = 0u;
+    }
+    __syncthreads();
+    if (!sIsLast)
+      return;
+  }
+  __threadfence();
+  // ---- last CTA: prefix over segments
+  if (tid == 0) {
+    unsigned long long c = 0;
+    int seg = -1, lastAll = -1;
+    for (int q = 0; q < nseg; q++) {
+      segPrefix[q] = c;
+      unsigned long long t = d.segTotal[q];
+      if (seg < 0 && c + t >= kFixOne)
+        seg = q;
+      c += t;
+      lastAll = max(lastAll, d.segLast[q]);
+    }
+    sSeg = seg;
+    sLastAll = lastAll;
+  }
+  __syncthreads();
+  IterState *st = d.st;
+  if (sLastAll < 0) {
+    if (tid == 0) {
+      st->stop = STOP_NO_COLUMN;
+      st->bucket1 = -1;
+    }
+    return;
+  }
+  if (sSeg < 0) {
+    // slope never exhausted: stop at the last break point group
+    if (tid == 0) {
+      st->bucket1 = -1;
+      st->thetaStar = __longlong_as_double((long long)d.histMin[sLastAll]);
+    }
+    return;
+  }
+  // ---- scan inside the crossing segment
+  const int b = sSeg * 1024 + tid;
+  const unsigned long long w = d.histWeight[b];
+  unsigned long long inc = w;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    unsigned long long t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o)
+      inc += t;
+  }
+  __syncthreads();
+  if (lane == 31)
+    sTot[warp] = inc;
+  __syncthreads();
+  unsigned long long base = segPrefix[sSeg];
+  for (int q = 0; q < warp; q++)
+    base += sTot[q];
+  const unsigned long long excl = base + inc - w;
+  if (excl < kFixOne && excl + w >= kFixOne) { // exactly one thread
+    st->bucket1 = b;
+    st->residual = kFixOne - excl;
+  }
+}
+
+// Level 2: candidates of the crossing bucket, next 12 bits of the ratio
+__global__ void chuzc_hist2_kernel(DeviceModel d)
+{
+  if (!iter_active(d.st))
+    return;
+  const int b1 = d.st->bucket1;
+  if (b1 < 0)
+    return;
+  const int sigma = d.st->sigma;
+  const double infeas = d.st->infeas;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < d.nm; j += gridDim.x * blockDim.x) {
+    const double alpha = d.alphaRow[j];
+    if (alpha == 0.0)
+      continue;
+    double a, dtil, range;
+    bool boxed;
+    if (!candidate(d, j, alpha, sigma, a, dtil, boxed, range))
+      continue;
+    const double ratio = dtil / a;
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(ratio);
+    if (((int)(bits >> 48) & (kHistBuckets - 1)) != b1)
+      continue;
+    const int sb = (int)(bits >> 36) & (kHist2Buckets - 1);
+    unsigned long long w = kFixCap;
+    if (boxed) {
+      double v = a * range / infeas * 1099511627776.0;
+      w = v >= 2199023255552.0 ? kFixCap : (unsigned long long)v;
+    }
+    atomicAdd(d.hist2Weight + sb, w);
+    atomicMin(d.hist2Min + sb, bits);
+  }
+}
+
+// Level-2 scan (single CTA, 4 sub-buckets per thread) -> theta*; also ||rho||^2 in a fixed order
+__global__ void __launch_bounds__(1024) chuzc_scan2_kernel(DeviceModel d)
+{
+  if (!iter_active(d.st))
+    return;
+  __shared__ unsigned long long sTot[32];
+  __shared__ int sLast[32];
   __shared__ double sNorm[32];
-  unsigned long long w[PER];
-  unsigned long long mn[PER];
+  __shared__ int sCross;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  IterState *st = d.st;
+  const int b1 = st->bucket1;
+  unsigned long long w[4], mn[4];
   unsigned long long tot = 0;
   int last = -1;
+  if (b1 >= 0) {
 #pragma unroll
-  for (int q = 0; q < PER; q++) {
-    int b = tid * PER + q;
-    w[q] = d.histWeight[b];
-    mn[q] = d.histMin[b];
-    tot += w[q];
-    if (mn[q] != kSentinel)
-      last = b;
-    d.histWeight[b] = 0ull;
-    d.histMin[b] = kSentinel;
+    for (int q = 0; q < 4; q++) {
+      const int b = tid * 4 + q;
+      w[q] = d.hist2Weight[b];
+      mn[q] = d.hist2Min[b];
+      tot += w[q];
+      if (mn[q] != kSentinel)
+        last = b;
+    }
   }
-  // inclusive scan of per-thread totals
   unsigned long long inc = tot;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
@@ -225,60 +360,58 @@ __global__ void __launch_bounds__(1024) chuzc_scan_kernel(DeviceModel d)
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1)
     wl = max(wl, __shfl_xor_sync(0xffffffffu, wl, o));
-  if (lane == 31)
-    warpTot[warp] = inc;
-  if (lane == 0)
-    sLast[warp] = wl;
-  if (tid == 0)
-    sCross = -1;
-  // ||rho||^2
   double nrm = 0.0;
   for (int i = tid; i < d.m; i += 1024) {
     double r = d.rho[i];
     nrm = fma(r, r, nrm);
   }
-  nrm = warp_sum(nrm);
-  if (lane == 0)
-    sNorm[warp] = nrm;
-  __syncthreads();
-  unsigned long long base = 0;
-  for (int q = 0; q < warp; q++)
-    base += warpTot[q];
-  unsigned long long excl = base + inc - tot;
-  if (excl < kFixOne && excl + tot >= kFixOne) {
-    unsigned long long c = excl;
-    int found = -1;
 #pragma unroll
-    for (int q = 0; q < PER; q++) {
-      c += w[q];
-      if (found < 0 && c >= kFixOne)
-        found = tid * PER + q;
-    }
-    sCross = found; // exactly one thread crosses
+  for (int o = 16; o > 0; o >>= 1)
+    nrm += __shfl_xor_sync(0xffffffffu, nrm, o);
+  if (lane == 31)
+    sTot[warp] = inc;
+  if (lane == 0) {
+    sLast[warp] = wl;
+    sNorm[warp] = nrm;
   }
+  if (tid == 0)
+    sCross = -1;
   __syncthreads();
   if (tid == 0) {
-    int lastAll = -1;
-    for (int q = 0; q < 32; q++)
-      lastAll = max(lastAll, sLast[q]);
     double nsum = 0.0;
     for (int q = 0; q < 32; q++)
       nsum += sNorm[q];
-    d.st->rhoNorm2 = nsum;
-    d.st->harrisBits = 0x7FF0000000000000ull; // +inf
-    d.st->chuzcKey = 0ull;
-    if (lastAll < 0) {
-      d.st->stop = STOP_NO_COLUMN;
-      d.st->thetaStar = 0.0;
-      sCross = -2;
-    } else if (sCross < 0) {
-      sCross = lastAll; // slope never exhausted: stop at the last breakpoint group
+    st->rhoNorm2 = nsum;
+    st->harrisBits = 0x7FF0000000000000ull; // +inf
+    st->chuzcKey = 0ull;
+  }
+  if (b1 < 0)
+    return; // thetaStar already set by scan1 (or no candidates)
+  unsigned long long base = 0;
+  for (int q = 0; q < warp; q++)
+    base += sTot[q];
+  const unsigned long long resid = st->residual;
+  const unsigned long long excl = base + inc - tot;
+  if (excl < resid && excl + tot >= resid) {
+    unsigned long long c = excl;
+    int found = -1;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      c += w[q];
+      if (found < 0 && c >= resid)
+        found = q;
     }
+    sCross = tid * 4 + found;
+    st->thetaStar = __longlong_as_double((long long)mn[found]);
   }
   __syncthreads();
-  const int b = sCross;
-  if (b >= 0 && tid == (b / PER))
-    d.st->thetaStar = __longlong_as_double((long long)mn[b % PER]);
+  if (sCross < 0 && tid == 0) {
+    // numerically possible only through fixed-point truncation: take the last sub-bucket
+    int lastAll = -1;
+    for (int q = 0; q < 32; q++)
+      lastAll = max(lastAll, sLast[q]);
+    st->thetaStar = __longlong_as_double((long long)d.hist2Min[lastAll]);
+  }
 }
 
 // Harris bound over candidates with ratio >= theta*  (ClpSimplexDual.cpp:4331-4395 upperTheta)
@@ -362,10 +495,12 @@ __global__ void chuzc_finish_kernel(DeviceModel d)
 
 void launch_chuzc(const DeviceModel &d, cudaStream_t s)
 {
-  chuzc_scan_kernel<<<1, 1024, 0, s>>>(d);
   int blocks = (d.nm + 255) / 256;
   if (blocks > 148 * 4)
     blocks = 148 * 4;
+  chuzc_scan1_kernel<<<kHistBuckets / 1024, 1024, 0, s>>>(d);
+  chuzc_hist2_kernel<<<blocks, 256, 0, s>>>(d);
+  chuzc_scan2_kernel<<<1, 1024, 0, s>>>(d);
   chuzc_harris_kernel<<<blocks, 256, 0, s>>>(d);
   chuzc_select_kernel<<<blocks, 256, 0, s>>>(d);
   chuzc_finish_kernel<<<1, 1, 0, s>>>(d);

@@ -24,6 +24,8 @@ __device__ __forceinline__ bool iter_active(const IterState *st)
   return st->stop == 0;
 }
 
+static inline int roundUp8(int v) { return (v + 7) / 8 * 8; }
+
 __device__ __forceinline__ double warp_sum(double v)
 {
 #pragma unroll
@@ -39,29 +41,31 @@ __global__ void gather_nucleus_kernel(DeviceModel d, const double *__restrict__ 
 {
   if (checkState && !iter_active(d.st))
     return;
-  int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= d.ldk)
-    return;
-  if (j >= d.k) { // zero padding so the GEMV can run over the padded row length
-    for (int c = 0; c < nrhs; c++)
-      xg[(size_t)c * d.ldk + j] = 0.0;
-    return;
+  const int k = d.fd->k, ldk = d.fd->ldk;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < ldk; j += gridDim.x * blockDim.x) {
+    if (j >= k) { // zero padding so the GEMV can run over the padded row length
+      for (int c = 0; c < nrhs; c++)
+        xg[(size_t)c * ldk + j] = 0.0;
+    } else {
+      int p = d.nucRow[j];
+      for (int c = 0; c < nrhs; c++)
+        xg[(size_t)c * ldk + j] = b[(size_t)c * bstride + p];
+    }
   }
-  int p = d.nucRow[j];
-  for (int c = 0; c < nrhs; c++)
-    xg[(size_t)c * d.ldk + j] = b[(size_t)c * bstride + p];
 }
 
 // y[c][i] = sum_j M[i][j] * x[c][j]   (M row-major k x ldk, one warp per row)
 // if outIndex != nullptr the result is scattered: out[c*ostride + outIndex[i]]
 template <int NRHS>
 __global__ void __launch_bounds__(256)
-    gemv_rows_kernel(const double *__restrict__ M, int k, int ldk, const double *__restrict__ x,
-                     double *__restrict__ out, int ostride, const int *__restrict__ outIndex,
-                     const IterState *st, bool checkState)
+    gemv_rows_kernel(const FactorDesc *__restrict__ fd, int transposed,
+                     const double *__restrict__ x, double *__restrict__ out, int ostride,
+                     const int *__restrict__ outIndex, const IterState *st, bool checkState)
 {
   if (checkState && !iter_active(st))
     return;
+  const int k = fd->k, ldk = fd->ldk;
+  const double *__restrict__ M = transposed ? fd->NinvT : fd->Ninv;
   const int warpsPerBlock = blockDim.x >> 5;
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -87,9 +91,10 @@ __global__ void __launch_bounds__(256)
       acc[c] = warp_sum(acc[c]);
     if (lane == 0) {
       int o = outIndex ? outIndex[i] : i;
+      const int os = ostride < 0 ? ldk : ostride;
 #pragma unroll
       for (int c = 0; c < NRHS; c++)
-        out[(size_t)c * ostride + o] = acc[c];
+        out[(size_t)c * os + o] = acc[c];
     }
   }
 }
@@ -106,25 +111,28 @@ __global__ void ftran_spread_kernel(DeviceModel d, double *__restrict__ b, int b
   if (p >= d.m)
     return; // whole 8-lane group exits together
   const unsigned gmask = 0xFFu << ((threadIdx.x & 31) & ~7);
+  const int ldk = d.fd->ldk;
+  const int *__restrict__ s1Col = d.fd->s1Col;
+  const double *__restrict__ s1Val = d.fd->s1Val;
   int ni = d.posToNuc[p];
   if (ni >= 0) {
     if (sub == 0)
       for (int c = 0; c < NRHS; c++)
-        b[(size_t)c * bstride + p] = y[(size_t)c * d.ldk + ni];
+        b[(size_t)c * bstride + p] = y[(size_t)c * ldk + ni];
     return;
   }
   double acc[NRHS];
 #pragma unroll
   for (int c = 0; c < NRHS; c++)
     acc[c] = 0.0;
-  if (d.k > 0) {
+  if (d.fd->k > 0) {
     int e0 = d.s1RowStart[p], e1 = d.s1RowStart[p + 1];
     for (int e = e0 + sub; e < e1; e += 8) {
-      double v = d.s1Val[e];
-      int j = d.s1Col[e];
+      double v = s1Val[e];
+      int j = s1Col[e];
 #pragma unroll
       for (int c = 0; c < NRHS; c++)
-        acc[c] = fma(v, y[(size_t)c * d.ldk + j], acc[c]);
+        acc[c] = fma(v, y[(size_t)c * ldk + j], acc[c]);
     }
   }
 #pragma unroll
@@ -208,21 +216,25 @@ template <int NRHS>
 static void ftran_impl(const DeviceModel &d, double *b, bool applyEtas, bool checkState,
                        cudaStream_t s)
 {
-  const int m = d.m, k = d.k;
-  if (k > 0) {
-    gather_nucleus_kernel<<<(d.ldk + 255) / 256, 256, 0, s>>>(d, b, m, d.ywork + (size_t)3 * d.ldk,
-                                                          NRHS, checkState);
-    int blocks = (k + 7) / 8;
-    gemv_rows_kernel<NRHS><<<blocks, 256, 0, s>>>(d.Ninv, k, d.ldk, d.ywork + (size_t)3 * d.ldk,
-                                                  d.ywork, d.ldk, nullptr, d.st, checkState);
-  }
+  const int m = d.m;
+  // fixed launch shapes (grid-stride kernels read k from the device-side FactorDesc)
+  const int maxk = d.m;
+  int gblocks = (roundUp8(maxk) + 255) / 256;
+  if (gblocks > 148)
+    gblocks = 148;
+  double *xg = d.ywork + (size_t)3 * roundUp8(maxk);
+  gather_nucleus_kernel<<<gblocks, 256, 0, s>>>(d, b, m, xg, NRHS, checkState);
+  int blocks = (maxk + 7) / 8;
+  if (blocks > 148 * 8)
+    blocks = 148 * 8;
+  gemv_rows_kernel<NRHS><<<blocks, 256, 0, s>>>(d.fd, 0, xg, d.ywork, -1, nullptr, d.st, checkState);
   ftran_spread_kernel<NRHS><<<(m * 8 + 255) / 256, 256, 0, s>>>(d, b, m, d.ywork, checkState);
   if (applyEtas) {
     pfi_mu_kernel<NRHS><<<(d.tmax + 7) / 8, 256, 0, s>>>(d, b, m, checkState);
-    int blocks = (m + 7) / 8;
-    if (blocks > 148 * 8)
-      blocks = 148 * 8;
-    pfi_apply_kernel<NRHS><<<blocks, 256, 0, s>>>(d, b, m, checkState);
+    int pblocks = (m + 7) / 8;
+    if (pblocks > 148 * 8)
+      pblocks = 148 * 8;
+    pfi_apply_kernel<NRHS><<<pblocks, 256, 0, s>>>(d, b, m, checkState);
   }
 }
 
@@ -323,32 +335,34 @@ __global__ void btran_s_kernel(DeviceModel d, bool checkState)
   if (checkState && !iter_active(d.st))
     return;
   const int lane = threadIdx.x & 31;
-  const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (j >= d.k)
-    return;
-  const int col = d.nucCol[j];
-  double acc = 0.0;
-  for (int e = d.colStart[col] + lane; e < d.colStart[col + 1]; e += 32) {
-    int i = d.rowIdx[e];
-    if (d.posToNuc[i] < 0)
-      acc = fma(d.val[e], d.uwork[i], acc);
+  const int k = d.fd->k, ldk = d.fd->ldk;
+  const int warpsPerBlock = blockDim.x >> 5;
+  for (int j = blockIdx.x * warpsPerBlock + (threadIdx.x >> 5); j < k;
+       j += gridDim.x * warpsPerBlock) {
+    const int col = d.nucCol[j];
+    double acc = 0.0;
+    for (int e = d.colStart[col] + lane; e < d.colStart[col + 1]; e += 32) {
+      int i = d.rowIdx[e];
+      if (d.posToNuc[i] < 0)
+        acc = fma(d.val[e], d.uwork[i], acc);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0)
+      d.swork[j] = acc + d.uwork[d.nucRow[j]];
   }
-  acc = warp_sum(acc);
-  if (lane == 0)
-    d.swork[j] = acc + d.uwork[d.nucRow[j]];
-  // zero the padding once so the GEMV can run over ldk
-  if (j == 0 && lane == 0)
-    for (int q = d.k; q < d.ldk; q++)
-      d.swork[q] = 0.0;
+  // zero the padding so the GEMV can run over ldk
+  if (blockIdx.x == 0 && threadIdx.x < 8 && k + threadIdx.x < ldk)
+    d.swork[k + threadIdx.x] = 0.0;
 }
 
 static void btran_tail(const DeviceModel &d, double *rhoOut, bool checkState, cudaStream_t s)
 {
-  if (d.k > 0) {
-    btran_s_kernel<<<(d.k + 7) / 8, 256, 0, s>>>(d, checkState);
-    gemv_rows_kernel<1><<<(d.k + 7) / 8, 256, 0, s>>>(d.NinvT, d.k, d.ldk, d.swork, rhoOut, d.m,
-                                                      d.nucRow, d.st, checkState);
-  }
+  int blocks = (d.m + 7) / 8;
+  if (blocks > 148 * 8)
+    blocks = 148 * 8;
+  btran_s_kernel<<<blocks, 256, 0, s>>>(d, checkState);
+  gemv_rows_kernel<1><<<blocks, 256, 0, s>>>(d.fd, 1, d.swork, rhoOut, d.m, d.nucRow, d.st,
+                                             checkState);
 }
 
 // rho = B_t^-T e_r with r = st->pivotRow ; result in d.rho

@@ -16,6 +16,8 @@ namespace clpb {
 
 __device__ __forceinline__ bool iter_active(const IterState *st) { return st->stop == 0; }
 
+constexpr int kFlipScanLimit = 24; // above this many flips a CSR row pass builds the flip rhs
+
 // ------------------------------------------------------------------ CHUZR
 __global__ void chuzr_kernel(DeviceModel d)
 {
@@ -23,6 +25,15 @@ __global__ void chuzr_kernel(DeviceModel d)
     return;
   const double tol = d.primalTolerance;
   unsigned long long best = 0ull;
+  // clear the ratio-test histograms for this iteration (the previous scans are complete)
+  for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < kHistBuckets; b += gridDim.x * blockDim.x) {
+    d.histWeight[b] = 0ull;
+    d.histMin[b] = 0xFFFFFFFFFFFFFFFFull;
+    if (b < kHist2Buckets) {
+      d.hist2Weight[b] = 0ull;
+      d.hist2Min[b] = 0xFFFFFFFFFFFFFFFFull;
+    }
+  }
   for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < d.m; p += gridDim.x * blockDim.x) {
     const int seq = d.pivotVariable[p];
     const double v = d.sol[seq];
@@ -83,6 +94,8 @@ void launch_chuzr(const DeviceModel &d, cudaStream_t s)
   int blocks = (d.m + 255) / 256;
   if (blocks > 148 * 4)
     blocks = 148 * 4;
+  if (blocks < 32)
+    blocks = 32; // also clears the ratio-test histograms
   chuzr_kernel<<<blocks, 256, 0, s>>>(d);
   chuzr_finish_kernel<<<1, 1, 0, s>>>(d);
 }
@@ -218,8 +231,9 @@ __global__ void __launch_bounds__(256) build_rhs3_kernel(DeviceModel d)
       __syncthreads();
     }
   }
-  // flipped columns
-  const int nf = d.st->numFlips;
+  // flipped columns (few flips: scan them here; many flips: flip_rhs_rows_kernel does a row pass)
+  const int nfAll = d.st->numFlips;
+  const int nf = nfAll <= kFlipScanLimit ? nfAll : 0;
   for (int f = 0; f < nf; f++) {
     const int j = d.flipList[f];
     const double range = d.upper[j] - d.lower[j];
@@ -249,6 +263,42 @@ __global__ void __launch_bounds__(256) build_rhs3_kernel(DeviceModel d)
   }
 }
 
+// Many flips: rhs3[2][i] = -sum_j a_ij delta_j over flipped j, one warp per row of the CSR copy
+// (streams the column indices once, 4 B per nonzero; fixed summation order).
+__global__ void __launch_bounds__(256)
+    flip_rhs_rows_kernel(DeviceModel d, const unsigned char *__restrict__ flipFlag)
+{
+  if (!iter_active(d.st))
+    return;
+  if (d.st->numFlips <= kFlipScanLimit)
+    return;
+  const int lane = threadIdx.x & 31;
+  const int warpsPerBlock = blockDim.x >> 5;
+  for (int i = blockIdx.x * warpsPerBlock + (threadIdx.x >> 5); i < d.m;
+       i += gridDim.x * warpsPerBlock) {
+    double acc = 0.0;
+    for (int e = d.rowStart[i] + lane; e < d.rowStart[i + 1]; e += 32) {
+      const int j = __ldg(d.colIdx + e);
+      if (flipFlag[j]) {
+        const double range = d.upper[j] - d.lower[j];
+        const double delta = d.status[j] == atUpperBound ? range : -range;
+        acc = fma(-delta, d.rval[e], acc);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+      acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) {
+      const int js = d.n + i;
+      if (flipFlag[js]) {
+        const double range = d.upper[js] - d.lower[js];
+        acc += d.status[js] == atUpperBound ? range : -range;
+      }
+      d.rhs3[(size_t)2 * d.m + i] = acc;
+    }
+  }
+}
+
 void launch_dual_update_and_flips(const DeviceModel &d, unsigned char *flipFlag, cudaStream_t s)
 {
   int blocks = (d.nm + 255) / 256;
@@ -257,6 +307,12 @@ void launch_dual_update_and_flips(const DeviceModel &d, unsigned char *flipFlag,
   dual_update_kernel<<<blocks, 256, 0, s>>>(d, flipFlag);
   flip_collect_kernel<<<1, 1024, 0, s>>>(d, flipFlag);
   build_rhs3_kernel<<<(d.m + 255) / 256, 256, 0, s>>>(d);
+  {
+    int rb = (d.m + 7) / 8;
+    if (rb > 148 * 16)
+      rb = 148 * 16;
+    flip_rhs_rows_kernel<<<rb, 256, 0, s>>>(d, flipFlag);
+  }
 }
 
 // ------------------------------------------------------------------ after the FTRANs

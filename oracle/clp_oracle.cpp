@@ -149,6 +149,141 @@ int dualColumn(int count, const double *alpha, const double *dj, const double *r
   return chosen;
 }
 
+// ------------------------------------------------------------------ bucketed BFRT
+// Restatement of the GPU's sort-free variant of the same ratio test (clp_b200/csrc/price.cu):
+// slope contributions are accumulated per ratio bucket (top 15 bits of the double), the step
+// stops at the smallest ratio of the bucket in which the slope is exhausted, then Harris +
+// largest |alpha|.  Lets tests follow the GPU's pivot sequence on the CPU.
+int dualColumnBucketed(int count, const double *alpha, const double *dj, const double *range,
+                       const unsigned char *stat, double infeasibility, double dualTolerance,
+                       double acceptablePivot, double *thetaOut, unsigned char *passed)
+{
+  const int NB = 32768;
+  static thread_local std::vector<unsigned long long> hw, hm;
+  hw.assign(NB, 0ull);
+  hm.assign(NB, ~0ull);
+  std::vector<double> A(count), D(count), R(count);
+  std::vector<char> ok(count, 0);
+  bool any = false;
+  for (int k = 0; k < count; k++) {
+    if (passed)
+      passed[k] = 0;
+    double ab = alpha[k], a = std::fabs(ab);
+    unsigned char s = stat[k];
+    if (a <= 1.0e-12)
+      continue;
+    double dt;
+    bool boxed = false;
+    if (s == ORC_atLowerBound) {
+      if (ab <= 0.0)
+        continue;
+      dt = dj[k] > 0.0 ? dj[k] : 0.0;
+      boxed = range[k] < 1.0e29;
+    } else if (s == ORC_atUpperBound) {
+      if (ab >= 0.0)
+        continue;
+      dt = dj[k] < 0.0 ? -dj[k] : 0.0;
+      boxed = range[k] < 1.0e29;
+    } else if (s == ORC_isFree || s == ORC_superBasic) {
+      dt = 0.0;
+    } else
+      continue;
+    ok[k] = 1;
+    any = true;
+    A[k] = a;
+    D[k] = dt;
+    double ratio = dt / a;
+    R[k] = ratio;
+    unsigned long long bits;
+    std::memcpy(&bits, &ratio, 8);
+    int b = (int)(bits >> 48) & (NB - 1);
+    unsigned long long w = 1ull << 41;
+    if (boxed) {
+      double v = a * range[k] / infeasibility * 1099511627776.0;
+      w = v >= 2199023255552.0 ? (1ull << 41) : (unsigned long long)v;
+    }
+    hw[b] += w;
+    hm[b] = std::min(hm[b], bits);
+  }
+  *thetaOut = 0.0;
+  if (!any)
+    return -1;
+  unsigned long long c = 0, before = 0;
+  int cross = -1, last = -1;
+  for (int b = 0; b < NB; b++) {
+    if (hm[b] != ~0ull)
+      last = b;
+    if (cross < 0 && c + hw[b] >= (1ull << 40)) {
+      cross = b;
+      before = c;
+    }
+    c += hw[b];
+  }
+  double thetaStar;
+  if (cross < 0) {
+    std::memcpy(&thetaStar, &hm[last], 8); // slope never exhausted: last break point group
+  } else {
+    // second level: the next 12 bits of the ratio inside the crossing bucket
+    const int NB2 = 4096;
+    std::vector<unsigned long long> hw2(NB2, 0ull), hm2(NB2, ~0ull);
+    for (int k = 0; k < count; k++) {
+      if (!ok[k])
+        continue;
+      unsigned long long bits;
+      std::memcpy(&bits, &R[k], 8);
+      if (((int)(bits >> 48) & (NB - 1)) != cross)
+        continue;
+      int sb = (int)(bits >> 36) & (NB2 - 1);
+      bool boxed = range[k] < 1.0e29 && (stat[k] == ORC_atLowerBound || stat[k] == ORC_atUpperBound);
+      unsigned long long w = 1ull << 41;
+      if (boxed) {
+        double v = A[k] * range[k] / infeasibility * 1099511627776.0;
+        w = v >= 2199023255552.0 ? (1ull << 41) : (unsigned long long)v;
+      }
+      hw2[sb] += w;
+      hm2[sb] = std::min(hm2[sb], bits);
+    }
+    const unsigned long long resid = (1ull << 40) - before;
+    unsigned long long c2 = 0;
+    int cross2 = -1, last2 = -1;
+    for (int b = 0; b < NB2; b++) {
+      if (hm2[b] != ~0ull)
+        last2 = b;
+      c2 += hw2[b];
+      if (cross2 < 0 && c2 >= resid)
+        cross2 = b;
+    }
+    if (cross2 < 0)
+      cross2 = last2;
+    std::memcpy(&thetaStar, &hm2[cross2], 8);
+  }
+  double harris = std::numeric_limits<double>::infinity();
+  for (int k = 0; k < count; k++)
+    if (ok[k] && A[k] >= acceptablePivot && R[k] >= thetaStar)
+      harris = std::min(harris, (D[k] + dualTolerance) / A[k]);
+  int best = -1;
+  unsigned long long bestKey = 0;
+  for (int k = 0; k < count; k++)
+    if (ok[k] && A[k] >= acceptablePivot && R[k] >= thetaStar && R[k] <= harris) {
+      unsigned long long bits;
+      std::memcpy(&bits, &A[k], 8);
+      unsigned long long key = (bits & ~0xFFFFFull) | (unsigned long long)(0xFFFFF - k);
+      if (key > bestKey) {
+        bestKey = key;
+        best = k;
+      }
+    }
+  if (best < 0)
+    return -1;
+  if (passed)
+    for (int k = 0; k < count; k++)
+      if (ok[k] && R[k] < thetaStar)
+        passed[k] = 1;
+  double t = dj[best] / alpha[best];
+  *thetaOut = t > 0.0 ? t : 0.0;
+  return best;
+}
+
 // ------------------------------------------------------------------ DSE recurrence
 void dseUpdate(int m, double *weights, const double *alphaColumn, const double *tau, int pivotRow,
                double rhoNorm2)
@@ -192,6 +327,7 @@ struct DualSimplex {
   int logLevel = 0;
   int threads = 1;
   double maximumSeconds = 1e30;
+  int bucketedRatioTest = 0; // 1 = mimic the GPU's sort-free ratio test
   // results
   int problemStatus = -1;
   int numberIterations = 0, numberRefactorizations = 0;
@@ -694,9 +830,23 @@ int DualSimplex::dual()
     }
     candPassed.assign(candIdx.size(), 0);
     double thetaDual = 0.0;
-    int kq = dualColumn(static_cast<int>(candIdx.size()), candAlpha.data(), candDj.data(),
-                        candRange.data(), candStat.data(), infeas, dualTolerance, acceptablePivot,
-                        &thetaDual, candPassed.data());
+    int kq = (bucketedRatioTest ? dualColumnBucketed : dualColumn)(
+        static_cast<int>(candIdx.size()), candAlpha.data(), candDj.data(), candRange.data(),
+        candStat.data(), infeas, dualTolerance, acceptablePivot, &thetaDual, candPassed.data());
+    if (logLevel > 3 && kq >= 0) {
+      double t2 = 0.0;
+      std::vector<unsigned char> p2(candIdx.size());
+      int k2 = (bucketedRatioTest ? dualColumn : dualColumnBucketed)(
+          static_cast<int>(candIdx.size()), candAlpha.data(), candDj.data(), candRange.data(),
+          candStat.data(), infeas, dualTolerance, acceptablePivot, &t2, p2.data());
+      int np1 = 0, np2 = 0;
+      for (size_t k = 0; k < candIdx.size(); k++) {
+        np1 += candPassed[k];
+        np2 += p2[k];
+      }
+      fprintf(stderr, "CMP it=%d infeas=%.6g used: k=%d theta=%.8g passed=%d alpha=%.4g | other: k=%d theta=%.8g passed=%d alpha=%.4g\n",
+              numberIterations, infeas, kq, thetaDual, np1, candAlpha[kq], k2, t2, np2, k2 >= 0 ? candAlpha[k2] : 0.0);
+    }
     if (kq < 0) {
       if (fac.numberPivots > 0) {
         needRefresh = true;
@@ -831,6 +981,13 @@ int DualSimplex::dual()
     else
       status[seqOut] = sigma < 0 ? ORC_atLowerBound : ORC_atUpperBound;
     pivotVariable[r] = seqIn;
+    if (logLevel > 2) {
+      int nfl = 0;
+      for (size_t k = 0; k < candIdx.size(); k++)
+        nfl += 0;
+      fprintf(stderr, "TRACE %d out=%d in=%d sigma=%d thetaD=%.12g thetaP=%.12g alpha=%.12g infeas=%.12g\n",
+              numberIterations, seqOut, seqIn, sigma, thetaDual, thetaPrimal, alphaFtran, infeas);
+    }
     numberIterations++;
     if (logLevel > 1 && (numberIterations % 100) == 0)
       fprintf(stderr, "oracle: it %d obj %.10g infeas %g theta %g\n", numberIterations,
@@ -910,6 +1067,8 @@ void orc_set_option(orc_model *h, const char *key, double value)
     s.threads = std::max(1, static_cast<int>(value));
   else if (k == "maximumSeconds")
     s.maximumSeconds = value;
+  else if (k == "bucketedRatioTest")
+    s.bucketedRatioTest = static_cast<int>(value);
 }
 void orc_set_status(orc_model *h, const unsigned char *status)
 {
@@ -996,6 +1155,13 @@ int orc_dual_column(int count, const double *alpha, const double *dj, const doub
 {
   return orc::dualColumn(count, alpha, dj, range, stat, infeasibility, dualTolerance,
                          acceptablePivot, theta_out, flips_out);
+}
+int orc_dual_column_bucketed(int count, const double *alpha, const double *dj, const double *range,
+                             const unsigned char *stat, double infeasibility, double dualTolerance,
+                             double acceptablePivot, double *theta_out, unsigned char *flips_out)
+{
+  return orc::dualColumnBucketed(count, alpha, dj, range, stat, infeasibility, dualTolerance,
+                                 acceptablePivot, theta_out, flips_out);
 }
 void orc_dse_update(int m, double *weights, const double *alphaColumn, const double *tau,
                     int pivotRow, double rhoNorm2)

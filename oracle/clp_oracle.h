@@ -34,7 +34,7 @@ orc_model *orc_create(int numberRows, int numberColumns, const int *columnStart,
 void orc_destroy(orc_model *);
 
 /* option keys: "primalTolerance","dualTolerance","dualBound","maximumIterations",
- * "factorizationFrequency","logLevel","threads","maximumSeconds","perturbation" */
+ * "factorizationFrequency","logLevel","threads","maximumSeconds","bucketedRatioTest" */
 void orc_set_option(orc_model *, const char *key, double value);
 
 /* optional starting basis: status[numberColumns+numberRows] (columns first, Clp order) */
@@ -80,6 +80,13 @@ void orc_times(const orc_model *, double scalar, const double *x, double *y);
 int orc_dual_column(int count, const double *alpha, const double *dj, const double *range,
                     const unsigned char *stat, double infeasibility, double dualTolerance,
                     double acceptablePivot, double *theta_out, unsigned char *flips_out);
+
+/* Same ratio test evaluated the way the GPU evaluates it (two-level ratio histogram instead of
+ * sorted passes; clp_b200/csrc/price.cu) -- lets tests follow the GPU's pivot sequence. */
+int orc_dual_column_bucketed(int count, const double *alpha, const double *dj,
+                             const double *range, const unsigned char *stat,
+                             double infeasibility, double dualTolerance, double acceptablePivot,
+                             double *theta_out, unsigned char *flips_out);
 
 /* ClpDualRowSteepest::updateWeights recurrence on explicit arrays (in place on weights) */
 void orc_dse_update(int m, double *weights, const double *alphaColumn, const double *tau,

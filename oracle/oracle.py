@@ -57,6 +57,7 @@ def lib():
         L.orc_dual_column.argtypes = [ctypes.c_int, c_double_p, c_double_p, c_double_p, c_ubyte_p,
                                       ctypes.c_double, ctypes.c_double, ctypes.c_double,
                                       c_double_p, c_ubyte_p]
+        L.orc_dual_column_bucketed.argtypes = L.orc_dual_column.argtypes
         L.orc_dse_update.argtypes = [ctypes.c_int, c_double_p, c_double_p, c_double_p,
                                      ctypes.c_int, ctypes.c_double]
         _lib = L
@@ -172,14 +173,15 @@ class OracleSimplex:
         return y
 
 
-def dual_column(alpha, dj, rng, stat, infeasibility, dual_tol=1e-7, acceptable=1e-7):
+def dual_column(alpha, dj, rng, stat, infeasibility, dual_tol=1e-7, acceptable=1e-7, bucketed=False):
     alpha = np.ascontiguousarray(alpha, dtype=np.float64)
     dj = np.ascontiguousarray(dj, dtype=np.float64)
     rng = np.ascontiguousarray(rng, dtype=np.float64)
     stat = np.ascontiguousarray(stat, dtype=np.uint8)
     theta = ctypes.c_double(0.0)
     flips = np.zeros(alpha.size, dtype=np.uint8)
-    k = lib().orc_dual_column(alpha.size, _dp(alpha), _dp(dj), _dp(rng), _up(stat),
+    fn = lib().orc_dual_column_bucketed if bucketed else lib().orc_dual_column
+    k = fn(alpha.size, _dp(alpha), _dp(dj), _dp(rng), _up(stat),
                               float(infeasibility), dual_tol, acceptable, ctypes.byref(theta),
                               _up(flips))
     return k, theta.value, flips
