@@ -48,6 +48,7 @@ SIGNATURES = {
     "Clpb_kernelLaunches": (ctypes.c_longlong, [ctypes.c_void_p]),
     "Clpb_phaseTimes": (None, [ctypes.c_void_p, c_double_p]),
     "Clpb_nucleusSize": (ctypes.c_int, [ctypes.c_void_p]),
+    "Clpb_timedWindow": (None, [ctypes.c_void_p, c_double_p, c_int_p]),
     "Clpb_ncclUniqueId": (ctypes.c_int, [c_ubyte_p]),
     "Clpb_initSharding": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, c_ubyte_p]),
     "Clpb_factorize": (ctypes.c_int, [ctypes.c_void_p, c_int_p, c_int_p]),

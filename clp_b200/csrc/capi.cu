@@ -136,6 +136,8 @@ int Clpb_setParameter(Clpb_Simplex *model, const char *key, double value)
     e.batch = std::max(1, (int)value);
   else if (k == "timing")
     e.timing = value != 0.0;
+  else if (k == "warmupIterations")
+    e.warmupIterations = (int)value;
   else if (k == "useGraph")
     e.useGraph = value != 0.0;
   else if (k == "objectiveOffset")
@@ -183,7 +185,7 @@ void Clpb_statusArray(Clpb_Simplex *model, unsigned char *st)
 }
 double Clpb_secondsInLoop(Clpb_Simplex *model) { return model->e.secondsInLoop; }
 long long Clpb_kernelLaunches(Clpb_Simplex *model) { return model->e.kernelLaunches; }
-void Clpb_phaseTimes(Clpb_Simplex *model, double *o)
+void Clpb_phaseTimes(Clpb_Simplex *model, double *o /* 12 */)
 {
   const clpb::PhaseTimes &p = model->e.phase;
   o[0] = p.chuzr;
@@ -195,8 +197,16 @@ void Clpb_phaseTimes(Clpb_Simplex *model, double *o)
   o[6] = p.update;
   o[7] = p.refactor;
   o[8] = (double)p.samples;
+  o[9] = p.priceKernel;
+  o[10] = p.ftranGemv;
+  o[11] = p.btranGemv;
 }
 int Clpb_nucleusSize(Clpb_Simplex *model) { return model->e.lastNucleusSize; }
+void Clpb_timedWindow(Clpb_Simplex *model, double *milliseconds, int *iterations)
+{
+  *milliseconds = model->e.timedMilliseconds;
+  *iterations = model->e.timedIterations;
+}
 
 int Clpb_ncclUniqueId(unsigned char *id128)
 {

@@ -22,6 +22,8 @@ namespace clpb {
 
 static inline int roundUp(int v, int a) { return (v + a - 1) / a * a; }
 
+KernelTimers *g_kernelTimers = nullptr;
+
 Engine::Engine() {}
 Engine::~Engine()
 {
@@ -274,6 +276,13 @@ int Engine::setupDevice()
     events.resize(16 * 8 + 2);
     for (auto &e : events)
       CUDA_OK(cudaEventCreate(&e));
+    kernelTimers.resize(16);
+    for (auto &kt : kernelTimers)
+      for (int q = 0; q < 2; q++) {
+        CUDA_OK(cudaEventCreate(&kt.price[q]));
+        CUDA_OK(cudaEventCreate(&kt.ftranGemv[q]));
+        CUDA_OK(cudaEventCreate(&kt.btranGemv[q]));
+      }
   }
   deviceReady = true;
   return 0;
@@ -556,6 +565,7 @@ int Engine::refresh()
 void Engine::enqueueIteration(bool timed, int slot)
 {
   cudaEvent_t *ev = timed ? &events[(size_t)slot * 8] : nullptr;
+  g_kernelTimers = timed ? &kernelTimers[slot] : nullptr;
   if (timed)
     cudaEventRecord(ev[0], stream);
   launch_chuzr(d, stream);
@@ -591,7 +601,8 @@ void Engine::enqueueIteration(bool timed, int slot)
   launch_pivot_updates(d, stream);
   if (timed)
     cudaEventRecord(ev[7], stream);
-  kernelLaunches += 2 + 4 + 2 + 4 + 3 + 5 + 4;
+  g_kernelTimers = nullptr;
+  kernelLaunches += 2 + 4 + 2 + 6 + 4 + 5 + 4;
 }
 
 void Engine::buildIterationGraph()
@@ -660,6 +671,13 @@ int Engine::dual()
   }
   int dualBoundIncreases = 0;
   int consecutiveTrouble = 0;
+  cudaEvent_t evStart = nullptr, evStop = nullptr;
+  CUDA_OK(cudaEventCreate(&evStart));
+  CUDA_OK(cudaEventCreate(&evStop));
+  bool windowOpen = false;
+  int windowStartIteration = 0;
+  timedMilliseconds = 0.0;
+  timedIterations = 0;
   const int maxPivots = d.tmax < tmax ? d.tmax : tmax;
   while (problemStatus < 0) {
     if (numberIterations >= maximumIterations) {
@@ -670,6 +688,12 @@ int Engine::dual()
     if (el > maximumSeconds) {
       problemStatus = 3;
       break;
+    }
+    if (!windowOpen && numberIterations >= warmupIterations) {
+      CUDA_OK(cudaStreamSynchronize(stream));
+      CUDA_OK(cudaEventRecord(evStart, stream));
+      windowOpen = true;
+      windowStartIteration = numberIterations;
     }
     // enqueue a batch of iterations; kernels become no-ops once the device sets a stop reason
     fetchState();
@@ -682,6 +706,8 @@ int Engine::dual()
       continue;
     }
     int count = std::min(std::min(batch, room), maximumIterations - numberIterations);
+    if (!windowOpen && warmupIterations > numberIterations)
+      count = std::min(count, warmupIterations - numberIterations);
     count = std::min(count, d.recCap);
     if (timing)
       count = std::min(count, 16);
@@ -710,6 +736,13 @@ int Engine::dual()
         phase.dualUpdate += ms[4];
         phase.ftran += ms[5];
         phase.update += ms[6];
+        float k0 = 0, k1 = 0, k2 = 0;
+        cudaEventElapsedTime(&k0, kernelTimers[b].price[0], kernelTimers[b].price[1]);
+        cudaEventElapsedTime(&k1, kernelTimers[b].ftranGemv[0], kernelTimers[b].ftranGemv[1]);
+        cudaEventElapsedTime(&k2, kernelTimers[b].btranGemv[0], kernelTimers[b].btranGemv[1]);
+        phase.priceKernel += k0;
+        phase.ftranGemv += k1;
+        phase.btranGemv += k2;
         phase.samples++;
       }
     }
@@ -809,6 +842,16 @@ int Engine::dual()
       break;
     }
   }
+  if (windowOpen) {
+    CUDA_OK(cudaEventRecord(evStop, stream));
+    CUDA_OK(cudaEventSynchronize(evStop));
+    float ms = 0.0f;
+    cudaEventElapsedTime(&ms, evStart, evStop);
+    timedMilliseconds = ms;
+    timedIterations = numberIterations - windowStartIteration;
+  }
+  cudaEventDestroy(evStart);
+  cudaEventDestroy(evStop);
   downloadSolution();
   secondsInLoop = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
   return problemStatus;

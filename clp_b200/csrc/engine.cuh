@@ -141,6 +141,12 @@ struct DeviceModel {
   double primalTolerance, dualTolerance, acceptablePivot, zeroTolerance;
 };
 
+// Optional per-kernel CUDA-event brackets (timing mode only): price kernel, FTRAN GEMV, BTRAN GEMV.
+struct KernelTimers {
+  cudaEvent_t price[2], ftranGemv[2], btranGemv[2];
+};
+extern KernelTimers *g_kernelTimers; // nullptr outside timing mode (engine.cu)
+
 // ---- launch wrappers (implemented in the .cu files) ---------------------------------------
 // solve.cu
 void launch_ftran(const DeviceModel &d, int nrhs, bool applyEtas, cudaStream_t s);

@@ -16,6 +16,7 @@ namespace clpb {
 struct PhaseTimes { // accumulated device milliseconds per phase (when timing is on)
   double chuzr = 0, btran = 0, price = 0, chuzc = 0, dualUpdate = 0, ftran = 0, update = 0,
          refactor = 0;
+  double priceKernel = 0, ftranGemv = 0, btranGemv = 0; // single kernels inside the phases
   long samples = 0;
 };
 
@@ -40,6 +41,9 @@ public:
   int batch = 16;                 // iterations enqueued per host synchronisation
   bool timing = false;
   bool useGraph = true;
+  int warmupIterations = 0;       // device-timed window starts once this many iterations ran
+  double timedMilliseconds = 0.0; // CUDA-event time of the window (iterations + refactorizations)
+  int timedIterations = 0;
   double objectiveOffset = 0.0;
   // column sharding of the pricing pass (multi-GPU): this rank prices [colBegin,colEnd)
   int rank = 0, worldSize = 1;
@@ -109,6 +113,7 @@ private:
   IterState *hState = nullptr; // pinned
   IterRecord *hRec = nullptr;
   std::vector<cudaEvent_t> events;
+  std::vector<KernelTimers> kernelTimers; // one per batch slot (timing mode)
   std::vector<unsigned char> hStatus;
   std::vector<int> hPivot;
   int tmax = 0;

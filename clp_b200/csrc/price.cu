@@ -85,9 +85,16 @@ __device__ __forceinline__ void histogram_add(const DeviceModel &d, double a, do
   atomicMin(d.histMin + b, (unsigned long long)__double_as_longlong(ratio));
 }
 
-// alphaRow[j] = rho^T a_j for nonbasic, non-fixed columns j in [colBegin,colEnd) + histogram
-__global__ void __launch_bounds__(256) price_kernel(DeviceModel d, int colBegin, int colEnd, bool fuseHist)
+// alphaRow[j] = rho^T a_j for nonbasic, non-fixed columns j in [colBegin,colEnd) + histogram.
+// One warp works on units of 8 consecutive columns: the eight dot products are formed one after
+// the other (4-way unrolled, coalesced 4 B + 8 B streams of the CSC arrays), then lanes 0..7 do
+// the ratio-test candidate logic for the eight columns in parallel (coalesced dj/status/bounds).
+// rho is staged in shared memory when it fits (SMEM_RHO): the random gathers then cost shared
+// memory bank cycles instead of one L1 tag lookup per lane.
+template <bool SMEM_RHO>
+__global__ void __launch_bounds__(512) price_kernel(DeviceModel d, int colBegin, int colEnd, bool fuseHist)
 {
+  extern __shared__ double srho[];
   if (!iter_active(d.st))
     return;
   const int lane = threadIdx.x & 31;
@@ -95,26 +102,65 @@ __global__ void __launch_bounds__(256) price_kernel(DeviceModel d, int colBegin,
   const int sigma = d.st->sigma;
   const double infeas = d.st->infeas;
   const double *__restrict__ rho = d.rho;
-  for (int j = colBegin + blockIdx.x * warpsPerBlock + (threadIdx.x >> 5); j < colEnd;
-       j += gridDim.x * warpsPerBlock) {
-    const unsigned char st = d.status[j];
-    if (st == basic || st == isFixed) {
-      if (lane == 0)
-        d.alphaRow[j] = 0.0;
-      continue;
+  if (SMEM_RHO) {
+    for (int i = threadIdx.x; i < d.m; i += blockDim.x)
+      srho[i] = rho[i];
+    __syncthreads();
+  }
+  const int *__restrict__ rowIdx = d.rowIdx;
+  const double *__restrict__ val = d.val;
+  const int nUnits = (colEnd - colBegin + 7) >> 3;
+  for (int u = blockIdx.x * warpsPerBlock + (threadIdx.x >> 5); u < nUnits; u += gridDim.x * warpsPerBlock) {
+    const int j0 = colBegin + (u << 3);
+    // lanes 0..8 fetch the column starts, lanes 0..7 the status bytes of the unit
+    int myStart = 0;
+    unsigned char myStat = basic;
+    if (lane <= 8 && j0 + lane <= colEnd)
+      myStart = d.colStart[j0 + lane];
+    if (lane < 8 && j0 + lane < colEnd)
+      myStat = d.status[j0 + lane];
+    double myAlpha = 0.0;
+#pragma unroll
+    for (int c = 0; c < 8; c++) {
+      const int e0 = __shfl_sync(0xffffffffu, myStart, c);
+      const int e1 = __shfl_sync(0xffffffffu, myStart, c + 1);
+      const unsigned char st = (unsigned char)__shfl_sync(0xffffffffu, (int)myStat, c);
+      if (j0 + c >= colEnd || st == basic || st == isFixed)
+        continue; // uniform across the warp
+      double acc = 0.0;
+      int e = e0 + lane;
+      for (; e + 96 < e1; e += 128) {
+        const int r0 = __ldg(rowIdx + e), r1 = __ldg(rowIdx + e + 32), r2 = __ldg(rowIdx + e + 64),
+                  r3 = __ldg(rowIdx + e + 96);
+        const double v0 = __ldg(val + e), v1 = __ldg(val + e + 32), v2 = __ldg(val + e + 64),
+                     v3 = __ldg(val + e + 96);
+        const double p0 = SMEM_RHO ? srho[r0] : __ldg(rho + r0);
+        const double p1 = SMEM_RHO ? srho[r1] : __ldg(rho + r1);
+        const double p2 = SMEM_RHO ? srho[r2] : __ldg(rho + r2);
+        const double p3 = SMEM_RHO ? srho[r3] : __ldg(rho + r3);
+        acc = fma(v0, p0, acc);
+        acc = fma(v1, p1, acc);
+        acc = fma(v2, p2, acc);
+        acc = fma(v3, p3, acc);
+      }
+      for (; e < e1; e += 32) {
+        const int r0 = __ldg(rowIdx + e);
+        const double v0 = __ldg(val + e);
+        acc = fma(v0, SMEM_RHO ? srho[r0] : __ldg(rho + r0), acc);
+      }
+      acc = warp_sum(acc);
+      if (lane == c)
+        myAlpha = acc;
     }
-    const int e0 = d.colStart[j], e1 = d.colStart[j + 1];
-    double acc = 0.0;
-    for (int e = e0 + lane; e < e1; e += 32)
-      acc = fma(__ldg(d.val + e), __ldg(rho + __ldg(d.rowIdx + e)), acc);
-    acc = warp_sum(acc);
-    if (lane == 0) {
-      if (fabs(acc) < d.zeroTolerance)
-        acc = 0.0;
-      d.alphaRow[j] = acc;
+    if (lane < 8 && j0 + lane < colEnd) {
+      const int j = j0 + lane;
+      double alpha = myAlpha;
+      if (fabs(alpha) < d.zeroTolerance)
+        alpha = 0.0;
+      d.alphaRow[j] = alpha;
       double a, dtil, range;
       bool boxed;
-      if (fuseHist && acc != 0.0 && candidate(d, j, acc, sigma, a, dtil, boxed, range))
+      if (fuseHist && alpha != 0.0 && candidate(d, j, alpha, sigma, a, dtil, boxed, range))
         histogram_add(d, a, dtil, boxed, range, infeas);
     }
   }
@@ -172,13 +218,31 @@ void launch_histogram(const DeviceModel &d, cudaStream_t s)
 void launch_price(const DeviceModel &d, int colBegin, int colEnd, bool fuseHist, cudaStream_t s)
 {
   int ncol = colEnd - colBegin;
-  if (ncol > 0) {
-    int blocks = (ncol + 7) / 8;
-    int cap = 148 * 16;
-    if (blocks > cap)
-      blocks = cap;
-    price_kernel<<<blocks, 256, 0, s>>>(d, colBegin, colEnd, fuseHist);
+  if (ncol <= 0)
+    return;
+  const size_t smemBytes = sizeof(double) * (size_t)d.m;
+  static bool attrSet = false;
+  if (!attrSet) {
+    cudaFuncSetAttribute(price_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    attrSet = true;
   }
+  const int nUnits = (ncol + 7) / 8;
+  if (g_kernelTimers)
+    cudaEventRecord(g_kernelTimers->price[0], s);
+  if (smemBytes <= 220 * 1024) {
+    const int ctasPerSm = smemBytes <= 110 * 1024 ? 2 : 1;
+    int blocks = 148 * ctasPerSm;
+    if (blocks * 16 > nUnits)
+      blocks = (nUnits + 15) / 16;
+    price_kernel<true><<<blocks, 512, smemBytes, s>>>(d, colBegin, colEnd, fuseHist);
+  } else {
+    int blocks = 148 * 4;
+    if (blocks * 16 > nUnits)
+      blocks = (nUnits + 15) / 16;
+    price_kernel<false><<<blocks, 512, 0, s>>>(d, colBegin, colEnd, fuseHist);
+  }
+  if (g_kernelTimers)
+    cudaEventRecord(g_kernelTimers->price[1], s);
 }
 void launch_price_slacks(const DeviceModel &d, bool fuseHist, cudaStream_t s)
 {

@@ -227,7 +227,11 @@ static void ftran_impl(const DeviceModel &d, double *b, bool applyEtas, bool che
   int blocks = (maxk + 7) / 8;
   if (blocks > 148 * 8)
     blocks = 148 * 8;
+  if (g_kernelTimers && checkState)
+    cudaEventRecord(g_kernelTimers->ftranGemv[0], s);
   gemv_rows_kernel<NRHS><<<blocks, 256, 0, s>>>(d.fd, 0, xg, d.ywork, -1, nullptr, d.st, checkState);
+  if (g_kernelTimers && checkState)
+    cudaEventRecord(g_kernelTimers->ftranGemv[1], s);
   ftran_spread_kernel<NRHS><<<(m * 8 + 255) / 256, 256, 0, s>>>(d, b, m, d.ywork, checkState);
   if (applyEtas) {
     pfi_mu_kernel<NRHS><<<(d.tmax + 7) / 8, 256, 0, s>>>(d, b, m, checkState);
@@ -361,8 +365,12 @@ static void btran_tail(const DeviceModel &d, double *rhoOut, bool checkState, cu
   if (blocks > 148 * 8)
     blocks = 148 * 8;
   btran_s_kernel<<<blocks, 256, 0, s>>>(d, checkState);
+  if (g_kernelTimers && checkState)
+    cudaEventRecord(g_kernelTimers->btranGemv[0], s);
   gemv_rows_kernel<1><<<blocks, 256, 0, s>>>(d.fd, 1, d.swork, rhoOut, d.m, d.nucRow, d.st,
                                              checkState);
+  if (g_kernelTimers && checkState)
+    cudaEventRecord(g_kernelTimers->btranGemv[1], s);
 }
 
 // rho = B_t^-T e_r with r = st->pivotRow ; result in d.rho

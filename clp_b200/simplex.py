@@ -127,10 +127,16 @@ class ClpSimplex:
     def kernelLaunches(self): return self._L.Clpb_kernelLaunches(self._h)
     def nucleusSize(self): return self._L.Clpb_nucleusSize(self._h)
 
+    def timedWindow(self):
+        ms = ctypes.c_double(0.0); it = ctypes.c_int(0)
+        self._L.Clpb_timedWindow(self._h, ctypes.byref(ms), ctypes.byref(it))
+        return ms.value, it.value
+
     def phaseTimes(self):
-        o = np.zeros(9)
+        o = np.zeros(12)
         self._L.Clpb_phaseTimes(self._h, _dp(o))
-        keys = ["chuzr", "btran", "price", "chuzc", "dualUpdate", "ftran", "update", "refactor", "samples"]
+        keys = ["chuzr", "btran", "price", "chuzc", "dualUpdate", "ftran", "update", "refactor", "samples",
+                "priceKernel", "ftranGemv", "btranGemv"]
         return dict(zip(keys, o.tolist()))
 
     def _vec(self, fn, size, dtype=np.float64):

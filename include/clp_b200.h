@@ -44,7 +44,8 @@ void Clpb_getProblem(Clpb_Simplex *model, int *start, int *index, double *value,
    Clp_setMaximumIterations :199, Clp_setMaximumSeconds :202, Clp_setLogLevel :314,
    ClpFactorization::maximumPivots (src/ClpFactorization.hpp:149).  Keys: "primalTolerance",
    "dualTolerance", "dualBound", "maximumIterations", "maximumSeconds", "logLevel",
-   "factorizationFrequency", "batch" (iterations enqueued per host sync), "timing" (0/1). */
+   "factorizationFrequency", "batch" (iterations enqueued per host sync), "timing" (0/1: per-phase
+   CUDA events, no graph replay), "useGraph" (0/1), "warmupIterations", "objectiveOffset". */
 int Clpb_setParameter(Clpb_Simplex *model, const char *key, double value);
 /* Clp_copyinStatus :280 : status[n+m], columns first */
 void Clpb_copyinStatus(Clpb_Simplex *model, const unsigned char *statusArray);
@@ -65,11 +66,15 @@ void Clpb_dualColumnSolution(Clpb_Simplex *model, double *reducedCost /* n */);
 void Clpb_dualRowSolution(Clpb_Simplex *model, double *rowPrice /* m */);
 void Clpb_statusArray(Clpb_Simplex *model, unsigned char *status /* n+m */);
 /* measurement: seconds in the iteration loop, kernels launched, per-phase device ms
-   (order: chuzr, btran, price, chuzc, dualUpdate, ftran, update, refactor, samples) */
+   (order: chuzr, btran, price, chuzc, dualUpdate, ftran, update, refactor, samples, then the
+   single kernels priceKernel, ftranGemv, btranGemv; 12 doubles) */
 double Clpb_secondsInLoop(Clpb_Simplex *model);
 long long Clpb_kernelLaunches(Clpb_Simplex *model);
-void Clpb_phaseTimes(Clpb_Simplex *model, double *out9);
+void Clpb_phaseTimes(Clpb_Simplex *model, double *out12);
 int Clpb_nucleusSize(Clpb_Simplex *model);
+/* CUDA-event time (on the engine's stream) and iteration count of the window that starts after
+   "warmupIterations" iterations and ends when Clpb_dual returns (refactorizations included) */
+void Clpb_timedWindow(Clpb_Simplex *model, double *milliseconds, int *iterations);
 
 /* column-sharded pricing across GPUs (one process per GPU).  ncclUniqueId (128 bytes) is
    created by rank 0 with Clpb_ncclUniqueId and shipped to the other ranks by the caller

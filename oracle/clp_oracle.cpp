@@ -328,6 +328,9 @@ struct DualSimplex {
   int threads = 1;
   double maximumSeconds = 1e30;
   int bucketedRatioTest = 0; // 1 = mimic the GPU's sort-free ratio test
+  int warmupIterations = 0;  // timed window starts after this many iterations
+  double timedSeconds = 0.0;
+  int timedIterations = 0;
   // results
   int problemStatus = -1;
   int numberIterations = 0, numberRefactorizations = 0;
@@ -724,8 +727,14 @@ int DualSimplex::dual()
     }
     pivotVariable = basics;
     for (int j = 0; j < nm; j++)
-      if (status[j] != ORC_basic)
+      if (status[j] != ORC_basic) {
+        // honour a user-supplied side (Clp_copyinStatus) when that bound exists
+        if (haveUserStatus && status[j] == ORC_atUpperBound && upper[j] < kInf)
+          sol[j] = upper[j];
+        else if (haveUserStatus && status[j] == ORC_atLowerBound && lower[j] > -kInf)
+          sol[j] = lower[j];
         setNonbasic(j);
+      }
   }
   fac.maximumPivots = factorizationFrequency > 0 ? factorizationFrequency
                                                  : defaultFactorizationFrequency();
@@ -741,7 +750,15 @@ int DualSimplex::dual()
   std::vector<unsigned char> candStat, candPassed;
   std::vector<int> flipList;
 
+  bool windowOpen = false;
+  auto tWindow = t0;
+  int windowStart = 0;
   while (problemStatus < 0) {
+    if (!windowOpen && numberIterations >= warmupIterations) {
+      windowOpen = true;
+      tWindow = std::chrono::steady_clock::now();
+      windowStart = numberIterations;
+    }
     if (numberIterations >= maximumIterations) {
       problemStatus = 3;
       break;
@@ -993,6 +1010,10 @@ int DualSimplex::dual()
       fprintf(stderr, "oracle: it %d obj %.10g infeas %g theta %g\n", numberIterations,
               computeObjective(), infeas, thetaDual);
   }
+  if (windowOpen) {
+    timedSeconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - tWindow).count();
+    timedIterations = numberIterations - windowStart;
+  }
   objectiveValue = computeObjective();
   secondsInLoop = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
   return problemStatus;
@@ -1067,6 +1088,8 @@ void orc_set_option(orc_model *h, const char *key, double value)
     s.threads = std::max(1, static_cast<int>(value));
   else if (k == "maximumSeconds")
     s.maximumSeconds = value;
+  else if (k == "warmupIterations")
+    s.warmupIterations = static_cast<int>(value);
   else if (k == "bucketedRatioTest")
     s.bucketedRatioTest = static_cast<int>(value);
 }
@@ -1080,6 +1103,8 @@ double orc_objective_value(const orc_model *h) { return h->s.objectiveValue; }
 int orc_number_iterations(const orc_model *h) { return h->s.numberIterations; }
 int orc_number_refactorizations(const orc_model *h) { return h->s.numberRefactorizations; }
 double orc_seconds_in_loop(const orc_model *h) { return h->s.secondsInLoop; }
+double orc_timed_seconds(const orc_model *h) { return h->s.timedSeconds; }
+int orc_timed_iterations(const orc_model *h) { return h->s.timedIterations; }
 void orc_get_column_solution(const orc_model *h, double *x)
 {
   std::copy(h->s.sol.begin(), h->s.sol.begin() + h->s.n, x);

@@ -47,6 +47,9 @@ double orc_objective_value(const orc_model *);
 int orc_number_iterations(const orc_model *);
 int orc_number_refactorizations(const orc_model *);
 double orc_seconds_in_loop(const orc_model *);
+/* window that starts after option "warmupIterations" iterations */
+double orc_timed_seconds(const orc_model *);
+int orc_timed_iterations(const orc_model *);
 /* iteration index and seconds at which the steady-state window began (after 1st refactor) */
 void orc_get_column_solution(const orc_model *, double *x);      /* n */
 void orc_get_row_activity(const orc_model *, double *y);         /* m */

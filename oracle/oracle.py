@@ -44,6 +44,9 @@ def lib():
         L.orc_number_refactorizations.argtypes = [ctypes.c_void_p]
         L.orc_seconds_in_loop.restype = ctypes.c_double
         L.orc_seconds_in_loop.argtypes = [ctypes.c_void_p]
+        L.orc_timed_seconds.restype = ctypes.c_double
+        L.orc_timed_seconds.argtypes = [ctypes.c_void_p]
+        L.orc_timed_iterations.argtypes = [ctypes.c_void_p]
         for f in ("orc_get_column_solution", "orc_get_row_activity", "orc_get_reduced_cost",
                   "orc_get_row_price"):
             getattr(L, f).argtypes = [ctypes.c_void_p, c_double_p]
@@ -117,6 +120,13 @@ class OracleSimplex:
     @property
     def seconds(self):
         return lib().orc_seconds_in_loop(self.h)
+
+    def timed_window(self):
+        return lib().orc_timed_seconds(self.h), lib().orc_timed_iterations(self.h)
+
+    def set_status(self, status):
+        st = np.ascontiguousarray(status, dtype=np.uint8)
+        lib().orc_set_status(self.h, _up(st))
 
     def _get(self, name, size):
         out = np.zeros(size)
