@@ -3,10 +3,12 @@
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload c2|c3|small]
 
-A *step* is one factorization cycle of the hot path: `cycle` dual simplex iterations (the
-reference's default ClpSimplex::defaultFactorizationFrequency, 275 for m = 10 000) plus the
-refactorization + recompute that ends the cycle.  W warm-up steps run untimed, then exactly
-K steps are timed with CUDA events on the engine's stream (max over ranks).
+A *step* is one factorization cycle of the hot path: `cycle` dual simplex iterations plus the
+refactorization + recompute (computePrimals/computeDuals) that ends the cycle.  `cycle` is the
+engine's default refactorization interval max(ClpSimplex::defaultFactorizationFrequency, m/5)
+= 2000 for m = 10 000 (an eta costs one 8m-byte panel column per solve here, a refactorization
+O(k^3) flops, so the optimum interval is longer than the reference's 275).  W warm-up steps run
+untimed, then exactly K steps are timed with CUDA events on the engine's stream (max over ranks).
 
 Workload (N = 1): BASELINE.json configs[1] -- synthetic random LP m=10k n=100k 1% nnz, fp64,
 dual steepest edge, no presolve / scaling / perturbation.  The timed window starts from a
@@ -46,9 +48,14 @@ WORKLOADS = {
 REF_ITERS_PER_STEP = 25
 
 
-def default_cycle(m):
+def clp_default_frequency(m):
     # ClpSimplex::defaultFactorizationFrequency (src/ClpSimplex.cpp:11401-11431)
     return min(10000, 75 + m // 50 if m < 10000 else 75 + 200 + (m - 10000) // 150)
+
+
+def default_cycle(m):
+    # Engine::setupDevice (clp_b200/csrc/engine.cu): max(Clp default, m/5), capped at 2048
+    return max(8, min(2048, max(clp_default_frequency(m), m // 5)))
 
 
 def build_workload(name):
@@ -150,7 +157,7 @@ def run_reference(args, lp, status, start, cycle):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=12)
+    ap.add_argument("--steps", type=int, default=8)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
@@ -246,7 +253,7 @@ def main():
 
     if rank == 0 and world == 1:
         # ---------------- per-kernel timing (CUDA events around single kernels, no graph replay)
-        p = new_model(batch=16, timing=1, maximumIterations=2 * cycle, factorizationFrequency=cycle)
+        p = new_model(batch=16, timing=1, maximumIterations=min(2 * cycle, 600), factorizationFrequency=cycle)
         p.dual()
         ph = p.phaseTimes()
         ns = max(1.0, ph["samples"])
@@ -273,7 +280,7 @@ def main():
                               "refactor_ms_total": ph["refactor"], "basic_structurals_at_start": nb}
         # ---------------- end to end through the C ABI with host buffers
         t0 = time.perf_counter()
-        e = new_model(batch=args.batch, maximumIterations=K * cycle, factorizationFrequency=cycle)
+        e = new_model(batch=args.batch, maximumIterations=min(K, 4) * cycle, factorizationFrequency=cycle)
         e.dual()
         x = e.primalColumnSolution(); e.dualRowSolution(); e.statusArray(); e.objectiveValue()
         wall = time.perf_counter() - t0
@@ -281,9 +288,9 @@ def main():
         h2d = (4 * (lp.n + 1) + 12 * lp.nnz) + (4 * (lp.m + 1) + 12 * lp.nnz) + 8 * 7 * nm + nm + 12 * lp.m
         d2h = 8 * 2 * nm + 8 * lp.m + nm + 4 * lp.m
         result["e2e"] = {"value": e.numberIterations() / wall, "unit": "iterations/s",
-                         "h2d_bytes_per_step": int(h2d / max(1, K)), "d2h_bytes_per_step": int(d2h / max(1, K)),
+                         "h2d_bytes_per_step": int(h2d / max(1, min(K, 4))), "d2h_bytes_per_step": int(d2h / max(1, min(K, 4))),
                          "includes": "Clpb_loadProblem (pageable host arrays -> HBM), basis hand-over, "
-                                     "Clpb_dual for K steps, solution read-back", "wall_s": wall,
+                                     "Clpb_dual for min(K,4) steps, solution read-back", "wall_s": wall,
                          "iterations": e.numberIterations()}
         # ---------------- CPU baseline: the oracle port on the host cores, bounded sample
         from oracle.oracle import OracleSimplex

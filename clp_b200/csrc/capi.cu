@@ -138,6 +138,8 @@ int Clpb_setParameter(Clpb_Simplex *model, const char *key, double value)
     e.timing = value != 0.0;
   else if (k == "warmupIterations")
     e.warmupIterations = (int)value;
+  else if (k == "usePriceTma")
+    e.usePriceTma = value != 0.0;
   else if (k == "useGraph")
     e.useGraph = value != 0.0;
   else if (k == "objectiveOffset")

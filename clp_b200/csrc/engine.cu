@@ -173,12 +173,42 @@ int Engine::setupDevice()
   p = dalloc<int>(n + 1);
   CUDA_OK(cudaMemcpy(p, hColStart.data(), sizeof(int) * (n + 1), cudaMemcpyHostToDevice));
   d.colStart = p;
-  p = dalloc<int>(nnz);
+  p = dalloc<int>(nnz + 16); // padding: TMA tiles are rounded to 16-byte granules
+  CUDA_OK(cudaMemset(p, 0, sizeof(int) * (nnz + 16)));
   CUDA_OK(cudaMemcpy(p, hRow.data(), sizeof(int) * nnz, cudaMemcpyHostToDevice));
   d.rowIdx = p;
-  q = dalloc<double>(nnz);
+  q = dalloc<double>(nnz + 16);
+  CUDA_OK(cudaMemset(q, 0, sizeof(double) * (nnz + 16)));
   CUDA_OK(cudaMemcpy(q, hVal.data(), sizeof(double) * nnz, cudaMemcpyHostToDevice));
   d.val = q;
+  {
+    // cut this rank's column range into tiles of whole columns, <= kPriceTile entries each
+    int per = (n + worldSize - 1) / worldSize;
+    int cb = worldSize > 1 ? std::min(n, rank * per) : 0;
+    int ce = worldSize > 1 ? std::min(n, cb + per) : n;
+    std::vector<int> tiles;
+    bool ok = true;
+    int c = cb;
+    while (c < ce && ok) {
+      tiles.push_back(c);
+      const int ea = hColStart[c] & ~3;
+      int c1 = c;
+      while (c1 < ce && c1 - c < kPriceTileCols && ((hColStart[c1 + 1] + 3) & ~3) - ea <= kPriceTile)
+        c1++;
+      if (c1 == c)
+        ok = false; // a single column does not fit a tile: fall back to the warp-per-column kernel
+      c = c1;
+    }
+    tiles.push_back(ce);
+    d.priceTileCol = nullptr;
+    d.numPriceTiles = 0;
+    if (ok && ce > cb && usePriceTma) {
+      int *pt = dalloc<int>(tiles.size());
+      CUDA_OK(cudaMemcpy(pt, tiles.data(), sizeof(int) * tiles.size(), cudaMemcpyHostToDevice));
+      d.priceTileCol = pt;
+      d.numPriceTiles = (int)tiles.size() - 1;
+    }
+  }
   p = dalloc<int>(m + 1);
   CUDA_OK(cudaMemcpy(p, rowStart.data(), sizeof(int) * (m + 1), cudaMemcpyHostToDevice));
   d.rowStart = p;
@@ -209,7 +239,11 @@ int Engine::setupDevice()
   d.nucCol = dalloc<int>(m);
   dS1RowStart = dalloc<int>(m + 1);
   d.s1RowStart = dS1RowStart;
-  tmax = factorizationFrequency > 0 ? factorizationFrequency : defaultFactorizationFrequency();
+  // Clp's default frequency balances its sparse FT update against a sparse refactorization; here
+  // an eta costs one extra 8m-byte panel column per solve while a refactorization costs O(k^3)
+  // flops, so the default cycle is longer (the accuracy gate still forces early refactorizations)
+  tmax = factorizationFrequency > 0 ? factorizationFrequency
+                                    : std::max(defaultFactorizationFrequency(), m / 5);
   tmax = std::max(8, std::min(tmax, 2048));
   d.tmax = roundUp(tmax, 8);
   d.W = dalloc<double>((size_t)m * d.tmax);
@@ -236,6 +270,8 @@ int Engine::setupDevice()
   CUDA_OK(cudaMemset(d.hist2Weight, 0, sizeof(unsigned long long) * kHist2Buckets));
   CUDA_OK(cudaMemset(d.hist2Min, 0xFF, sizeof(unsigned long long) * kHist2Buckets));
   d.flipList = dalloc<int>(nm);
+  d.flipBits = dalloc<unsigned int>((nm + 31) / 32 + 4);
+  CUDA_OK(cudaMemset(d.flipBits, 0, sizeof(unsigned int) * ((nm + 31) / 32 + 4)));
   d.st = dalloc<IterState>(1);
   d.fd = dalloc<FactorDesc>(1);
   CUDA_OK(cudaMemset(d.fd, 0, sizeof(FactorDesc)));
@@ -578,21 +614,22 @@ void Engine::enqueueIteration(bool timed, int slot)
     int per = (n + worldSize - 1) / worldSize;
     int c0 = std::min(n, rank * per), c1 = std::min(n, c0 + per);
     launch_price(d, c0, c1, false, stream);
+    launch_price_slacks(d, c0, c1, false, stream); // status mask / tolerance on the own shard
     // one exchange per pricing pass: all-gather of the row shards (padded to 'per' entries;
-    // the padding lands on the slack part, which is written afterwards)
+    // the padding lands on the slack part, which is rewritten afterwards)
     allGatherFn(ncclComm, d.alphaRow, sizeof(double) * per, stream);
-    launch_price_slacks(d, false, stream);
+    launch_price_slacks(d, 0, 0, false, stream);
     launch_histogram(d, stream);
   } else {
     launch_price(d, 0, n, true, stream);
-    launch_price_slacks(d, true, stream);
+    launch_price_slacks(d, 0, n, true, stream);
   }
   if (timed)
     cudaEventRecord(ev[3], stream);
   launch_chuzc(d, stream);
   if (timed)
     cudaEventRecord(ev[4], stream);
-  launch_dual_update_and_flips(d, dFlipFlag, stream);
+  launch_dual_update_and_flips(d, d.flipBits, stream);
   if (timed)
     cudaEventRecord(ev[5], stream);
   launch_ftran(d, 3, true, stream);

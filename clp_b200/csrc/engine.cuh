@@ -33,6 +33,10 @@ constexpr double kDevexTryNorm = 1.0e-4; // DEVEX_TRY_NORM ClpSimplex.hpp:2056
 constexpr int kHistBuckets = 32768;       // ratio-test histogram level 1: 11 exponent + 4 mantissa bits
 constexpr int kHist2Buckets = 4096;       // level 2: the next 12 mantissa bits inside the crossing bucket
 constexpr int kMaxFlips = 8192;
+constexpr int kPriceTile = 3072;          // entries per TMA-staged tile of the CSC arrays
+constexpr int kPriceStages = 3;           // tiles in flight per CTA
+constexpr int kPriceTileAlloc = kPriceTile + 8;
+constexpr int kPriceTileCols = 512;       // columns per tile (shared alpha buffer)
 
 // stop reasons written by the device into IterState.stop
 enum : int { STOP_NONE = 0, STOP_NO_ROW = 1, STOP_NO_COLUMN = 2, STOP_INACCURATE = 3,
@@ -93,6 +97,8 @@ struct DeviceModel {
   const int *rowStart;
   const int *colIdx;
   const double *rval;
+  const int *priceTileCol; // [numPriceTiles+1] first column of each price tile (this rank's range)
+  int numPriceTiles;
   // rim, length n+m (columns then rows, Clp order)
   double *cost, *costTrue, *lower, *upper, *lowerTrue, *upperTrue, *sol, *dj;
   unsigned char *status, *fake;
@@ -133,7 +139,8 @@ struct DeviceModel {
   unsigned long long *segTotal;   // [kHistBuckets/1024] per-segment totals of the level-1 scan
   int *segLast;                   // last non-empty bucket per segment
   unsigned int *scanCounter;      // last-block-done ticket
-  int *flipList;      // [kMaxFlips]
+  int *flipList;      // [n+m] flipped sequences of this iteration, ascending
+  unsigned int *flipBits; // [(n+m+31)/32] bit mask of the same (cleared by CHUZR)
   IterState *st;
   IterRecord *rec;    // ring of records (device)
   int recCap;
@@ -156,7 +163,7 @@ void launch_ftran_buffer(const DeviceModel &d, double *buf, int nrhs, bool apply
 void launch_btran_dense(const DeviceModel &d, double *vec, bool applyEtas, cudaStream_t s); // vec(m) in/out
 // price.cu
 void launch_price(const DeviceModel &d, int colBegin, int colEnd, bool fuseHistogram, cudaStream_t s);
-void launch_price_slacks(const DeviceModel &d, bool fuseHistogram, cudaStream_t s);
+void launch_price_slacks(const DeviceModel &d, int colBegin, int colEnd, bool fuseHistogram, cudaStream_t s);
 void launch_histogram(const DeviceModel &d, cudaStream_t s);
 void launch_transpose_times(const DeviceModel &d, const double *pi, double *z, double scalar,
                             cudaStream_t s);
@@ -165,7 +172,7 @@ void launch_times_rows(const DeviceModel &d, const double *x, double *y, double 
 void launch_chuzc(const DeviceModel &d, cudaStream_t s);
 // update.cu
 void launch_chuzr(const DeviceModel &d, cudaStream_t s);
-void launch_dual_update_and_flips(const DeviceModel &d, unsigned char *flipFlag, cudaStream_t s);
+void launch_dual_update_and_flips(const DeviceModel &d, unsigned int *flipBits, cudaStream_t s);
 void launch_pivot_updates(const DeviceModel &d, cudaStream_t s);
 void launch_make_dual_feasible(const DeviceModel &d, double dualBound, int *counters, cudaStream_t s);
 void launch_compute_primals(const DeviceModel &d, double *xn, double *rhs, cudaStream_t s);

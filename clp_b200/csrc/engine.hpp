@@ -41,6 +41,7 @@ public:
   int batch = 16;                 // iterations enqueued per host synchronisation
   bool timing = false;
   bool useGraph = true;
+  bool usePriceTma = true;        // TMA-staged price kernel (false: warp-per-column kernel)
   int warmupIterations = 0;       // device-timed window starts once this many iterations ran
   double timedMilliseconds = 0.0; // CUDA-event time of the window (iterations + refactorizations)
   int timedIterations = 0;

@@ -166,6 +166,149 @@ __global__ void __launch_bounds__(512) price_kernel(DeviceModel d, int colBegin,
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// PRICE, TMA-staged variant.  The CSC arrays are cut into tiles of whole columns with at most
+// kPriceTile entries (host, once per matrix).  A persistent CTA per SM walks its tiles with a
+// two-stage pipeline: one thread issues cp.async.bulk (TMA, 1-D) copies of the tile's row
+// indices and values into shared memory, completion is signalled on an mbarrier; the CTA then
+// multiplies by rho (staged in shared memory), reduces per column from shared memory and does
+// the ratio-test candidate logic for all columns of the tile in parallel.
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count)
+{
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes)
+{
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar)
+{
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
+{
+  asm volatile("{\n"
+               ".reg .pred p;\n"
+               "WAIT_LOOP:\n"
+               "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+               "@p bra WAIT_DONE;\n"
+               "bra WAIT_LOOP;\n"
+               "WAIT_DONE:\n"
+               "}\n" ::"r"(smem_u32(bar)),
+               "r"(parity)
+               : "memory");
+}
+
+template <bool SMEM_RHO>
+__global__ void __launch_bounds__(1024, 1)
+    price_tma_kernel(DeviceModel d, const int *__restrict__ tileCol, int ntiles)
+{
+  extern __shared__ __align__(128) unsigned char smemRaw[];
+  if (!iter_active(d.st))
+    return;
+  // layout: barriers | scol[stage][kPriceTileCols+8] | sidx[stage] | sval[stage] | srho
+  unsigned long long *full = reinterpret_cast<unsigned long long *>(smemRaw);
+  int *scol = reinterpret_cast<int *>(smemRaw + 128);
+  int *sidx = scol + kPriceStages * (kPriceTileCols + 8);
+  double *sval = reinterpret_cast<double *>(sidx + kPriceStages * kPriceTileAlloc);
+  double *srho = sval + kPriceStages * kPriceTileAlloc;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int *__restrict__ colStart = d.colStart;
+  auto issue = [&](int t, int stage) {
+    const int c0 = tileCol[t], c1 = tileCol[t + 1];
+    const int ea = colStart[c0] & ~3;
+    const int eb = (colStart[c1] + 3) & ~3;
+    const unsigned cnt = (unsigned)(eb - ea);
+    mbar_expect_tx(&full[stage], cnt * 12u);
+    bulk_g2s(sidx + stage * kPriceTileAlloc, d.rowIdx + ea, cnt * 4u, &full[stage]);
+    bulk_g2s(sval + stage * kPriceTileAlloc, d.val + ea, cnt * 8u, &full[stage]);
+  };
+  if (tid == 0) {
+    for (int q = 0; q < kPriceStages; q++)
+      mbar_init(&full[q], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    for (int q = 0; q < kPriceStages; q++)
+      if ((int)(blockIdx.x + q * gridDim.x) < ntiles)
+        issue(blockIdx.x + q * gridDim.x, q);
+  }
+  if (SMEM_RHO)
+    for (int i = tid; i < d.m; i += 1024)
+      srho[i] = d.rho[i];
+  __syncthreads();
+  const double *__restrict__ rho = d.rho;
+  int it = 0;
+  for (int t = blockIdx.x; t < ntiles; t += gridDim.x, it++) {
+    const int stage = it % kPriceStages;
+    const int c0 = tileCol[t], c1 = tileCol[t + 1];
+    const int ncol = c1 - c0;
+    int *sc = scol + stage * (kPriceTileCols + 8);
+    if (tid <= ncol)
+      sc[tid] = colStart[c0 + tid]; // overlaps with the wait / product phase
+    const int ea = colStart[c0] & ~3;
+    const int cnt = ((colStart[c1] + 3) & ~3) - ea;
+    mbar_wait(&full[stage], (unsigned)((it / kPriceStages) & 1));
+    double *v = sval + stage * kPriceTileAlloc;
+    const int *ix = sidx + stage * kPriceTileAlloc;
+    for (int e = tid; e < cnt; e += 1024) {
+      const int r = ix[e];
+      v[e] *= SMEM_RHO ? srho[r] : __ldg(rho + r);
+    }
+    __syncthreads();
+    for (int c = warp; c < ncol; c += 32) {
+      const int s1 = sc[c + 1] - ea;
+      double acc = 0.0;
+      for (int e = sc[c] - ea + lane; e < s1; e += 32)
+        acc += v[e];
+      acc = warp_sum(acc);
+      if (lane == 0)
+        d.alphaRow[c0 + c] = acc; // raw dot product; row_finalize_kernel applies status/tolerance
+    }
+    __syncthreads();
+    if (tid == 0) {
+      const int next = t + kPriceStages * gridDim.x;
+      if (next < ntiles) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        issue(next, stage);
+      }
+    }
+  }
+}
+
+// Second half of PRICE: one thread per variable of the row.  Columns: apply the status mask and
+// the zero tolerance to the raw dot products; rows: alpha_{n+i} = -rho_i; both: ratio-test
+// candidate test + level-1 histogram (coalesced reads of status / dj / bounds).
+__global__ void row_finalize_kernel(DeviceModel d, int colBegin, int colEnd, bool fuseHist)
+{
+  if (!iter_active(d.st))
+    return;
+  const int sigma = d.st->sigma;
+  const double infeas = d.st->infeas;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < d.nm; j += gridDim.x * blockDim.x) {
+    double alpha;
+    const unsigned char st = d.status[j];
+    if (j < d.n) {
+      if (j < colBegin || j >= colEnd)
+        continue;
+      alpha = (st == basic || st == isFixed) ? 0.0 : d.alphaRow[j];
+    } else {
+      alpha = (st == basic || st == isFixed) ? 0.0 : -d.rho[j - d.n];
+    }
+    if (fabs(alpha) < d.zeroTolerance)
+      alpha = 0.0;
+    d.alphaRow[j] = alpha;
+    double a, dtil, range;
+    bool boxed;
+    if (fuseHist && alpha != 0.0 && candidate(d, j, alpha, sigma, a, dtil, boxed, range))
+      histogram_add(d, a, dtil, boxed, range, infeas);
+  }
+}
+
 // slack part of the row: alpha_{n+i} = -rho_i for nonbasic rows
 __global__ void price_slack_kernel(DeviceModel d, bool fuseHist)
 {
@@ -220,33 +363,55 @@ void launch_price(const DeviceModel &d, int colBegin, int colEnd, bool fuseHist,
   int ncol = colEnd - colBegin;
   if (ncol <= 0)
     return;
-  const size_t smemBytes = sizeof(double) * (size_t)d.m;
+  const size_t rhoBytes = sizeof(double) * (size_t)d.m;
   static bool attrSet = false;
   if (!attrSet) {
     cudaFuncSetAttribute(price_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    cudaFuncSetAttribute(price_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(price_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     attrSet = true;
   }
-  const int nUnits = (ncol + 7) / 8;
   if (g_kernelTimers)
     cudaEventRecord(g_kernelTimers->price[0], s);
-  if (smemBytes <= 220 * 1024) {
-    const int ctasPerSm = smemBytes <= 110 * 1024 ? 2 : 1;
-    int blocks = 148 * ctasPerSm;
-    if (blocks * 16 > nUnits)
-      blocks = (nUnits + 15) / 16;
-    price_kernel<true><<<blocks, 512, smemBytes, s>>>(d, colBegin, colEnd, fuseHist);
+  const size_t tileBytes = 128 + (size_t)kPriceStages * ((kPriceTileCols + 8) * 4 + (size_t)kPriceTileAlloc * 12);
+  if (d.priceTileCol != nullptr && d.numPriceTiles > 0) {
+    // TMA-staged tiles (tiles were cut for this rank's column range at set-up)
+    int blocks = d.numPriceTiles < 148 ? d.numPriceTiles : 148;
+    if (tileBytes + rhoBytes <= 227 * 1024)
+      price_tma_kernel<true><<<blocks, 1024, tileBytes + rhoBytes, s>>>(d, d.priceTileCol, d.numPriceTiles);
+    else
+      price_tma_kernel<false><<<blocks, 1024, tileBytes, s>>>(d, d.priceTileCol, d.numPriceTiles);
   } else {
-    int blocks = 148 * 4;
-    if (blocks * 16 > nUnits)
-      blocks = (nUnits + 15) / 16;
-    price_kernel<false><<<blocks, 512, 0, s>>>(d, colBegin, colEnd, fuseHist);
+    const int nUnits = (ncol + 7) / 8;
+    if (rhoBytes <= 220 * 1024) {
+      const int ctasPerSm = rhoBytes <= 110 * 1024 ? 2 : 1;
+      int blocks = 148 * ctasPerSm;
+      if (blocks * 16 > nUnits)
+        blocks = (nUnits + 15) / 16;
+      price_kernel<true><<<blocks, 512, rhoBytes, s>>>(d, colBegin, colEnd, fuseHist);
+    } else {
+      int blocks = 148 * 4;
+      if (blocks * 16 > nUnits)
+        blocks = (nUnits + 15) / 16;
+      price_kernel<false><<<blocks, 512, 0, s>>>(d, colBegin, colEnd, fuseHist);
+    }
   }
   if (g_kernelTimers)
     cudaEventRecord(g_kernelTimers->price[1], s);
 }
-void launch_price_slacks(const DeviceModel &d, bool fuseHist, cudaStream_t s)
+// slack part of the row (+ status mask / histogram for the columns when the TMA kernel ran).
+// colBegin/colEnd: the column range this rank priced; fuseHist=false in column-sharded runs,
+// where the histogram is built after the all-gather by launch_histogram.
+void launch_price_slacks(const DeviceModel &d, int colBegin, int colEnd, bool fuseHist, cudaStream_t s)
 {
-  price_slack_kernel<<<(d.m + 255) / 256, 256, 0, s>>>(d, fuseHist);
+  if (d.priceTileCol != nullptr && d.numPriceTiles > 0) {
+    int blocks = (d.nm + 255) / 256;
+    if (blocks > 148 * 8)
+      blocks = 148 * 8;
+    row_finalize_kernel<<<blocks, 256, 0, s>>>(d, colBegin, colEnd, fuseHist);
+  } else {
+    price_slack_kernel<<<(d.m + 255) / 256, 256, 0, s>>>(d, fuseHist);
+  }
 }
 
 // ---------------------------------------------------------------------------------------

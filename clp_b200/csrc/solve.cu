@@ -54,7 +54,9 @@ __global__ void gather_nucleus_kernel(DeviceModel d, const double *__restrict__ 
   }
 }
 
-// y[c][i] = sum_j M[i][j] * x[c][j]   (M row-major k x ldk, one warp per row)
+// y[c][i] = sum_j M[i][j] * x[c][j]   (M row-major k x ldk).  One CTA streams one row at a time:
+// every thread issues four 16-byte loads back to back, so a CTA keeps 16 KB of one contiguous
+// row in flight (long DRAM streams, one per resident CTA).
 // if outIndex != nullptr the result is scattered: out[c*ostride + outIndex[i]]
 template <int NRHS>
 __global__ void __launch_bounds__(256)
@@ -64,38 +66,60 @@ __global__ void __launch_bounds__(256)
 {
   if (checkState && !iter_active(st))
     return;
+  __shared__ double part[8][NRHS];
   const int k = fd->k, ldk = fd->ldk;
   const double *__restrict__ M = transposed ? fd->NinvT : fd->Ninv;
-  const int warpsPerBlock = blockDim.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const int warp = threadIdx.x >> 5;
-  for (int i = blockIdx.x * warpsPerBlock + warp; i < k; i += gridDim.x * warpsPerBlock) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int half = ldk >> 1; // ldk is a multiple of 8, padding is zero
+  for (int i = blockIdx.x; i < k; i += gridDim.x) {
     const double2 *row = reinterpret_cast<const double2 *>(M + (size_t)i * ldk);
     double acc[NRHS];
 #pragma unroll
     for (int c = 0; c < NRHS; c++)
       acc[c] = 0.0;
-    const int half = ldk >> 1; // ldk is a multiple of 8, padding is zero
-#pragma unroll 4
-    for (int j = lane; j < half; j += 32) {
-      double2 a = __ldg(row + j);
+    for (int j = threadIdx.x; j < half; j += 1024) {
+      const double2 z2 = make_double2(0.0, 0.0);
+      const int j1 = j + 256, j2 = j + 512, j3 = j + 768;
+      const double2 a0 = __ldcs(row + j);
+      const double2 a1 = j1 < half ? __ldcs(row + j1) : z2;
+      const double2 a2 = j2 < half ? __ldcs(row + j2) : z2;
+      const double2 a3 = j3 < half ? __ldcs(row + j3) : z2;
 #pragma unroll
       for (int c = 0; c < NRHS; c++) {
-        const double2 xv = __ldg(reinterpret_cast<const double2 *>(x + (size_t)c * ldk) + j);
-        acc[c] = fma(a.x, xv.x, acc[c]);
-        acc[c] = fma(a.y, xv.y, acc[c]);
+        const double2 *xc = reinterpret_cast<const double2 *>(x + (size_t)c * ldk);
+        const double2 x0 = __ldg(xc + j);
+        const double2 x1 = j1 < half ? __ldg(xc + j1) : z2;
+        const double2 x2 = j2 < half ? __ldg(xc + j2) : z2;
+        const double2 x3 = j3 < half ? __ldg(xc + j3) : z2;
+        acc[c] = fma(a0.x, x0.x, acc[c]);
+        acc[c] = fma(a0.y, x0.y, acc[c]);
+        acc[c] = fma(a1.x, x1.x, acc[c]);
+        acc[c] = fma(a1.y, x1.y, acc[c]);
+        acc[c] = fma(a2.x, x2.x, acc[c]);
+        acc[c] = fma(a2.y, x2.y, acc[c]);
+        acc[c] = fma(a3.x, x3.x, acc[c]);
+        acc[c] = fma(a3.y, x3.y, acc[c]);
       }
     }
 #pragma unroll
     for (int c = 0; c < NRHS; c++)
       acc[c] = warp_sum(acc[c]);
     if (lane == 0) {
-      int o = outIndex ? outIndex[i] : i;
-      const int os = ostride < 0 ? ldk : ostride;
 #pragma unroll
       for (int c = 0; c < NRHS; c++)
-        out[(size_t)c * os + o] = acc[c];
+        part[warp][c] = acc[c];
     }
+    __syncthreads();
+    if (threadIdx.x < NRHS) {
+      double sum = 0.0;
+#pragma unroll
+      for (int w = 0; w < 8; w++)
+        sum += part[w][threadIdx.x];
+      const int o = outIndex ? outIndex[i] : i;
+      const int os = ostride < 0 ? ldk : ostride;
+      out[(size_t)threadIdx.x * os + o] = sum;
+    }
+    __syncthreads();
   }
 }
 
@@ -224,9 +248,7 @@ static void ftran_impl(const DeviceModel &d, double *b, bool applyEtas, bool che
     gblocks = 148;
   double *xg = d.ywork + (size_t)3 * roundUp8(maxk);
   gather_nucleus_kernel<<<gblocks, 256, 0, s>>>(d, b, m, xg, NRHS, checkState);
-  int blocks = (maxk + 7) / 8;
-  if (blocks > 148 * 8)
-    blocks = 148 * 8;
+  int blocks = maxk < 148 * 6 ? maxk : 148 * 6;
   if (g_kernelTimers && checkState)
     cudaEventRecord(g_kernelTimers->ftranGemv[0], s);
   gemv_rows_kernel<NRHS><<<blocks, 256, 0, s>>>(d.fd, 0, xg, d.ywork, -1, nullptr, d.st, checkState);
@@ -361,10 +383,11 @@ __global__ void btran_s_kernel(DeviceModel d, bool checkState)
 
 static void btran_tail(const DeviceModel &d, double *rhoOut, bool checkState, cudaStream_t s)
 {
-  int blocks = (d.m + 7) / 8;
-  if (blocks > 148 * 8)
-    blocks = 148 * 8;
-  btran_s_kernel<<<blocks, 256, 0, s>>>(d, checkState);
+  int sblocks = (d.m + 7) / 8;
+  if (sblocks > 148 * 8)
+    sblocks = 148 * 8;
+  btran_s_kernel<<<sblocks, 256, 0, s>>>(d, checkState);
+  int blocks = d.m < 148 * 6 ? d.m : 148 * 6;
   if (g_kernelTimers && checkState)
     cudaEventRecord(g_kernelTimers->btranGemv[0], s);
   gemv_rows_kernel<1><<<blocks, 256, 0, s>>>(d.fd, 1, d.swork, rhoOut, d.m, d.nucRow, d.st,

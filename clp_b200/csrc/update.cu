@@ -34,6 +34,8 @@ __global__ void chuzr_kernel(DeviceModel d)
       d.hist2Min[b] = 0xFFFFFFFFFFFFFFFFull;
     }
   }
+  for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < ((d.nm + 31) >> 5); w += gridDim.x * blockDim.x)
+    d.flipBits[w] = 0u;
   for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < d.m; p += gridDim.x * blockDim.x) {
     const int seq = d.pivotVariable[p];
     const double v = d.sol[seq];
@@ -104,7 +106,7 @@ void launch_chuzr(const DeviceModel &d, cudaStream_t s)
 // dj -= thetaDual * sigma * alpha over the pivot row; variables whose dj changes sign flip to
 // the other bound when boxed, otherwise their cost is shifted (ClpSimplexDual.cpp:4705-4772).
 // flipFlag[j] (stored in d.fake's neighbour array, see engine.cu) marks flipped variables.
-__global__ void dual_update_kernel(DeviceModel d, unsigned char *__restrict__ flipFlag)
+__global__ void dual_update_kernel(DeviceModel d, unsigned int *__restrict__ flipBits)
 {
   if (!iter_active(d.st))
     return;
@@ -113,7 +115,6 @@ __global__ void dual_update_kernel(DeviceModel d, unsigned char *__restrict__ fl
   const int seqIn = d.st->seqIn;
   const double tol = d.dualTolerance;
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < d.nm; j += gridDim.x * blockDim.x) {
-    unsigned char flag = 0;
     const double alpha = d.alphaRow[j];
     if (alpha != 0.0 && j != seqIn) {
       const unsigned char st = d.status[j];
@@ -130,7 +131,7 @@ __global__ void dual_update_kernel(DeviceModel d, unsigned char *__restrict__ fl
               d.status[j] = atLowerBound;
               d.sol[j] = lo;
             }
-            flag = 1;
+            atomicOr(flipBits + (j >> 5), 1u << (j & 31));
           } else {
             d.cost[j] -= dnew;
             dnew = 0.0;
@@ -144,31 +145,31 @@ __global__ void dual_update_kernel(DeviceModel d, unsigned char *__restrict__ fl
         d.dj[j] = dnew;
       }
     }
-    flipFlag[j] = flag;
   }
 }
 
-// single CTA: ordered compaction of flipFlag into flipList (ascending sequence => fixed order)
+// single CTA: ordered expansion of the flip bit mask into flipList (ascending sequence => the
+// flip right-hand side is summed in a fixed order)
 __global__ void __launch_bounds__(1024) flip_collect_kernel(DeviceModel d,
-                                                           const unsigned char *__restrict__ flipFlag)
+                                                           const unsigned int *__restrict__ flipBits)
 {
   if (!iter_active(d.st))
     return;
   __shared__ int warpCount[32];
   __shared__ int base;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nwords = (d.nm + 31) >> 5;
   if (tid == 0)
     base = 0;
   __syncthreads();
-  for (int start = 0; start < d.nm; start += 1024 * 8) {
-    // each thread owns 8 consecutive flags
-    const int j0 = start + tid * 8;
+  for (int start = 0; start < nwords; start += 1024 * 4) {
+    unsigned int w[4];
     int cnt = 0;
-    unsigned char f[8];
 #pragma unroll
-    for (int q = 0; q < 8; q++) {
-      f[q] = (j0 + q < d.nm) ? flipFlag[j0 + q] : 0;
-      cnt += f[q];
+    for (int q = 0; q < 4; q++) {
+      const int wi = start + tid * 4 + q;
+      w[q] = wi < nwords ? flipBits[wi] : 0u;
+      cnt += __popc(w[q]);
     }
     int inc = cnt;
 #pragma unroll
@@ -181,17 +182,23 @@ __global__ void __launch_bounds__(1024) flip_collect_kernel(DeviceModel d,
       warpCount[warp] = inc;
     __syncthreads();
     int off = base + inc - cnt;
-    for (int w = 0; w < warp; w++)
-      off += warpCount[w];
+    for (int q = 0; q < warp; q++)
+      off += warpCount[q];
 #pragma unroll
-    for (int q = 0; q < 8; q++)
-      if (f[q])
-        d.flipList[off++] = j0 + q;
+    for (int q = 0; q < 4; q++) {
+      unsigned int bits = w[q];
+      const int j0 = (start + tid * 4 + q) << 5;
+      while (bits) {
+        const int b = __ffs(bits) - 1;
+        bits &= bits - 1;
+        d.flipList[off++] = j0 + b;
+      }
+    }
     __syncthreads();
     if (tid == 1023) {
       int tot = 0;
-      for (int w = 0; w < 32; w++)
-        tot += warpCount[w];
+      for (int q = 0; q < 32; q++)
+        tot += warpCount[q];
       base += tot;
     }
     __syncthreads();
@@ -264,22 +271,30 @@ __global__ void __launch_bounds__(256) build_rhs3_kernel(DeviceModel d)
 }
 
 // Many flips: rhs3[2][i] = -sum_j a_ij delta_j over flipped j, one warp per row of the CSR copy
-// (streams the column indices once, 4 B per nonzero; fixed summation order).
+// (streams the column indices once, 4 B per nonzero; fixed summation order).  The flip bit mask
+// (n+m bits) is staged in shared memory so the per-entry test costs no global gather.
 __global__ void __launch_bounds__(256)
-    flip_rhs_rows_kernel(DeviceModel d, const unsigned char *__restrict__ flipFlag)
+    flip_rhs_rows_kernel(DeviceModel d, const unsigned int *__restrict__ flipBits)
 {
+  extern __shared__ unsigned int sbits[];
   if (!iter_active(d.st))
     return;
   if (d.st->numFlips <= kFlipScanLimit)
     return;
+  const int nwords = (d.nm + 31) >> 5;
+  for (int i = threadIdx.x; i < nwords; i += blockDim.x)
+    sbits[i] = flipBits[i];
+  __syncthreads();
   const int lane = threadIdx.x & 31;
   const int warpsPerBlock = blockDim.x >> 5;
   for (int i = blockIdx.x * warpsPerBlock + (threadIdx.x >> 5); i < d.m;
        i += gridDim.x * warpsPerBlock) {
     double acc = 0.0;
-    for (int e = d.rowStart[i] + lane; e < d.rowStart[i + 1]; e += 32) {
-      const int j = __ldg(d.colIdx + e);
-      if (flipFlag[j]) {
+    const int e1 = d.rowStart[i + 1];
+#pragma unroll 4
+    for (int e = d.rowStart[i] + lane; e < e1; e += 32) {
+      const int j = __ldcs(d.colIdx + e);
+      if ((sbits[j >> 5] >> (j & 31)) & 1u) {
         const double range = d.upper[j] - d.lower[j];
         const double delta = d.status[j] == atUpperBound ? range : -range;
         acc = fma(-delta, d.rval[e], acc);
@@ -290,7 +305,7 @@ __global__ void __launch_bounds__(256)
       acc += __shfl_xor_sync(0xffffffffu, acc, o);
     if (lane == 0) {
       const int js = d.n + i;
-      if (flipFlag[js]) {
+      if ((sbits[js >> 5] >> (js & 31)) & 1u) {
         const double range = d.upper[js] - d.lower[js];
         acc += d.status[js] == atUpperBound ? range : -range;
       }
@@ -299,19 +314,25 @@ __global__ void __launch_bounds__(256)
   }
 }
 
-void launch_dual_update_and_flips(const DeviceModel &d, unsigned char *flipFlag, cudaStream_t s)
+void launch_dual_update_and_flips(const DeviceModel &d, unsigned int *flipBits, cudaStream_t s)
 {
   int blocks = (d.nm + 255) / 256;
   if (blocks > 148 * 8)
     blocks = 148 * 8;
-  dual_update_kernel<<<blocks, 256, 0, s>>>(d, flipFlag);
-  flip_collect_kernel<<<1, 1024, 0, s>>>(d, flipFlag);
+  dual_update_kernel<<<blocks, 256, 0, s>>>(d, flipBits);
+  flip_collect_kernel<<<1, 1024, 0, s>>>(d, flipBits);
   build_rhs3_kernel<<<(d.m + 255) / 256, 256, 0, s>>>(d);
   {
     int rb = (d.m + 7) / 8;
-    if (rb > 148 * 16)
-      rb = 148 * 16;
-    flip_rhs_rows_kernel<<<rb, 256, 0, s>>>(d, flipFlag);
+    if (rb > 148 * 8)
+      rb = 148 * 8;
+    const size_t sb = sizeof(unsigned int) * (size_t)((d.nm + 31) >> 5);
+    static bool attrSet = false;
+    if (!attrSet) {
+      cudaFuncSetAttribute(flip_rhs_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      attrSet = true;
+    }
+    flip_rhs_rows_kernel<<<rb, 256, sb, s>>>(d, flipBits);
   }
 }
 

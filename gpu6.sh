@@ -1,0 +1,16 @@
+cd $GRAFT_REPO_ROOT; mkdir -p gpurun_out
+export PATH=$PATH:/usr/local/cuda/bin
+timeout 1500 python -m pytest tests -m gpu -q --timeout 300 -x 2>&1 | tail -30 > gpurun_out/pytest_gpu.log; tail -6 gpurun_out/pytest_gpu.log
+timeout 900 python bench.py --steps 4 --warmup 3 > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err; python - <<'PY'
+import json
+try:
+    r=json.load(open('gpurun_out/bench_n1.json'))
+    print({k:r[k] for k in ('value','ms_per_step','gpu_launches')}, r['config']['timed_iterations'], r['config']['nucleus_size'])
+    print(r['roofline']['all']); print(r['roofline']['phase_us_per_iteration'], r['roofline']['refactor_ms_total'])
+    print(r['e2e']['value'], r['cpu_baseline']['value'])
+except Exception as e: print('bench parse fail', e)
+PY
+tail -3 gpurun_out/bench_n1.err
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k 'regex:^(?!lu_|trsm|gemm_sub|set_perm|transpose|zero_pad|gather_nucleus_matrix).*' -s 60 -c 300 --csv --log-file gpurun_out/launches_c2.csv python tests/ncu_target.py c2 24 > gpurun_out/ncu1.log 2>&1; tail -1 gpurun_out/ncu1.log
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:price_tma -s 6 -c 1 -o gpurun_out/prof_price -f python tests/ncu_target.py c2 12 > gpurun_out/ncu2.log 2>&1; tail -1 gpurun_out/ncu2.log
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:gemv_rows -s 12 -c 2 -o gpurun_out/prof_gemv -f python tests/ncu_target.py c2 12 > gpurun_out/ncu3.log 2>&1; tail -1 gpurun_out/ncu3.log
