@@ -202,11 +202,21 @@ int Engine::setupDevice()
     tiles.push_back(ce);
     d.priceTileCol = nullptr;
     d.numPriceTiles = 0;
-    if (ok && ce > cb && usePriceTma) {
-      int *pt = dalloc<int>(tiles.size());
-      CUDA_OK(cudaMemcpy(pt, tiles.data(), sizeof(int) * tiles.size(), cudaMemcpyHostToDevice));
+    const int ntl = (int)tiles.size() - 1;
+    if (ok && ce > cb && usePriceTma && (ntl + 147) / 148 <= kPriceMaxTilesPerCta) {
+      std::vector<int> desc((size_t)ntl * 4);
+      for (int t = 0; t < ntl; t++) {
+        const int t0 = tiles[t], t1 = tiles[t + 1];
+        const int ea = hColStart[t0] & ~3;
+        desc[4 * t + 0] = t0;
+        desc[4 * t + 1] = t1 - t0;
+        desc[4 * t + 2] = ea;
+        desc[4 * t + 3] = ((hColStart[t1] + 3) & ~3) - ea;
+      }
+      int *pt = dalloc<int>(desc.size());
+      CUDA_OK(cudaMemcpy(pt, desc.data(), sizeof(int) * desc.size(), cudaMemcpyHostToDevice));
       d.priceTileCol = pt;
-      d.numPriceTiles = (int)tiles.size() - 1;
+      d.numPriceTiles = ntl;
     }
   }
   p = dalloc<int>(m + 1);

@@ -35,6 +35,7 @@ constexpr int kHist2Buckets = 4096;       // level 2: the next 12 mantissa bits 
 constexpr int kMaxFlips = 8192;
 constexpr int kPriceTile = 3072;          // entries per TMA-staged tile of the CSC arrays
 constexpr int kPriceStages = 3;           // tiles in flight per CTA
+constexpr int kPriceMaxTilesPerCta = 1024; // descriptors staged in shared memory per CTA
 constexpr int kPriceTileAlloc = kPriceTile + 8;
 constexpr int kPriceTileCols = 512;       // columns per tile (shared alpha buffer)
 
@@ -97,7 +98,7 @@ struct DeviceModel {
   const int *rowStart;
   const int *colIdx;
   const double *rval;
-  const int *priceTileCol; // [numPriceTiles+1] first column of each price tile (this rank's range)
+  const int *priceTileCol; // [numPriceTiles] int4 descriptors {firstCol, nCols, firstEntry, nEntries}
   int numPriceTiles;
   // rim, length n+m (columns then rows, Clp order)
   double *cost, *costTrue, *lower, *upper, *lowerTrue, *upperTrue, *sol, *dj;

@@ -204,54 +204,57 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned pari
                : "memory");
 }
 
+// tile descriptor (host-built): first column, number of columns, first entry (multiple of 4),
+// number of entries (multiple of 4)
 template <bool SMEM_RHO>
 __global__ void __launch_bounds__(1024, 1)
-    price_tma_kernel(DeviceModel d, const int *__restrict__ tileCol, int ntiles)
+    price_tma_kernel(DeviceModel d, const int4 *__restrict__ tileDesc, int ntiles, int descCap)
 {
   extern __shared__ __align__(128) unsigned char smemRaw[];
   if (!iter_active(d.st))
     return;
-  // layout: barriers | scol[stage][kPriceTileCols+8] | sidx[stage] | sval[stage] | srho
+  // layout: barriers | sdesc[descCap] | scol[stage][kPriceTileCols+8] | sidx | sval | srho
   unsigned long long *full = reinterpret_cast<unsigned long long *>(smemRaw);
-  int *scol = reinterpret_cast<int *>(smemRaw + 128);
+  int4 *sdesc = reinterpret_cast<int4 *>(smemRaw + 128);
+  int *scol = reinterpret_cast<int *>(smemRaw + 128 + descCap * 16);
   int *sidx = scol + kPriceStages * (kPriceTileCols + 8);
   double *sval = reinterpret_cast<double *>(sidx + kPriceStages * kPriceTileAlloc);
   double *srho = sval + kPriceStages * kPriceTileAlloc;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int *__restrict__ colStart = d.colStart;
-  auto issue = [&](int t, int stage) {
-    const int c0 = tileCol[t], c1 = tileCol[t + 1];
-    const int ea = colStart[c0] & ~3;
-    const int eb = (colStart[c1] + 3) & ~3;
-    const unsigned cnt = (unsigned)(eb - ea);
-    mbar_expect_tx(&full[stage], cnt * 12u);
-    bulk_g2s(sidx + stage * kPriceTileAlloc, d.rowIdx + ea, cnt * 4u, &full[stage]);
-    bulk_g2s(sval + stage * kPriceTileAlloc, d.val + ea, cnt * 8u, &full[stage]);
-  };
+  // this CTA's tiles: blockIdx.x, blockIdx.x + gridDim.x, ...  (descriptors staged once)
+  const int myTiles = ((int)blockIdx.x < ntiles) ? (ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  if (tid < myTiles)
+    sdesc[tid] = tileDesc[blockIdx.x + tid * gridDim.x];
   if (tid == 0) {
     for (int q = 0; q < kPriceStages; q++)
       mbar_init(&full[q], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    for (int q = 0; q < kPriceStages; q++)
-      if ((int)(blockIdx.x + q * gridDim.x) < ntiles)
-        issue(blockIdx.x + q * gridDim.x, q);
   }
+  __syncthreads();
+  auto issue = [&](int i, int stage) {
+    const int4 ds = sdesc[i];
+    const unsigned cnt = (unsigned)ds.w;
+    mbar_expect_tx(&full[stage], cnt * 12u);
+    bulk_g2s(sidx + stage * kPriceTileAlloc, d.rowIdx + ds.z, cnt * 4u, &full[stage]);
+    bulk_g2s(sval + stage * kPriceTileAlloc, d.val + ds.z, cnt * 8u, &full[stage]);
+  };
+  if (tid == 0)
+    for (int q = 0; q < kPriceStages && q < myTiles; q++)
+      issue(q, q);
   if (SMEM_RHO)
     for (int i = tid; i < d.m; i += 1024)
       srho[i] = d.rho[i];
   __syncthreads();
   const double *__restrict__ rho = d.rho;
-  int it = 0;
-  for (int t = blockIdx.x; t < ntiles; t += gridDim.x, it++) {
+  for (int it = 0; it < myTiles; it++) {
     const int stage = it % kPriceStages;
-    const int c0 = tileCol[t], c1 = tileCol[t + 1];
-    const int ncol = c1 - c0;
+    const int4 ds = sdesc[it];
+    const int c0 = ds.x, ncol = ds.y, ea = ds.z, cnt = ds.w;
     int *sc = scol + stage * (kPriceTileCols + 8);
     if (tid <= ncol)
-      sc[tid] = colStart[c0 + tid]; // overlaps with the wait / product phase
-    const int ea = colStart[c0] & ~3;
-    const int cnt = ((colStart[c1] + 3) & ~3) - ea;
+      sc[tid] = colStart[c0 + tid] - ea; // overlaps with the wait / product phase
     mbar_wait(&full[stage], (unsigned)((it / kPriceStages) & 1));
     double *v = sval + stage * kPriceTileAlloc;
     const int *ix = sidx + stage * kPriceTileAlloc;
@@ -261,21 +264,18 @@ __global__ void __launch_bounds__(1024, 1)
     }
     __syncthreads();
     for (int c = warp; c < ncol; c += 32) {
-      const int s1 = sc[c + 1] - ea;
+      const int s1 = sc[c + 1];
       double acc = 0.0;
-      for (int e = sc[c] - ea + lane; e < s1; e += 32)
+      for (int e = sc[c] + lane; e < s1; e += 32)
         acc += v[e];
       acc = warp_sum(acc);
       if (lane == 0)
         d.alphaRow[c0 + c] = acc; // raw dot product; row_finalize_kernel applies status/tolerance
     }
     __syncthreads();
-    if (tid == 0) {
-      const int next = t + kPriceStages * gridDim.x;
-      if (next < ntiles) {
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        issue(next, stage);
-      }
+    if (tid == 0 && it + kPriceStages < myTiles) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      issue(it + kPriceStages, stage);
     }
   }
 }
@@ -373,14 +373,18 @@ void launch_price(const DeviceModel &d, int colBegin, int colEnd, bool fuseHist,
   }
   if (g_kernelTimers)
     cudaEventRecord(g_kernelTimers->price[0], s);
-  const size_t tileBytes = 128 + (size_t)kPriceStages * ((kPriceTileCols + 8) * 4 + (size_t)kPriceTileAlloc * 12);
+  const int gridTma = d.numPriceTiles < 148 ? (d.numPriceTiles > 0 ? d.numPriceTiles : 1) : 148;
+  const int descCap = ((d.numPriceTiles + gridTma - 1) / gridTma + 7) / 8 * 8;
+  const size_t tileBytes = 128 + (size_t)descCap * 16 +
+                           (size_t)kPriceStages * ((kPriceTileCols + 8) * 4 + (size_t)kPriceTileAlloc * 12);
   if (d.priceTileCol != nullptr && d.numPriceTiles > 0) {
     // TMA-staged tiles (tiles were cut for this rank's column range at set-up)
     int blocks = d.numPriceTiles < 148 ? d.numPriceTiles : 148;
+    const int4 *desc = reinterpret_cast<const int4 *>(d.priceTileCol);
     if (tileBytes + rhoBytes <= 227 * 1024)
-      price_tma_kernel<true><<<blocks, 1024, tileBytes + rhoBytes, s>>>(d, d.priceTileCol, d.numPriceTiles);
+      price_tma_kernel<true><<<blocks, 1024, tileBytes + rhoBytes, s>>>(d, desc, d.numPriceTiles, descCap);
     else
-      price_tma_kernel<false><<<blocks, 1024, tileBytes, s>>>(d, d.priceTileCol, d.numPriceTiles);
+      price_tma_kernel<false><<<blocks, 1024, tileBytes, s>>>(d, desc, d.numPriceTiles, descCap);
   } else {
     const int nUnits = (ncol + 7) / 8;
     if (rhoBytes <= 220 * 1024) {

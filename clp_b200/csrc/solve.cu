@@ -248,7 +248,7 @@ static void ftran_impl(const DeviceModel &d, double *b, bool applyEtas, bool che
     gblocks = 148;
   double *xg = d.ywork + (size_t)3 * roundUp8(maxk);
   gather_nucleus_kernel<<<gblocks, 256, 0, s>>>(d, b, m, xg, NRHS, checkState);
-  int blocks = maxk < 148 * 6 ? maxk : 148 * 6;
+  int blocks = maxk < 148 * 8 ? maxk : 148 * 8;
   if (g_kernelTimers && checkState)
     cudaEventRecord(g_kernelTimers->ftranGemv[0], s);
   gemv_rows_kernel<NRHS><<<blocks, 256, 0, s>>>(d.fd, 0, xg, d.ywork, -1, nullptr, d.st, checkState);
@@ -387,7 +387,7 @@ static void btran_tail(const DeviceModel &d, double *rhoOut, bool checkState, cu
   if (sblocks > 148 * 8)
     sblocks = 148 * 8;
   btran_s_kernel<<<sblocks, 256, 0, s>>>(d, checkState);
-  int blocks = d.m < 148 * 6 ? d.m : 148 * 6;
+  int blocks = d.m < 148 * 8 ? d.m : 148 * 8;
   if (g_kernelTimers && checkState)
     cudaEventRecord(g_kernelTimers->btranGemv[0], s);
   gemv_rows_kernel<1><<<blocks, 256, 0, s>>>(d.fd, 1, d.swork, rhoOut, d.m, d.nucRow, d.st,
