@@ -170,72 +170,59 @@ __global__ void __launch_bounds__(128)
       col[i] = x[i];
 }
 
-// C[M x N] -= A[M x K] * B[K x N]  (column major, fp64 FMA).  128x128 tile per CTA, 8x8
-// accumulators per thread (4 FMA per shared-memory double: the FP64 pipe, not LDS, is the
-// limiter), K in steps of 16 with register prefetch of the next A/B slices.
+// C[M x N] -= A[M x K] * B[K x N]  (column major).  64x64 tile per CTA, 4x4 per thread.
 __global__ void __launch_bounds__(256)
     gemm_sub_kernel(double *__restrict__ C, int ldc, const double *__restrict__ A, int lda,
                     const double *__restrict__ B, int ldb, int M, int N, int K)
 {
-  __shared__ double As[16][128];
-  __shared__ double Bs[16][128];
+  __shared__ double As[16][64 + 1];
+  __shared__ double Bs[16][64 + 1];
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-  const int m0 = blockIdx.x * 128, n0 = blockIdx.y * 128;
-  double acc[8][8];
+  const int m0 = blockIdx.x * 64, n0 = blockIdx.y * 64;
+  double acc[4][4];
 #pragma unroll
-  for (int a = 0; a < 8; a++)
+  for (int a = 0; a < 4; a++)
 #pragma unroll
-    for (int b = 0; b < 8; b++)
+    for (int b = 0; b < 4; b++)
       acc[a][b] = 0.0;
-  double ra[8], rb[8];
-  auto loadTiles = [&](int k0) {
-#pragma unroll
-    for (int q = 0; q < 8; q++) {
-      const int e = threadIdx.x + 256 * q;
-      const int i = e & 127, l = e >> 7;
-      const int gi = m0 + i, gl = k0 + l;
-      ra[q] = (gi < M && gl < K) ? A[(size_t)gl * lda + gi] : 0.0;
-      const int l2 = e & 15, jn = e >> 4;
-      const int gl2 = k0 + l2, gj = n0 + jn;
-      rb[q] = (gl2 < K && gj < N) ? B[(size_t)gj * ldb + gl2] : 0.0;
-    }
-  };
-  loadTiles(0);
   for (int k0 = 0; k0 < K; k0 += 16) {
-#pragma unroll
-    for (int q = 0; q < 8; q++) {
-      const int e = threadIdx.x + 256 * q;
-      As[e >> 7][e & 127] = ra[q];
-      Bs[e & 15][e >> 4] = rb[q];
+    // A tile: 64 rows x 16 cols ; B tile: 16 rows x 64 cols
+    for (int e = threadIdx.x; e < 64 * 16; e += 256) {
+      int i = e & 63, l = e >> 6;
+      int gi = m0 + i, gl = k0 + l;
+      As[l][i] = (gi < M && gl < K) ? A[(size_t)gl * lda + gi] : 0.0;
+    }
+    for (int e = threadIdx.x; e < 64 * 16; e += 256) {
+      int l = e & 15, jn = e >> 4;
+      int gl = k0 + l, gj = n0 + jn;
+      Bs[l][jn] = (gl < K && gj < N) ? B[(size_t)gj * ldb + gl] : 0.0;
     }
     __syncthreads();
-    if (k0 + 16 < K)
-      loadTiles(k0 + 16);
 #pragma unroll
     for (int l = 0; l < 16; l++) {
-      double av[8], bv[8];
+      double av[4], bv[4];
 #pragma unroll
-      for (int a = 0; a < 8; a++)
+      for (int a = 0; a < 4; a++)
         av[a] = As[l][tx + 16 * a];
 #pragma unroll
-      for (int b = 0; b < 8; b++)
+      for (int b = 0; b < 4; b++)
         bv[b] = Bs[l][ty + 16 * b];
 #pragma unroll
-      for (int a = 0; a < 8; a++)
+      for (int a = 0; a < 4; a++)
 #pragma unroll
-        for (int b = 0; b < 8; b++)
+        for (int b = 0; b < 4; b++)
           acc[a][b] = fma(av[a], bv[b], acc[a][b]);
     }
     __syncthreads();
   }
 #pragma unroll
-  for (int b = 0; b < 8; b++) {
-    const int gj = n0 + ty + 16 * b;
+  for (int b = 0; b < 4; b++) {
+    int gj = n0 + ty + 16 * b;
     if (gj >= N)
       continue;
 #pragma unroll
-    for (int a = 0; a < 8; a++) {
-      const int gi = m0 + tx + 16 * a;
+    for (int a = 0; a < 4; a++) {
+      int gi = m0 + tx + 16 * a;
       if (gi < M)
         C[(size_t)gj * ldc + gi] -= acc[a][b];
     }
@@ -247,7 +234,7 @@ static void gemm_sub(double *C, int ldc, const double *A, int lda, const double 
 {
   if (M <= 0 || N <= 0 || K <= 0)
     return;
-  dim3 grid((M + 127) / 128, (N + 127) / 128);
+  dim3 grid((M + 63) / 64, (N + 63) / 64);
   gemm_sub_kernel<<<grid, 256, 0, s>>>(C, ldc, A, lda, B, ldb, M, N, K);
 }
 

@@ -80,9 +80,10 @@ __device__ __forceinline__ void histogram_add(const DeviceModel &d, double a, do
   if (boxed) {
     double v = a * range / infeas * 1099511627776.0;
     w = v >= 2199023255552.0 ? kFixCap : (unsigned long long)v;
+    if (w == 0ull)
+      w = 1ull; // a bucket with a candidate is never "empty"
   }
   atomicAdd(d.histWeight + b, w);
-  atomicMin(d.histMin + b, (unsigned long long)__double_as_longlong(ratio));
 }
 
 // alphaRow[j] = rho^T a_j for nonbasic, non-fixed columns j in [colBegin,colEnd) + histogram.
@@ -248,29 +249,71 @@ __global__ void __launch_bounds__(1024, 1)
       srho[i] = d.rho[i];
   __syncthreads();
   const double *__restrict__ rho = d.rho;
+  const int half = tid >> 4, l16 = tid & 15; // 64 half-warps, one column each per round
+  const unsigned hmask = 0xFFFFu << (lane & 16);
+  // column bounds of this half-warp's columns, fetched one tile ahead (global, L2 resident)
+  int nb0[2] = {0, 0}, nb1[2] = {0, 0};
+  auto fetchBounds = [&](int i) {
+    const int4 dn = sdesc[i];
+#pragma unroll
+    for (int q = 0; q < 2; q++) {
+      const int c = half + 64 * q;
+      nb0[q] = c < dn.y ? colStart[dn.x + c] - dn.z : 0;
+      nb1[q] = c < dn.y ? colStart[dn.x + c + 1] - dn.z : 0;
+    }
+  };
+  if (myTiles > 0)
+    fetchBounds(0);
   for (int it = 0; it < myTiles; it++) {
     const int stage = it % kPriceStages;
     const int4 ds = sdesc[it];
-    const int c0 = ds.x, ncol = ds.y, ea = ds.z, cnt = ds.w;
-    int *sc = scol + stage * (kPriceTileCols + 8);
-    if (tid <= ncol)
-      sc[tid] = colStart[c0 + tid] - ea; // overlaps with the wait / product phase
-    mbar_wait(&full[stage], (unsigned)((it / kPriceStages) & 1));
-    double *v = sval + stage * kPriceTileAlloc;
-    const int *ix = sidx + stage * kPriceTileAlloc;
-    for (int e = tid; e < cnt; e += 1024) {
-      const int r = ix[e];
-      v[e] *= SMEM_RHO ? srho[r] : __ldg(rho + r);
+    const int c0 = ds.x, ncol = ds.y, ea = ds.z;
+    int b0[2], b1[2];
+#pragma unroll
+    for (int q = 0; q < 2; q++) {
+      b0[q] = nb0[q];
+      b1[q] = nb1[q];
     }
-    __syncthreads();
-    for (int c = warp; c < ncol; c += 32) {
-      const int s1 = sc[c + 1];
+    if (it + 1 < myTiles)
+      fetchBounds(it + 1);
+    mbar_wait(&full[stage], (unsigned)((it / kPriceStages) & 1));
+    const double *v = sval + stage * kPriceTileAlloc;
+    const int *ix = sidx + stage * kPriceTileAlloc;
+#pragma unroll
+    for (int q = 0; q < 2; q++) {
+      const int c = half + 64 * q;
+      if (c < ncol) { // uniform per half-warp
+        double acc0 = 0.0, acc1 = 0.0;
+        int e = b0[q] + l16;
+        for (; e + 16 < b1[q]; e += 32) {
+          const int r0 = ix[e], r1 = ix[e + 16];
+          const double v0 = v[e], v1 = v[e + 16];
+          acc0 = fma(v0, SMEM_RHO ? srho[r0] : __ldg(rho + r0), acc0);
+          acc1 = fma(v1, SMEM_RHO ? srho[r1] : __ldg(rho + r1), acc1);
+        }
+        if (e < b1[q])
+          acc0 = fma(v[e], SMEM_RHO ? srho[ix[e]] : __ldg(rho + ix[e]), acc0);
+        double acc = acc0 + acc1;
+        acc += __shfl_xor_sync(hmask, acc, 8);
+        acc += __shfl_xor_sync(hmask, acc, 4);
+        acc += __shfl_xor_sync(hmask, acc, 2);
+        acc += __shfl_xor_sync(hmask, acc, 1);
+        if (l16 == 0)
+          d.alphaRow[c0 + c] = acc; // raw dot product; row_finalize_kernel applies status/tolerance
+      }
+    }
+    // columns beyond 128 per tile (very short columns): generic loop
+    for (int c = half + 128; c < ncol; c += 64) {
+      const int e1 = colStart[c0 + c + 1] - ea;
       double acc = 0.0;
-      for (int e = sc[c] + lane; e < s1; e += 32)
-        acc += v[e];
-      acc = warp_sum(acc);
-      if (lane == 0)
-        d.alphaRow[c0 + c] = acc; // raw dot product; row_finalize_kernel applies status/tolerance
+      for (int e = colStart[c0 + c] - ea + l16; e < e1; e += 16)
+        acc = fma(v[e], SMEM_RHO ? srho[ix[e]] : __ldg(rho + ix[e]), acc);
+      acc += __shfl_xor_sync(hmask, acc, 8);
+      acc += __shfl_xor_sync(hmask, acc, 4);
+      acc += __shfl_xor_sync(hmask, acc, 2);
+      acc += __shfl_xor_sync(hmask, acc, 1);
+      if (l16 == 0)
+        d.alphaRow[c0 + c] = acc;
     }
     __syncthreads();
     if (tid == 0 && it + kPriceStages < myTiles) {
@@ -436,7 +479,7 @@ __global__ void __launch_bounds__(1024) chuzc_scan1_kernel(DeviceModel d)
   {
     const int b = blockIdx.x * 1024 + tid;
     unsigned long long w = d.histWeight[b];
-    int last = d.histMin[b] != kSentinel ? b : -1;
+    int last = w != 0ull ? b : -1;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       w += __shfl_xor_sync(0xffffffffu, w, o);
@@ -492,10 +535,11 @@ __global__ void __launch_bounds__(1024) chuzc_scan1_kernel(DeviceModel d)
     return;
   }
   if (sSeg < 0) {
-    // slope never exhausted: stop at the last break point group
+    // slope never exhausted: stop at the last break point group (level 2 then takes the last
+    // non-empty sub-bucket of the last non-empty bucket)
     if (tid == 0) {
-      st->bucket1 = -1;
-      st->thetaStar = __longlong_as_double((long long)d.histMin[sLastAll]);
+      st->bucket1 = sLastAll;
+      st->residual = 0xFFFFFFFFFFFFFFFFull;
     }
     return;
   }
@@ -550,6 +594,8 @@ __global__ void chuzc_hist2_kernel(DeviceModel d)
     if (boxed) {
       double v = a * range / infeas * 1099511627776.0;
       w = v >= 2199023255552.0 ? kFixCap : (unsigned long long)v;
+      if (w == 0ull)
+        w = 1ull;
     }
     atomicAdd(d.hist2Weight + sb, w);
     atomicMin(d.hist2Min + sb, bits);

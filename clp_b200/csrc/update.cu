@@ -28,7 +28,6 @@ __global__ void chuzr_kernel(DeviceModel d)
   // clear the ratio-test histograms for this iteration (the previous scans are complete)
   for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < kHistBuckets; b += gridDim.x * blockDim.x) {
     d.histWeight[b] = 0ull;
-    d.histMin[b] = 0xFFFFFFFFFFFFFFFFull;
     if (b < kHist2Buckets) {
       d.hist2Weight[b] = 0ull;
       d.hist2Min[b] = 0xFFFFFFFFFFFFFFFFull;
@@ -291,13 +290,19 @@ __global__ void __launch_bounds__(256)
        i += gridDim.x * warpsPerBlock) {
     double acc = 0.0;
     const int e1 = d.rowStart[i + 1];
-#pragma unroll 4
-    for (int e = d.rowStart[i] + lane; e < e1; e += 32) {
-      const int j = __ldcs(d.colIdx + e);
-      if ((sbits[j >> 5] >> (j & 31)) & 1u) {
-        const double range = d.upper[j] - d.lower[j];
-        const double delta = d.status[j] == atUpperBound ? range : -range;
-        acc = fma(-delta, d.rval[e], acc);
+    for (int e = d.rowStart[i] + lane; e < e1; e += 256) {
+      int jj[8];
+#pragma unroll
+      for (int q = 0; q < 8; q++)
+        jj[q] = (e + 32 * q < e1) ? __ldcs(d.colIdx + e + 32 * q) : -1;
+#pragma unroll
+      for (int q = 0; q < 8; q++) {
+        const int j = jj[q];
+        if (j >= 0 && ((sbits[j >> 5] >> (j & 31)) & 1u)) {
+          const double range = d.upper[j] - d.lower[j];
+          const double delta = d.status[j] == atUpperBound ? range : -range;
+          acc = fma(-delta, d.rval[e + 32 * q], acc);
+        }
       }
     }
 #pragma unroll

@@ -201,6 +201,8 @@ int dualColumnBucketed(int count, const double *alpha, const double *dj, const d
     if (boxed) {
       double v = a * range[k] / infeasibility * 1099511627776.0;
       w = v >= 2199023255552.0 ? (1ull << 41) : (unsigned long long)v;
+      if (w == 0ull)
+        w = 1ull;
     }
     hw[b] += w;
     hm[b] = std::min(hm[b], bits);
@@ -220,9 +222,13 @@ int dualColumnBucketed(int count, const double *alpha, const double *dj, const d
     c += hw[b];
   }
   double thetaStar;
-  if (cross < 0) {
-    std::memcpy(&thetaStar, &hm[last], 8); // slope never exhausted: last break point group
-  } else {
+  bool neverExhausted = false;
+  if (cross < 0) { // slope never exhausted: last break point group (last sub-bucket of the last bucket)
+    cross = last;
+    before = 0;
+    neverExhausted = true;
+  }
+  {
     // second level: the next 12 bits of the ratio inside the crossing bucket
     const int NB2 = 4096;
     std::vector<unsigned long long> hw2(NB2, 0ull), hm2(NB2, ~0ull);
@@ -239,11 +245,13 @@ int dualColumnBucketed(int count, const double *alpha, const double *dj, const d
       if (boxed) {
         double v = A[k] * range[k] / infeasibility * 1099511627776.0;
         w = v >= 2199023255552.0 ? (1ull << 41) : (unsigned long long)v;
+        if (w == 0ull)
+          w = 1ull;
       }
       hw2[sb] += w;
       hm2[sb] = std::min(hm2[sb], bits);
     }
-    const unsigned long long resid = (1ull << 40) - before;
+    const unsigned long long resid = neverExhausted ? ~0ull : (1ull << 40) - before;
     unsigned long long c2 = 0;
     int cross2 = -1, last2 = -1;
     for (int b = 0; b < NB2; b++) {

@@ -1,0 +1,45 @@
+"""Column-sharded pricing across 2 GPUs (one process per GPU, one NCCL all-gather per pricing
+pass): every rank must take the same pivots as the single-GPU run."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+from conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+
+
+def _gpu_count():
+    try:
+        import torch
+
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
+
+
+@pytest.mark.skipif(_gpu_count() < 2, reason="needs 2 GPUs")
+def test_two_gpu_sharded_solve_matches_single_gpu():
+    import clp_b200
+    from clp_b200 import generators as G
+
+    args = ["1500", "20000", "0.01", "31"]
+    lp = G.random_sparse_lp(1500, 20000, 0.01, 31)
+    s = clp_b200.ClpSimplex(); s.loadLP(lp)
+    assert s.dual() == 0
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+           "--master-addr", "127.0.0.1", "--master-port", "29631", os.path.join(ROOT, "tests", "multigpu_worker.py")] + args
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-3000:]
+    line = [l for l in out.stdout.splitlines() if l.startswith("MULTIGPU_RESULT")][0]
+    res = json.loads(line.split(" ", 1)[1])
+    assert len(res) == 2
+    for r in res:
+        assert r["status"] == 0
+        assert r["iterations"] == s.numberIterations()          # identical pivot sequence
+        assert r["objective"] == res[0]["objective"]             # ranks bit-identical
+        assert abs(r["objective"] - s.objectiveValue()) <= 1e-9 * (1 + abs(s.objectiveValue()))
+        assert abs(r["objective"] - lp.known_objective) <= 1e-8 * (1 + abs(lp.known_objective))
