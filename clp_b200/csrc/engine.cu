@@ -203,7 +203,7 @@ int Engine::setupDevice()
     d.priceTileCol = nullptr;
     d.numPriceTiles = 0;
     const int ntl = (int)tiles.size() - 1;
-    if (ok && ce > cb && usePriceTma && (ntl + 147) / 148 <= kPriceMaxTilesPerCta) {
+    if (ok && ce > cb && usePriceTma) {
       std::vector<int> desc((size_t)ntl * 4);
       for (int t = 0; t < ntl; t++) {
         const int t0 = tiles[t], t1 = tiles[t + 1];

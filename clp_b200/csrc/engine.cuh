@@ -33,11 +33,12 @@ constexpr double kDevexTryNorm = 1.0e-4; // DEVEX_TRY_NORM ClpSimplex.hpp:2056
 constexpr int kHistBuckets = 32768;       // ratio-test histogram level 1: 11 exponent + 4 mantissa bits
 constexpr int kHist2Buckets = 4096;       // level 2: the next 12 mantissa bits inside the crossing bucket
 constexpr int kMaxFlips = 8192;
-constexpr int kPriceTile = 3072;          // entries per TMA-staged tile of the CSC arrays
-constexpr int kPriceStages = 3;           // tiles in flight per CTA
+constexpr int kPriceTile = 1024;          // entries per TMA-staged tile of the CSC arrays
+constexpr int kPriceStages = 2;           // tiles in flight per pipeline
+constexpr int kPriceGroups = 4;           // independent 256-thread pipelines per CTA
 constexpr int kPriceMaxTilesPerCta = 1024; // descriptors staged in shared memory per CTA
 constexpr int kPriceTileAlloc = kPriceTile + 8;
-constexpr int kPriceTileCols = 512;       // columns per tile (shared alpha buffer)
+constexpr int kPriceTileCols = 8;         // columns per tile (one warp each)
 
 // stop reasons written by the device into IterState.stop
 enum : int { STOP_NONE = 0, STOP_NO_ROW = 1, STOP_NO_COLUMN = 2, STOP_INACCURATE = 3,

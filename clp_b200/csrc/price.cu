@@ -205,8 +205,12 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned pari
                : "memory");
 }
 
-// tile descriptor (host-built): first column, number of columns, first entry (multiple of 4),
-// number of entries (multiple of 4)
+// tile descriptor (host-built): first column, number of columns (<= 8), first entry (multiple
+// of 4), number of entries (multiple of 4, <= kPriceTile).
+// The CTA (1024 threads) is split into kPriceGroups independent 256-thread pipelines, each with
+// its own tiles, mbarriers and named barrier, so that one group's latency chain (mbarrier wait ->
+// shared-memory gathers -> warp reduction) overlaps with the others' instead of stalling the
+// whole CTA; rho is staged once per CTA and shared by the groups.
 template <bool SMEM_RHO>
 __global__ void __launch_bounds__(1024, 1)
     price_tma_kernel(DeviceModel d, const int4 *__restrict__ tileDesc, int ntiles, int descCap)
@@ -214,22 +218,28 @@ __global__ void __launch_bounds__(1024, 1)
   extern __shared__ __align__(128) unsigned char smemRaw[];
   if (!iter_active(d.st))
     return;
-  // layout: barriers | sdesc[descCap] | scol[stage][kPriceTileCols+8] | sidx | sval | srho
-  unsigned long long *full = reinterpret_cast<unsigned long long *>(smemRaw);
-  int4 *sdesc = reinterpret_cast<int4 *>(smemRaw + 128);
-  int *scol = reinterpret_cast<int *>(smemRaw + 128 + descCap * 16);
-  int *sidx = scol + kPriceStages * (kPriceTileCols + 8);
-  double *sval = reinterpret_cast<double *>(sidx + kPriceStages * kPriceTileAlloc);
-  double *srho = sval + kPriceStages * kPriceTileAlloc;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // layout: barriers[groups][stages] | sdesc[groups][descCap] | sidx[groups][stages][tile] |
+  //         sval[groups][stages][tile] | srho[m]
+  unsigned long long *fullAll = reinterpret_cast<unsigned long long *>(smemRaw);
+  int4 *sdescAll = reinterpret_cast<int4 *>(smemRaw + 128);
+  int *sidxAll = reinterpret_cast<int *>(smemRaw + 128 + (size_t)kPriceGroups * descCap * 16);
+  double *svalAll = reinterpret_cast<double *>(sidxAll + kPriceGroups * kPriceStages * kPriceTileAlloc);
+  double *srho = svalAll + kPriceGroups * kPriceStages * kPriceTileAlloc;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int grp = tid >> 8, gt = tid & 255, gwarp = gt >> 5;
+  unsigned long long *full = fullAll + grp * kPriceStages;
+  int4 *sdesc = sdescAll + grp * descCap;
+  int *sidx = sidxAll + grp * kPriceStages * kPriceTileAlloc;
+  double *sval = svalAll + grp * kPriceStages * kPriceTileAlloc;
   const int *__restrict__ colStart = d.colStart;
-  // this CTA's tiles: blockIdx.x, blockIdx.x + gridDim.x, ...  (descriptors staged once)
-  const int myTiles = ((int)blockIdx.x < ntiles) ? (ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
-  if (tid < myTiles)
-    sdesc[tid] = tileDesc[blockIdx.x + tid * gridDim.x];
+  const int G = gridDim.x * kPriceGroups;         // pipelines in the grid
+  const int gg = blockIdx.x * kPriceGroups + grp; // this pipeline
+  const int myTiles = gg < ntiles ? (ntiles - 1 - gg) / G + 1 : 0;
+  for (int i = gt; i < myTiles; i += 256)
+    sdesc[i] = tileDesc[gg + (size_t)i * G];
   if (tid == 0) {
-    for (int q = 0; q < kPriceStages; q++)
-      mbar_init(&full[q], 1);
+    for (int q = 0; q < kPriceGroups * kPriceStages; q++)
+      mbar_init(&fullAll[q], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -241,7 +251,7 @@ __global__ void __launch_bounds__(1024, 1)
     bulk_g2s(sidx + stage * kPriceTileAlloc, d.rowIdx + ds.z, cnt * 4u, &full[stage]);
     bulk_g2s(sval + stage * kPriceTileAlloc, d.val + ds.z, cnt * 8u, &full[stage]);
   };
-  if (tid == 0)
+  if (gt == 0)
     for (int q = 0; q < kPriceStages && q < myTiles; q++)
       issue(q, q);
   if (SMEM_RHO)
@@ -249,74 +259,42 @@ __global__ void __launch_bounds__(1024, 1)
       srho[i] = d.rho[i];
   __syncthreads();
   const double *__restrict__ rho = d.rho;
-  const int half = tid >> 4, l16 = tid & 15; // 64 half-warps, one column each per round
-  const unsigned hmask = 0xFFFFu << (lane & 16);
-  // column bounds of this half-warp's columns, fetched one tile ahead (global, L2 resident)
-  int nb0[2] = {0, 0}, nb1[2] = {0, 0};
+  // bounds of this warp's column, fetched one tile ahead (global, L2 resident)
+  int nb0 = 0, nb1 = 0;
   auto fetchBounds = [&](int i) {
     const int4 dn = sdesc[i];
-#pragma unroll
-    for (int q = 0; q < 2; q++) {
-      const int c = half + 64 * q;
-      nb0[q] = c < dn.y ? colStart[dn.x + c] - dn.z : 0;
-      nb1[q] = c < dn.y ? colStart[dn.x + c + 1] - dn.z : 0;
-    }
+    nb0 = gwarp < dn.y ? colStart[dn.x + gwarp] - dn.z : 0;
+    nb1 = gwarp < dn.y ? colStart[dn.x + gwarp + 1] - dn.z : 0;
   };
   if (myTiles > 0)
     fetchBounds(0);
   for (int it = 0; it < myTiles; it++) {
     const int stage = it % kPriceStages;
     const int4 ds = sdesc[it];
-    const int c0 = ds.x, ncol = ds.y, ea = ds.z;
-    int b0[2], b1[2];
-#pragma unroll
-    for (int q = 0; q < 2; q++) {
-      b0[q] = nb0[q];
-      b1[q] = nb1[q];
-    }
+    const int b0 = nb0, b1 = nb1;
     if (it + 1 < myTiles)
       fetchBounds(it + 1);
     mbar_wait(&full[stage], (unsigned)((it / kPriceStages) & 1));
-    const double *v = sval + stage * kPriceTileAlloc;
-    const int *ix = sidx + stage * kPriceTileAlloc;
-#pragma unroll
-    for (int q = 0; q < 2; q++) {
-      const int c = half + 64 * q;
-      if (c < ncol) { // uniform per half-warp
-        double acc0 = 0.0, acc1 = 0.0;
-        int e = b0[q] + l16;
-        for (; e + 16 < b1[q]; e += 32) {
-          const int r0 = ix[e], r1 = ix[e + 16];
-          const double v0 = v[e], v1 = v[e + 16];
-          acc0 = fma(v0, SMEM_RHO ? srho[r0] : __ldg(rho + r0), acc0);
-          acc1 = fma(v1, SMEM_RHO ? srho[r1] : __ldg(rho + r1), acc1);
-        }
-        if (e < b1[q])
-          acc0 = fma(v[e], SMEM_RHO ? srho[ix[e]] : __ldg(rho + ix[e]), acc0);
-        double acc = acc0 + acc1;
-        acc += __shfl_xor_sync(hmask, acc, 8);
-        acc += __shfl_xor_sync(hmask, acc, 4);
-        acc += __shfl_xor_sync(hmask, acc, 2);
-        acc += __shfl_xor_sync(hmask, acc, 1);
-        if (l16 == 0)
-          d.alphaRow[c0 + c] = acc; // raw dot product; row_finalize_kernel applies status/tolerance
+    if (gwarp < ds.y) { // one warp per column of the tile
+      const double *v = sval + stage * kPriceTileAlloc;
+      const int *ix = sidx + stage * kPriceTileAlloc;
+      double acc0 = 0.0, acc1 = 0.0;
+      int e = b0 + lane;
+      for (; e + 32 < b1; e += 64) {
+        const int r0 = ix[e], r1 = ix[e + 32];
+        const double v0 = v[e], v1 = v[e + 32];
+        acc0 = fma(v0, SMEM_RHO ? srho[r0] : __ldg(rho + r0), acc0);
+        acc1 = fma(v1, SMEM_RHO ? srho[r1] : __ldg(rho + r1), acc1);
       }
+      if (e < b1)
+        acc0 = fma(v[e], SMEM_RHO ? srho[ix[e]] : __ldg(rho + ix[e]), acc0);
+      const double acc = warp_sum(acc0 + acc1);
+      if (lane == 0)
+        d.alphaRow[ds.x + gwarp] = acc; // raw dot product; row_finalize_kernel applies status/tolerance
     }
-    // columns beyond 128 per tile (very short columns): generic loop
-    for (int c = half + 128; c < ncol; c += 64) {
-      const int e1 = colStart[c0 + c + 1] - ea;
-      double acc = 0.0;
-      for (int e = colStart[c0 + c] - ea + l16; e < e1; e += 16)
-        acc = fma(v[e], SMEM_RHO ? srho[ix[e]] : __ldg(rho + ix[e]), acc);
-      acc += __shfl_xor_sync(hmask, acc, 8);
-      acc += __shfl_xor_sync(hmask, acc, 4);
-      acc += __shfl_xor_sync(hmask, acc, 2);
-      acc += __shfl_xor_sync(hmask, acc, 1);
-      if (l16 == 0)
-        d.alphaRow[c0 + c] = acc;
-    }
-    __syncthreads();
-    if (tid == 0 && it + kPriceStages < myTiles) {
+    // group barrier: every warp of this pipeline is done with the stage
+    asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "r"(256) : "memory");
+    if (gt == 0 && it + kPriceStages < myTiles) {
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       issue(it + kPriceStages, stage);
     }
@@ -416,13 +394,18 @@ void launch_price(const DeviceModel &d, int colBegin, int colEnd, bool fuseHist,
   }
   if (g_kernelTimers)
     cudaEventRecord(g_kernelTimers->price[0], s);
-  const int gridTma = d.numPriceTiles < 148 ? (d.numPriceTiles > 0 ? d.numPriceTiles : 1) : 148;
-  const int descCap = ((d.numPriceTiles + gridTma - 1) / gridTma + 7) / 8 * 8;
-  const size_t tileBytes = 128 + (size_t)descCap * 16 +
-                           (size_t)kPriceStages * ((kPriceTileCols + 8) * 4 + (size_t)kPriceTileAlloc * 12);
+  int gridTma = (d.numPriceTiles + kPriceGroups - 1) / kPriceGroups;
+  if (gridTma > 148)
+    gridTma = 148;
+  if (gridTma < 1)
+    gridTma = 1;
+  const int pipes = gridTma * kPriceGroups;
+  const int descCap = ((d.numPriceTiles + pipes - 1) / pipes + 7) / 8 * 8;
+  const size_t tileBytes = 128 + (size_t)kPriceGroups * descCap * 16 +
+                           (size_t)kPriceGroups * kPriceStages * (size_t)kPriceTileAlloc * 12;
   if (d.priceTileCol != nullptr && d.numPriceTiles > 0) {
     // TMA-staged tiles (tiles were cut for this rank's column range at set-up)
-    int blocks = d.numPriceTiles < 148 ? d.numPriceTiles : 148;
+    int blocks = gridTma;
     const int4 *desc = reinterpret_cast<const int4 *>(d.priceTileCol);
     if (tileBytes + rhoBytes <= 227 * 1024)
       price_tma_kernel<true><<<blocks, 1024, tileBytes + rhoBytes, s>>>(d, desc, d.numPriceTiles, descCap);

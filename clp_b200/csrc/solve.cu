@@ -54,9 +54,10 @@ __global__ void gather_nucleus_kernel(DeviceModel d, const double *__restrict__ 
   }
 }
 
-// y[c][i] = sum_j M[i][j] * x[c][j]   (M row-major k x ldk).  One CTA streams one row at a time:
-// every thread issues four 16-byte loads back to back, so a CTA keeps 16 KB of one contiguous
-// row in flight (long DRAM streams, one per resident CTA).
+// y[c][i] = sum_j M[i][j] * x[c][j]   (M row-major k x ldk).  One CTA streams a group of four
+// consecutive rows: each thread issues the four 16-byte loads (one per row) back to back and
+// reuses every x value for the four rows, so the L1 traffic for x is NRHS/4 of the matrix
+// traffic and 16 KB of matrix (4 KB contiguous per row) are in flight per CTA step.
 // if outIndex != nullptr the result is scattered: out[c*ostride + outIndex[i]]
 template <int NRHS>
 __global__ void __launch_bounds__(256)
@@ -66,58 +67,61 @@ __global__ void __launch_bounds__(256)
 {
   if (checkState && !iter_active(st))
     return;
-  __shared__ double part[8][NRHS];
+  constexpr int R = 4;
+  __shared__ double part[8][R * NRHS];
   const int k = fd->k, ldk = fd->ldk;
   const double *__restrict__ M = transposed ? fd->NinvT : fd->Ninv;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int half = ldk >> 1; // ldk is a multiple of 8, padding is zero
-  for (int i = blockIdx.x; i < k; i += gridDim.x) {
-    const double2 *row = reinterpret_cast<const double2 *>(M + (size_t)i * ldk);
-    double acc[NRHS];
+  const int ngroups = (k + R - 1) / R;
+  for (int g = blockIdx.x; g < ngroups; g += gridDim.x) {
+    const int i0 = g * R;
+    const double2 *row[R];
 #pragma unroll
-    for (int c = 0; c < NRHS; c++)
-      acc[c] = 0.0;
-    for (int j = threadIdx.x; j < half; j += 1024) {
-      const double2 z2 = make_double2(0.0, 0.0);
-      const int j1 = j + 256, j2 = j + 512, j3 = j + 768;
-      const double2 a0 = __ldcs(row + j);
-      const double2 a1 = j1 < half ? __ldcs(row + j1) : z2;
-      const double2 a2 = j2 < half ? __ldcs(row + j2) : z2;
-      const double2 a3 = j3 < half ? __ldcs(row + j3) : z2;
+    for (int r = 0; r < R; r++) // rows beyond k alias the last row (results discarded)
+      row[r] = reinterpret_cast<const double2 *>(M + (size_t)min(i0 + r, k - 1) * ldk);
+    double acc[R][NRHS];
+#pragma unroll
+    for (int r = 0; r < R; r++)
+#pragma unroll
+      for (int c = 0; c < NRHS; c++)
+        acc[r][c] = 0.0;
+#pragma unroll 2
+    for (int j = threadIdx.x; j < half; j += 256) {
+      double2 a[R];
+#pragma unroll
+      for (int r = 0; r < R; r++)
+        a[r] = __ldcs(row[r] + j);
 #pragma unroll
       for (int c = 0; c < NRHS; c++) {
-        const double2 *xc = reinterpret_cast<const double2 *>(x + (size_t)c * ldk);
-        const double2 x0 = __ldg(xc + j);
-        const double2 x1 = j1 < half ? __ldg(xc + j1) : z2;
-        const double2 x2 = j2 < half ? __ldg(xc + j2) : z2;
-        const double2 x3 = j3 < half ? __ldg(xc + j3) : z2;
-        acc[c] = fma(a0.x, x0.x, acc[c]);
-        acc[c] = fma(a0.y, x0.y, acc[c]);
-        acc[c] = fma(a1.x, x1.x, acc[c]);
-        acc[c] = fma(a1.y, x1.y, acc[c]);
-        acc[c] = fma(a2.x, x2.x, acc[c]);
-        acc[c] = fma(a2.y, x2.y, acc[c]);
-        acc[c] = fma(a3.x, x3.x, acc[c]);
-        acc[c] = fma(a3.y, x3.y, acc[c]);
+        const double2 xv = __ldg(reinterpret_cast<const double2 *>(x + (size_t)c * ldk) + j);
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+          acc[r][c] = fma(a[r].x, xv.x, acc[r][c]);
+          acc[r][c] = fma(a[r].y, xv.y, acc[r][c]);
+        }
       }
     }
 #pragma unroll
-    for (int c = 0; c < NRHS; c++)
-      acc[c] = warp_sum(acc[c]);
-    if (lane == 0) {
+    for (int r = 0; r < R; r++)
 #pragma unroll
-      for (int c = 0; c < NRHS; c++)
-        part[warp][c] = acc[c];
-    }
+      for (int c = 0; c < NRHS; c++) {
+        const double v = warp_sum(acc[r][c]);
+        if (lane == 0)
+          part[warp][r * NRHS + c] = v;
+      }
     __syncthreads();
-    if (threadIdx.x < NRHS) {
+    if (threadIdx.x < R * NRHS) {
       double sum = 0.0;
 #pragma unroll
       for (int w = 0; w < 8; w++)
         sum += part[w][threadIdx.x];
-      const int o = outIndex ? outIndex[i] : i;
-      const int os = ostride < 0 ? ldk : ostride;
-      out[(size_t)threadIdx.x * os + o] = sum;
+      const int r = threadIdx.x / NRHS, c = threadIdx.x % NRHS;
+      if (i0 + r < k) {
+        const int o = outIndex ? outIndex[i0 + r] : i0 + r;
+        const int os = ostride < 0 ? ldk : ostride;
+        out[(size_t)c * os + o] = sum;
+      }
     }
     __syncthreads();
   }
