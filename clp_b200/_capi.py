@@ -59,6 +59,7 @@ SIGNATURES = {
     "Clpb_times": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_double, c_double_p, c_double_p]),
     "Clpb_dualColumn": (ctypes.c_int, [ctypes.c_void_p, c_double_p, c_double_p, c_ubyte_p, ctypes.c_int,
                                        ctypes.c_double, c_double_p]),
+    "Clpb_denseInvert": (ctypes.c_int, [ctypes.c_int, c_double_p, c_double_p]),
     "Clpb_startup": (ctypes.c_int, [ctypes.c_void_p]),
     "Clpb_iterate": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "Clpb_getWeights": (None, [ctypes.c_void_p, c_double_p]),

@@ -210,6 +210,36 @@ void Clpb_timedWindow(Clpb_Simplex *model, double *milliseconds, int *iterations
   *iterations = model->e.timedIterations;
 }
 
+int Clpb_denseInvert(int k, const double *a, double *x)
+{
+  return guarded([&] {
+    int devCount = 0;
+    if (cudaGetDeviceCount(&devCount) != cudaSuccess || devCount == 0)
+      throw std::runtime_error("no CUDA device");
+    const int ld = (k + 7) / 8 * 8;
+    double *dA = nullptr, *dX = nullptr;
+    int *dI = nullptr, *dP = nullptr, *dInfo = nullptr;
+    cudaMalloc(&dA, sizeof(double) * (size_t)k * ld);
+    cudaMalloc(&dX, sizeof(double) * (size_t)k * ld);
+    cudaMalloc(&dI, sizeof(int) * k);
+    cudaMalloc(&dP, sizeof(int) * k);
+    cudaMalloc(&dInfo, sizeof(int));
+    cudaMemset(dA, 0, sizeof(double) * (size_t)k * ld);
+    // column-major with leading dimension ld
+    cudaMemcpy2D(dA, sizeof(double) * ld, a, sizeof(double) * k, sizeof(double) * k, k, cudaMemcpyHostToDevice);
+    std::vector<int> hi(k), hp(k);
+    cudaStream_t s;
+    cudaStreamCreate(&s);
+    int info = clpb::dense_invert(dA, dX, k, ld, dI, dP, dInfo, hi.data(), hp.data(), 1.0e-11, s);
+    cudaStreamSynchronize(s);
+    if (info == 0)
+      cudaMemcpy2D(x, sizeof(double) * k, dX, sizeof(double) * ld, sizeof(double) * k, k, cudaMemcpyDeviceToHost);
+    cudaStreamDestroy(s);
+    cudaFree(dA); cudaFree(dX); cudaFree(dI); cudaFree(dP); cudaFree(dInfo);
+    return info;
+  });
+}
+
 int Clpb_ncclUniqueId(unsigned char *id128)
 {
   if (!loadNccl())

@@ -16,7 +16,160 @@ namespace clpb {
 
 constexpr int NB = 32;
 
-// ---- panel factorization: columns [j0, j0+nb) rows [j0, k), single CTA ------------------
+// ---- panel factorization: columns [j0, j0+nb) rows [j0, k) -------------------------------
+// Cooperative multi-CTA kernel.  The rows of the panel are dealt round-robin to the CTAs
+// (row j0 + c + q*gridDim.x belongs to CTA c) and live in shared memory for the whole panel,
+// so global memory is read once and written once.  Per column there is ONE grid barrier: before
+// it every CTA publishes its best pivot candidate (packed |value|,row key) together with that
+// candidate row, and the owner of the diagonal row publishes the diagonal row; after it every
+// CTA knows the pivot row, the two owners exchange the rows, and all CTAs eliminate.
+constexpr int kSlabPitch = NB + 1;       // padded row pitch in shared memory (bank conflicts)
+constexpr int kPanelMaxRowsPerCta = 640; // 640 rows x 33 x 8 B = 165 KB of shared memory
+
+__device__ __forceinline__ void grid_barrier(unsigned int *counter, unsigned int target)
+{
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(counter, 1u);
+    while (*((volatile unsigned int *)counter) < target)
+      ;
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+// rows [j0 + cta*R, j0 + (cta+1)*R) of the panel belong to CTA 'cta'
+__global__ void __launch_bounds__(256)
+    lu_panel_coop_kernel(double *__restrict__ A, int k, int ld, int j0, int nb, int R,
+                         int *__restrict__ ipiv, int *__restrict__ info, double singularTol,
+                         unsigned long long *__restrict__ pubKey, double *__restrict__ pubRows,
+                         double *__restrict__ pubDiag, unsigned int *__restrict__ barrierCounter,
+                         unsigned int barrierBase)
+{
+  extern __shared__ double slab[]; // [R][kSlabPitch]
+  __shared__ unsigned long long sBest[8];
+  __shared__ int sWinCta[8];
+  __shared__ double urow[NB];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int G = gridDim.x, cta = blockIdx.x;
+  const int r0 = j0 + cta * R;                         // first global row of this CTA
+  const int rowsLocal = max(0, min(R, k - r0));
+  for (int c = 0; c < nb; c++)
+    for (int q = tid; q < rowsLocal; q += 256)
+      slab[q * kSlabPitch + c] = A[(size_t)(j0 + c) * ld + r0 + q];
+  __syncthreads();
+  unsigned int bar = barrierBase;
+  for (int jj = 0; jj < nb; jj++) {
+    const int j = j0 + jj; // diagonal row / column
+    const int ownerJ = (j - j0) / R;
+    // ---- local pivot candidate over rows >= j
+    unsigned long long best = 0ull;
+    for (int q = tid; q < rowsLocal; q += 256) {
+      const int gi = r0 + q;
+      if (gi >= j) {
+        const double a = fabs(slab[q * kSlabPitch + jj]);
+        // key: |a| bits (low 20 bits dropped) | (0xFFFFF - relative row): ties take the smallest row
+        const unsigned long long key =
+            ((unsigned long long)__double_as_longlong(a) & ~0xFFFFFull) | (unsigned long long)(0xFFFFF - (gi - j0));
+        best = max(best, key);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+      best = max(best, __shfl_xor_sync(0xffffffffu, best, o));
+    if (lane == 0)
+      sBest[warp] = best;
+    __syncthreads();
+    unsigned long long cand = 0ull;
+#pragma unroll
+    for (int w = 0; w < 8; w++)
+      cand = max(cand, sBest[w]);
+    if (tid == 0)
+      pubKey[(size_t)jj * G + cta] = cand;
+    // publish the candidate row and (owner only) the diagonal row
+    if (cand != 0ull && tid < NB) {
+      const int q = j0 + (0xFFFFF - (int)(cand & 0xFFFFFull)) - r0;
+      pubRows[((size_t)jj * G + cta) * NB + tid] = slab[q * kSlabPitch + tid];
+    }
+    if (ownerJ == cta && tid < NB)
+      pubDiag[(size_t)jj * NB + tid] = slab[(j - r0) * kSlabPitch + tid];
+    bar += G;
+    grid_barrier(barrierCounter, bar);
+    // ---- global winner (every CTA scans the G keys: identical result everywhere)
+    unsigned long long win = 0ull;
+    int winCta = 0;
+    for (int c = tid; c < G; c += 256) {
+      const unsigned long long b = ((volatile unsigned long long *)pubKey)[(size_t)jj * G + c];
+      if (b > win) {
+        win = b;
+        winCta = c;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const unsigned long long ob = __shfl_xor_sync(0xffffffffu, win, o);
+      const int oc = __shfl_xor_sync(0xffffffffu, winCta, o);
+      if (ob > win) {
+        win = ob;
+        winCta = oc;
+      }
+    }
+    if (lane == 0) {
+      sBest[warp] = win;
+      sWinCta[warp] = winCta;
+    }
+    __syncthreads();
+    unsigned long long wkey = 0ull;
+    int wCta = 0;
+#pragma unroll
+    for (int w = 0; w < 8; w++)
+      if (sBest[w] > wkey) {
+        wkey = sBest[w];
+        wCta = sWinCta[w];
+      }
+    const double pivAbs = __longlong_as_double((long long)(wkey & ~0xFFFFFull));
+    const int piv = j0 + (0xFFFFF - (int)(wkey & 0xFFFFFull)); // global pivot row
+    const bool singular = (wkey == 0ull) || !(pivAbs >= singularTol);
+    if (cta == 0 && tid == 0) {
+      ipiv[j] = singular ? j : piv;
+      if (singular && *info == 0)
+        *info = j + 1;
+    }
+    if (singular) {
+      __syncthreads();
+      continue; // uniform across the grid: leave the column, the caller repairs the basis
+    }
+    // pivot row values (before elimination)
+    if (tid < NB)
+      urow[tid] = ((volatile double *)pubRows)[((size_t)jj * G + wCta) * NB + tid];
+    __syncthreads();
+    // exchange: the old diagonal row moves to row piv, the pivot row moves to row j
+    if (piv != j && piv >= r0 && piv < r0 + rowsLocal && tid < NB)
+      slab[(piv - r0) * kSlabPitch + tid] = ((volatile double *)pubDiag)[(size_t)jj * NB + tid];
+    __syncthreads();
+    if (ownerJ == cta && tid < NB)
+      slab[(j - r0) * kSlabPitch + tid] = urow[tid];
+    __syncthreads();
+    // ---- eliminate rows below the diagonal
+    const double inv = 1.0 / urow[jj];
+    for (int q = tid; q < rowsLocal; q += 256) {
+      if (r0 + q > j) {
+        double *r = slab + q * kSlabPitch;
+        const double l = r[jj] * inv;
+        r[jj] = l;
+        for (int c = jj + 1; c < nb; c++)
+          r[c] = fma(-l, urow[c], r[c]);
+      }
+    }
+    __syncthreads();
+  }
+  for (int c = 0; c < nb; c++)
+    for (int q = tid; q < rowsLocal; q += 256)
+      A[(size_t)(j0 + c) * ld + r0 + q] = slab[q * kSlabPitch + c];
+}
+
+// ---- single-CTA fallback (very tall panels that do not fit the cooperative kernel's slabs)
 __global__ void __launch_bounds__(1024)
     lu_panel_kernel(double *__restrict__ A, int k, int ld, int j0, int nb, int *__restrict__ ipiv,
                     int *__restrict__ info, double singularTol)
@@ -295,9 +448,45 @@ int dense_invert(double *A, double *X, int k, int ld, int *dIpiv, int *dPerm, in
   if (k <= 0)
     return 0;
   cudaMemsetAsync(dInfo, 0, sizeof(int), s);
+  // scratch of the cooperative panel kernel (allocated once per process)
+  static unsigned long long *pubKey = nullptr;
+  static double *pubRows = nullptr, *pubDiag = nullptr;
+  static unsigned int *barCounter = nullptr;
+  static int numSMs = 0;
+  if (!pubKey) {
+    cudaDeviceGetAttribute(&numSMs, cudaDevAttrMultiProcessorCount, 0);
+    if (numSMs <= 0)
+      numSMs = 148;
+    cudaMalloc(&pubKey, sizeof(unsigned long long) * NB * numSMs);
+    cudaMalloc(&pubRows, sizeof(double) * NB * numSMs * NB);
+    cudaMalloc(&pubDiag, sizeof(double) * NB * NB);
+    cudaMalloc(&barCounter, sizeof(unsigned int));
+    cudaFuncSetAttribute(lu_panel_coop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         kPanelMaxRowsPerCta * kSlabPitch * (int)sizeof(double));
+  }
+  cudaMemsetAsync(barCounter, 0, sizeof(unsigned int), s);
+  unsigned int barrierBase = 0;
   for (int j0 = 0; j0 < k; j0 += NB) {
     int nb = k - j0 < NB ? k - j0 : NB;
-    lu_panel_kernel<<<1, 1024, 0, s>>>(A, k, ld, j0, nb, dIpiv, dInfo, singularTol);
+    const int nrows = k - j0;
+    int G = (nrows + 31) / 32; // at least 32 rows per CTA
+    if (G > numSMs)
+      G = numSMs;
+    if (G < 1)
+      G = 1;
+    int R = (nrows + G - 1) / G;
+    if (R <= kPanelMaxRowsPerCta) {
+      double *Aarg = A;
+      int karg = k, ldarg = ld, j0arg = j0, nbarg = nb, Rarg = R;
+      double tolarg = singularTol;
+      void *args[] = {&Aarg, &karg, &ldarg, &j0arg, &nbarg, &Rarg, &dIpiv, &dInfo, &tolarg,
+                      &pubKey, &pubRows, &pubDiag, &barCounter, &barrierBase};
+      cudaLaunchCooperativeKernel((void *)lu_panel_coop_kernel, dim3(G), dim3(256), args,
+                                  (size_t)R * kSlabPitch * sizeof(double), s);
+      barrierBase += (unsigned int)nb * (unsigned int)G;
+    } else {
+      lu_panel_kernel<<<1, 1024, 0, s>>>(A, k, ld, j0, nb, dIpiv, dInfo, singularTol);
+    }
     // interchanges on the columns left and right of the panel
     if (j0 > 0)
       lu_swap_kernel<<<(j0 + 127) / 128, 128, 0, s>>>(A, ld, j0, nb, dIpiv, 0, j0);

@@ -260,18 +260,21 @@ __global__ void __launch_bounds__(1024, 1)
   __syncthreads();
   const double *__restrict__ rho = d.rho;
   // bounds of this warp's column, fetched one tile ahead (global, L2 resident)
+  // (raw values are kept in registers and only consumed one iteration later, so the loads never
+  // stall the warp that issued them)
   int nb0 = 0, nb1 = 0;
   auto fetchBounds = [&](int i) {
     const int4 dn = sdesc[i];
-    nb0 = gwarp < dn.y ? colStart[dn.x + gwarp] - dn.z : 0;
-    nb1 = gwarp < dn.y ? colStart[dn.x + gwarp + 1] - dn.z : 0;
+    const int c = dn.x + min(gwarp, dn.y - 1);
+    nb0 = __ldg(colStart + c);
+    nb1 = __ldg(colStart + c + 1);
   };
   if (myTiles > 0)
     fetchBounds(0);
   for (int it = 0; it < myTiles; it++) {
     const int stage = it % kPriceStages;
     const int4 ds = sdesc[it];
-    const int b0 = nb0, b1 = nb1;
+    const int b0 = nb0 - ds.z, b1 = nb1 - ds.z;
     if (it + 1 < myTiles)
       fetchBounds(it + 1);
     mbar_wait(&full[stage], (unsigned)((it / kPriceStages) & 1));

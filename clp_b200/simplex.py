@@ -16,6 +16,10 @@ from . import _capi
 from ._capi import c_double_p, c_int_p, c_ubyte_p
 
 
+class NoDeviceError(RuntimeError):
+    pass
+
+
 def _dp(a):
     return a.ctypes.data_as(c_double_p)
 
@@ -28,8 +32,18 @@ def _up(a):
     return a.ctypes.data_as(c_ubyte_p)
 
 
-class NoDeviceError(RuntimeError):
-    pass
+
+
+def denseInvert(a):
+    """Inverse of a dense matrix by the refactorization kernels (blocked LU with partial
+    pivoting + blocked substitution).  Returns (info, inverse)."""
+    a = np.asfortranarray(a, dtype=np.float64)
+    k = a.shape[0]
+    x = np.zeros((k, k), dtype=np.float64, order="F")
+    info = _capi.lib().Clpb_denseInvert(int(k), _dp(a), _dp(x))
+    if info == _capi.NO_DEVICE:
+        raise NoDeviceError("clp_b200 needs a CUDA device (no CPU fallback)")
+    return info, x
 
 
 class ClpSimplex:

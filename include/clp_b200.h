@@ -102,6 +102,10 @@ int Clpb_times(Clpb_Simplex *model, double scalar, const double *x, double *y);
 int Clpb_dualColumn(Clpb_Simplex *model, const double *alphaRow, const double *dj,
                     const unsigned char *status, int direction, double infeasibility,
                     double *theta);
+/* The dense kernel of the refactorization on its own (CoinAbcDgetrf + inverse,
+   src/AbcSimplexParallel.cpp:2491): a[k*k] column-major in, x = a^-1 column-major out.
+   Returns 0, or 1 + the index of the first column without an acceptable pivot. */
+int Clpb_denseInvert(int k, const double *a, double *x);
 /* run the startup of dual() (basis from status, factorize, computePrimals/Duals) and then
    'count' iterations; DSE weights by pivot row (ClpDualRowSteepest::weights_) */
 int Clpb_startup(Clpb_Simplex *model);

@@ -133,6 +133,29 @@ def test_unit_test_3x5_primals():
     np.testing.assert_allclose(sol[:5], [20.0 / 7.0, 3.0, 0.0, 0.0, 23.0 / 7.0], rtol=1e-12, atol=1e-12)
 
 
+@pytest.mark.parametrize("k", [1, 5, 31, 33, 100, 257, 700, 1500])
+def test_dense_invert(k):
+    """the dense LU + inverse of the refactorization (cooperative multi-CTA panel, TRSM, DGEMM)"""
+    rng = np.random.default_rng(k)
+    a = rng.standard_normal((k, k)) + np.diag(rng.uniform(0.5, 1.5, size=k) * np.sqrt(k) * rng.choice([-1, 1], size=k))
+    # make partial pivoting matter: shuffle rows
+    a = a[rng.permutation(k)]
+    info, x = clp_b200.denseInvert(a)
+    assert info == 0
+    ref = np.linalg.inv(a)
+    np.testing.assert_allclose(x, ref, rtol=1e-9, atol=1e-9 * np.abs(ref).max())
+    res = np.abs(a @ x - np.eye(k)).max()
+    assert res < 1e-10 * k
+
+
+def test_dense_invert_singular():
+    rng = np.random.default_rng(0)
+    a = rng.standard_normal((64, 64))
+    a[:, 40] = a[:, 3] * 2.0 - a[:, 7]
+    info, _ = clp_b200.denseInvert(a)
+    assert info > 0
+
+
 # ------------------------------------------------------------------ ratio test
 def test_dual_column_against_oracle():
     lp = G.random_sparse_lp(200, 3000, 0.03, 21)
