@@ -267,6 +267,13 @@ int Engine::setupDevice()
   d.uwork = dalloc<double>(m);
   d.ywork = dalloc<double>((size_t)6 * roundUp(m, 8));
   d.swork = dalloc<double>(roundUp(m, 8));
+  d.flipAcc = dalloc<long long>(m);
+  CUDA_OK(cudaMemset(d.flipAcc, 0, sizeof(long long) * m));
+  d.tailCounter = dalloc<unsigned int>(16);
+  CUDA_OK(cudaMemset(d.tailCounter, 0, sizeof(unsigned int) * 16));
+  d.amax = 1.0;
+  for (long long e = 0; e < nnz; e++)
+    d.amax = std::max(d.amax, std::fabs(hVal[e]));
   d.mu = dalloc<double>((size_t)3 * d.tmax);
   d.nu = dalloc<double>(d.tmax);
   d.histWeight = dalloc<unsigned long long>(kHistBuckets);
@@ -386,6 +393,8 @@ void Engine::resetStateForRun()
   CUDA_OK(cudaMemcpy(d.upper, hUpper.data(), sizeof(double) * nm, cudaMemcpyHostToDevice));
   CUDA_OK(cudaMemset(d.fake, 0, nm));
   CUDA_OK(cudaMemset(d.st, 0, sizeof(IterState)));
+  CUDA_OK(cudaMemset(d.flipAcc, 0, sizeof(long long) * m));
+  CUDA_OK(cudaMemset(d.tailCounter, 0, sizeof(unsigned int) * 16));
   d.primalTolerance = primalTolerance;
   d.dualTolerance = dualTolerance;
   d.acceptablePivot = acceptablePivot;
@@ -608,13 +617,13 @@ int Engine::refresh()
 }
 
 // ---------------------------------------------------------------------------------------
+// One iteration = 17 kernels (18 when column-sharded).  CHUZR is not among them: the row of the
+// next iteration is chosen by the update kernel of the previous one, and launch_chuzr() runs once
+// at the start of every batch (enqueueBatchStart).
 void Engine::enqueueIteration(bool timed, int slot)
 {
   cudaEvent_t *ev = timed ? &events[(size_t)slot * 8] : nullptr;
   g_kernelTimers = timed ? &kernelTimers[slot] : nullptr;
-  if (timed)
-    cudaEventRecord(ev[0], stream);
-  launch_chuzr(d, stream);
   if (timed)
     cudaEventRecord(ev[1], stream);
   launch_btran_unit(d, true, stream);
@@ -642,14 +651,21 @@ void Engine::enqueueIteration(bool timed, int slot)
   launch_dual_update_and_flips(d, d.flipBits, stream);
   if (timed)
     cudaEventRecord(ev[5], stream);
-  launch_ftran(d, 3, true, stream);
+  launch_ftran_iteration(d, stream);
   if (timed)
     cudaEventRecord(ev[6], stream);
   launch_pivot_updates(d, stream);
   if (timed)
     cudaEventRecord(ev[7], stream);
   g_kernelTimers = nullptr;
-  kernelLaunches += 2 + 4 + 2 + 6 + 4 + 5 + 4;
+  kernelLaunches += 3 + 2 + 4 + 3 + 5 + 1 + (worldSize > 1 ? 3 : 0);
+}
+
+// start of a batch: stand-alone CHUZR (2 kernels)
+void Engine::enqueueBatchStart()
+{
+  launch_chuzr(d, stream);
+  kernelLaunches += 2;
 }
 
 void Engine::buildIterationGraph()
@@ -759,6 +775,10 @@ int Engine::dual()
     if (timing)
       count = std::min(count, 16);
     const int before = hState->iterations;
+    cudaEvent_t evChuzr0 = timing ? events[0] : nullptr;
+    if (timing)
+      cudaEventRecord(evChuzr0, stream);
+    enqueueBatchStart();
     if (useGraph && !timing) {
       buildIterationGraph();
       for (int b = 0; b < count; b++)
@@ -774,7 +794,10 @@ int Engine::dual()
     if (timing) {
       for (int b = 0; b < done; b++) {
         float ms[7];
-        for (int q = 0; q < 7; q++)
+        ms[0] = 0.0f; // CHUZR is fused into the previous iteration's update kernel
+        if (b == 0)
+          cudaEventElapsedTime(&ms[0], events[0], events[1]); // the batch's stand-alone CHUZR
+        for (int q = 1; q < 7; q++)
           cudaEventElapsedTime(&ms[q], events[(size_t)b * 8 + q], events[(size_t)b * 8 + q + 1]);
         phase.chuzr += ms[0];
         phase.btran += ms[1];
@@ -1011,6 +1034,7 @@ int Engine::iterate(int count)
     int c = std::min(count, d.recCap);
     fetchState();
     const int before = hState->iterations;
+    enqueueBatchStart();
     for (int b = 0; b < c; b++)
       enqueueIteration(false, b);
     fetchState();

@@ -69,6 +69,9 @@ struct IterState {
   int costShifts;        // number of cost shifts since they were last removed
   int bucket1;           // level-1 ratio bucket in which the BFRT slope is exhausted (-1: none)
   unsigned long long residual; // fixed-point slope still to absorb inside bucket1
+  // bound-flip right-hand side in fixed point (order independent => bit-identical on every rank)
+  unsigned long long flipMaxBits; // max range (u-l) over this iteration's flips (double bits)
+  double flipScale, flipInvScale; // contribution * flipScale is accumulated as int64
 };
 
 struct IterRecord { // what the host reads back per iteration
@@ -132,6 +135,9 @@ struct DeviceModel {
   double *ywork;      // [3 x k] + scratch
   double *uwork;      // [m] BTRAN input after eta transposes
   double *swork;      // [k]
+  long long *flipAcc; // [m] fixed-point accumulator of the bound-flip right-hand side (zero when idle)
+  double amax;        // max(1, max |a_ij|): bound for the fixed-point scale of flipAcc
+  unsigned int *tailCounter; // [16] last-block-done tickets (one per kernel that has a tail)
   double *mu;         // [3 x tmax]
   double *nu;         // [tmax]
   // ratio test
@@ -160,6 +166,7 @@ extern KernelTimers *g_kernelTimers; // nullptr outside timing mode (engine.cu)
 // solve.cu
 void launch_ftran(const DeviceModel &d, int nrhs, bool applyEtas, cudaStream_t s);
 void launch_btran_unit(const DeviceModel &d, bool checkState, cudaStream_t s); // rho = B^-T e_r (r = st->pivotRow)
+void launch_ftran_iteration(const DeviceModel &d, cudaStream_t s); // 3 rhs + etas + pivot scalars (tail)
 void launch_eta_rowvec(const DeviceModel &d, int mode, bool checkState, cudaStream_t s);
 void launch_ftran_buffer(const DeviceModel &d, double *buf, int nrhs, bool applyEtas, cudaStream_t s);
 void launch_btran_dense(const DeviceModel &d, double *vec, bool applyEtas, cudaStream_t s); // vec(m) in/out
@@ -173,7 +180,7 @@ void launch_times_rows(const DeviceModel &d, const double *x, double *y, double 
                        cudaStream_t s);
 void launch_chuzc(const DeviceModel &d, cudaStream_t s);
 // update.cu
-void launch_chuzr(const DeviceModel &d, cudaStream_t s);
+void launch_chuzr(const DeviceModel &d, cudaStream_t s); // stand-alone CHUZR (start of a batch)
 void launch_dual_update_and_flips(const DeviceModel &d, unsigned int *flipBits, cudaStream_t s);
 void launch_pivot_updates(const DeviceModel &d, cudaStream_t s);
 void launch_make_dual_feasible(const DeviceModel &d, double dualBound, int *counters, cudaStream_t s);

@@ -129,6 +129,7 @@ private:
   int refactor();          // factorize current basis (repairs singular bases)
   int refresh();           // refactor + computeDuals + makeDualFeasible + computePrimals
   void enqueueIteration(bool timed, int slot);
+  void enqueueBatchStart();
   void fetchState();
   void downloadSolution();
   int defaultFactorizationFrequency() const;

@@ -323,59 +323,75 @@ __global__ void __launch_bounds__(128)
       col[i] = x[i];
 }
 
-// C[M x N] -= A[M x K] * B[K x N]  (column major).  64x64 tile per CTA, 4x4 per thread.
+// C[M x N] -= A[M x K] * B[K x N]  (column major, fp64 FMA).  128x128 tile per CTA, 256 threads as
+// 16 x 16, 8x8 register tile per thread (rows tx + 16a, columns ty + 16b), K in chunks of 16 staged
+// through shared memory with the next chunk prefetched into registers.  The reference's dense tail
+// uses an 8x8-blocked CoinAbcDgemm the same way (src/CoinAbcHelperFunctions.cpp:1658).
+constexpr int GT = 128, GK = 16;
 __global__ void __launch_bounds__(256)
     gemm_sub_kernel(double *__restrict__ C, int ldc, const double *__restrict__ A, int lda,
                     const double *__restrict__ B, int ldb, int M, int N, int K)
 {
-  __shared__ double As[16][64 + 1];
-  __shared__ double Bs[16][64 + 1];
+  __shared__ double As[GK][GT + 1];
+  __shared__ double Bs[GK][GT + 1];
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-  const int m0 = blockIdx.x * 64, n0 = blockIdx.y * 64;
-  double acc[4][4];
+  const int m0 = blockIdx.x * GT, n0 = blockIdx.y * GT;
+  double acc[8][8];
 #pragma unroll
-  for (int a = 0; a < 4; a++)
+  for (int a = 0; a < 8; a++)
 #pragma unroll
-    for (int b = 0; b < 4; b++)
+    for (int b = 0; b < 8; b++)
       acc[a][b] = 0.0;
-  for (int k0 = 0; k0 < K; k0 += 16) {
-    // A tile: 64 rows x 16 cols ; B tile: 16 rows x 64 cols
-    for (int e = threadIdx.x; e < 64 * 16; e += 256) {
-      int i = e & 63, l = e >> 6;
-      int gi = m0 + i, gl = k0 + l;
-      As[l][i] = (gi < M && gl < K) ? A[(size_t)gl * lda + gi] : 0.0;
+  // this thread's share of a chunk: 8 elements of the A tile, 8 of the B tile
+  double pa[8], pb[8];
+  auto fetch = [&](int k0) {
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+      const int e = threadIdx.x + 256 * q;
+      const int i = e & (GT - 1), l = e >> 7; // A tile: 128 rows x 16 k
+      const int gi = m0 + i, gl = k0 + l;
+      pa[q] = (gi < M && gl < K) ? A[(size_t)gl * lda + gi] : 0.0;
+      const int lb = e & (GK - 1), jn = e >> 4; // B tile: 16 k x 128 columns
+      const int glb = k0 + lb, gj = n0 + jn;
+      pb[q] = (glb < K && gj < N) ? B[(size_t)gj * ldb + glb] : 0.0;
     }
-    for (int e = threadIdx.x; e < 64 * 16; e += 256) {
-      int l = e & 15, jn = e >> 4;
-      int gl = k0 + l, gj = n0 + jn;
-      Bs[l][jn] = (gl < K && gj < N) ? B[(size_t)gj * ldb + gl] : 0.0;
+  };
+  fetch(0);
+  for (int k0 = 0; k0 < K; k0 += GK) {
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+      const int e = threadIdx.x + 256 * q;
+      As[e >> 7][e & (GT - 1)] = pa[q];
+      Bs[e & (GK - 1)][e >> 4] = pb[q];
     }
     __syncthreads();
+    if (k0 + GK < K)
+      fetch(k0 + GK);
 #pragma unroll
-    for (int l = 0; l < 16; l++) {
-      double av[4], bv[4];
+    for (int l = 0; l < GK; l++) {
+      double av[8], bv[8];
 #pragma unroll
-      for (int a = 0; a < 4; a++)
+      for (int a = 0; a < 8; a++)
         av[a] = As[l][tx + 16 * a];
 #pragma unroll
-      for (int b = 0; b < 4; b++)
+      for (int b = 0; b < 8; b++)
         bv[b] = Bs[l][ty + 16 * b];
 #pragma unroll
-      for (int a = 0; a < 4; a++)
+      for (int a = 0; a < 8; a++)
 #pragma unroll
-        for (int b = 0; b < 4; b++)
+        for (int b = 0; b < 8; b++)
           acc[a][b] = fma(av[a], bv[b], acc[a][b]);
     }
     __syncthreads();
   }
 #pragma unroll
-  for (int b = 0; b < 4; b++) {
-    int gj = n0 + ty + 16 * b;
+  for (int b = 0; b < 8; b++) {
+    const int gj = n0 + ty + 16 * b;
     if (gj >= N)
       continue;
 #pragma unroll
-    for (int a = 0; a < 4; a++) {
-      int gi = m0 + tx + 16 * a;
+    for (int a = 0; a < 8; a++) {
+      const int gi = m0 + tx + 16 * a;
       if (gi < M)
         C[(size_t)gj * ldc + gi] -= acc[a][b];
     }
@@ -387,7 +403,7 @@ static void gemm_sub(double *C, int ldc, const double *A, int lda, const double 
 {
   if (M <= 0 || N <= 0 || K <= 0)
     return;
-  dim3 grid((M + 63) / 64, (N + 63) / 64);
+  dim3 grid((M + GT - 1) / GT, (N + GT - 1) / GT);
   gemm_sub_kernel<<<grid, 256, 0, s>>>(C, ldc, A, lda, B, ldb, M, N, K);
 }
 
@@ -519,21 +535,36 @@ int dense_invert(double *A, double *X, int k, int ld, int *dIpiv, int *dPerm, in
     size_t total = (size_t)ld * k;
     set_permuted_identity_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(X, k, ld, dPerm);
   }
+  // Two-level blocking: triangular solves with the NB x NB diagonal blocks, rank-NB updates only
+  // inside an outer block of OB columns, one rank-OB update per outer block for the rest (the bulk
+  // of the 2k^3 flops then runs with K = OB, where the DGEMM is not bound by the C traffic).
+  constexpr int OB = 128;
   // forward: X := L^-1 X
-  for (int j0 = 0; j0 < k; j0 += NB) {
-    int nb = k - j0 < NB ? k - j0 : NB;
-    trsm_kernel<<<(k + 127) / 128, 128, 0, s>>>(A, ld, X, ld, j0, nb, 0, k, true);
-    int r0 = j0 + nb;
-    if (r0 < k)
-      gemm_sub(X + r0, ld, A + (size_t)j0 * ld + r0, ld, X + j0, ld, k - r0, k, nb, s);
+  for (int J0 = 0; J0 < k; J0 += OB) {
+    const int J1 = J0 + OB < k ? J0 + OB : k;
+    for (int j0 = J0; j0 < J1; j0 += NB) {
+      int nb = J1 - j0 < NB ? J1 - j0 : NB;
+      trsm_kernel<<<(k + 127) / 128, 128, 0, s>>>(A, ld, X, ld, j0, nb, 0, k, true);
+      int r0 = j0 + nb;
+      if (r0 < J1)
+        gemm_sub(X + r0, ld, A + (size_t)j0 * ld + r0, ld, X + j0, ld, J1 - r0, k, nb, s);
+    }
+    if (J1 < k)
+      gemm_sub(X + J1, ld, A + (size_t)J0 * ld + J1, ld, X + J0, ld, k - J1, k, J1 - J0, s);
   }
   // backward: X := U^-1 X
-  int lastBlock = ((k - 1) / NB) * NB;
-  for (int j0 = lastBlock; j0 >= 0; j0 -= NB) {
-    int nb = k - j0 < NB ? k - j0 : NB;
-    trsm_kernel<<<(k + 127) / 128, 128, 0, s>>>(A, ld, X, ld, j0, nb, 0, k, false);
-    if (j0 > 0)
-      gemm_sub(X, ld, A + (size_t)j0 * ld, ld, X + j0, ld, j0, k, nb, s);
+  const int lastOuter = ((k - 1) / OB) * OB;
+  for (int J0 = lastOuter; J0 >= 0; J0 -= OB) {
+    const int J1 = J0 + OB < k ? J0 + OB : k;
+    const int lastInner = J0 + ((J1 - J0 - 1) / NB) * NB;
+    for (int j0 = lastInner; j0 >= J0; j0 -= NB) {
+      int nb = J1 - j0 < NB ? J1 - j0 : NB;
+      trsm_kernel<<<(k + 127) / 128, 128, 0, s>>>(A, ld, X, ld, j0, nb, 0, k, false);
+      if (j0 > J0)
+        gemm_sub(X + J0, ld, A + (size_t)j0 * ld + J0, ld, X + j0, ld, j0 - J0, k, nb, s);
+    }
+    if (J0 > 0)
+      gemm_sub(X, ld, A + (size_t)J0 * ld, ld, X + J0, ld, J0, k, J1 - J0, s);
   }
   zero_padding_kernel<<<(k + 255) / 256, 256, 0, s>>>(X, k, ld);
   return 0;

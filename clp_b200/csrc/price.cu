@@ -16,19 +16,9 @@
 // bound beyond theta* (atomicMin) and one pass picks the largest |alpha| inside
 // [theta*, harris] (atomicMax on a packed (|alpha|,sequence) key).  Candidates with a ratio
 // below theta* are "passed": the dual update flips them to their other bound (BFRT).
-#include "engine.cuh"
+#include "kernels_common.cuh"
 
 namespace clpb {
-
-__device__ __forceinline__ bool iter_active(const IterState *st) { return st->stop == 0; }
-
-__device__ __forceinline__ double warp_sum(double v)
-{
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1)
-    v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
 
 constexpr unsigned long long kFixOne = 1ull << 40; // fixed-point 1.0 (== infeasibility)
 constexpr unsigned long long kFixCap = 1ull << 41;
@@ -71,11 +61,9 @@ __device__ __forceinline__ bool candidate(const DeviceModel &d, int j, double al
   return true;
 }
 
-__device__ __forceinline__ void histogram_add(const DeviceModel &d, double a, double dtil,
-                                              bool boxed, double range, double infeas)
+// slope contribution of a candidate in 2^-40 fixed point relative to the primal infeasibility
+__device__ __forceinline__ unsigned long long slope_weight(double a, bool boxed, double range, double infeas)
 {
-  const double ratio = dtil / a;
-  const int b = ratio_bucket(ratio);
   unsigned long long w = kFixCap;
   if (boxed) {
     double v = a * range / infeas * 1099511627776.0;
@@ -83,7 +71,13 @@ __device__ __forceinline__ void histogram_add(const DeviceModel &d, double a, do
     if (w == 0ull)
       w = 1ull; // a bucket with a candidate is never "empty"
   }
-  atomicAdd(d.histWeight + b, w);
+  return w;
+}
+
+__device__ __forceinline__ void histogram_add(const DeviceModel &d, double a, double dtil,
+                                              bool boxed, double range, double infeas)
+{
+  atomicAdd(d.histWeight + ratio_bucket(dtil / a), slope_weight(a, boxed, range, infeas));
 }
 
 // alphaRow[j] = rho^T a_j for nonbasic, non-fixed columns j in [colBegin,colEnd) + histogram.
@@ -307,29 +301,33 @@ __global__ void __launch_bounds__(1024, 1)
 // Second half of PRICE: one thread per variable of the row.  Columns: apply the status mask and
 // the zero tolerance to the raw dot products; rows: alpha_{n+i} = -rho_i; both: ratio-test
 // candidate test + level-1 histogram (coalesced reads of status / dj / bounds).
-__global__ void row_finalize_kernel(DeviceModel d, int colBegin, int colEnd, bool fuseHist)
+__global__ void __launch_bounds__(256) row_finalize_kernel(DeviceModel d, int colBegin, int colEnd, bool fuseHist)
 {
   if (!iter_active(d.st))
     return;
   const int sigma = d.st->sigma;
   const double infeas = d.st->infeas;
-  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < d.nm; j += gridDim.x * blockDim.x) {
-    double alpha;
-    const unsigned char st = d.status[j];
-    if (j < d.n) {
-      if (j < colBegin || j >= colEnd)
-        continue;
-      alpha = (st == basic || st == isFixed) ? 0.0 : d.alphaRow[j];
-    } else {
-      alpha = (st == basic || st == isFixed) ? 0.0 : -d.rho[j - d.n];
+  // warp-uniform trip count: the aggregated histogram add is a warp collective
+  for (int base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31; base < d.nm; base += gridDim.x * blockDim.x) {
+    const int j = base + (threadIdx.x & 31);
+    bool cand = false;
+    double a = 1.0, dtil = 0.0, range = 0.0;
+    bool boxed = false;
+    if (j < d.nm && !(j < d.n && (j < colBegin || j >= colEnd))) {
+      double alpha;
+      const unsigned char st = d.status[j];
+      if (j < d.n)
+        alpha = (st == basic || st == isFixed) ? 0.0 : d.alphaRow[j];
+      else
+        alpha = (st == basic || st == isFixed) ? 0.0 : -d.rho[j - d.n];
+      if (fabs(alpha) < d.zeroTolerance)
+        alpha = 0.0;
+      d.alphaRow[j] = alpha;
+      cand = fuseHist && alpha != 0.0 && candidate(d, j, alpha, sigma, a, dtil, boxed, range);
     }
-    if (fabs(alpha) < d.zeroTolerance)
-      alpha = 0.0;
-    d.alphaRow[j] = alpha;
-    double a, dtil, range;
-    bool boxed;
-    if (fuseHist && alpha != 0.0 && candidate(d, j, alpha, sigma, a, dtil, boxed, range))
-      histogram_add(d, a, dtil, boxed, range, infeas);
+    if (fuseHist)
+      hist_add_aggregated(d.histWeight, cand ? ratio_bucket(dtil / a) : 0,
+                          cand ? slope_weight(a, boxed, range, infeas) : 0ull, cand);
   }
 }
 
@@ -358,20 +356,23 @@ __global__ void price_slack_kernel(DeviceModel d, bool fuseHist)
 
 // stand-alone histogram pass over a complete tableau row (column-sharded runs: after the
 // all-gather of the row; also used by the ratio-test parity tests)
-__global__ void histogram_kernel(DeviceModel d)
+__global__ void __launch_bounds__(256) histogram_kernel(DeviceModel d)
 {
   if (!iter_active(d.st))
     return;
   const int sigma = d.st->sigma;
   const double infeas = d.st->infeas;
-  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < d.nm; j += gridDim.x * blockDim.x) {
-    const double alpha = d.alphaRow[j];
-    if (alpha == 0.0)
-      continue;
-    double a, dtil, range;
-    bool boxed;
-    if (candidate(d, j, alpha, sigma, a, dtil, boxed, range))
-      histogram_add(d, a, dtil, boxed, range, infeas);
+  for (int base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31; base < d.nm; base += gridDim.x * blockDim.x) {
+    const int j = base + (threadIdx.x & 31);
+    bool cand = false;
+    double a = 1.0, dtil = 0.0, range = 0.0;
+    bool boxed = false;
+    if (j < d.nm) {
+      const double alpha = d.alphaRow[j];
+      cand = alpha != 0.0 && candidate(d, j, alpha, sigma, a, dtil, boxed, range);
+    }
+    hist_add_aggregated(d.histWeight, cand ? ratio_bucket(dtil / a) : 0,
+                        cand ? slope_weight(a, boxed, range, infeas) : 0ull, cand);
   }
 }
 void launch_histogram(const DeviceModel &d, cudaStream_t s)
@@ -553,46 +554,9 @@ __global__ void __launch_bounds__(1024) chuzc_scan1_kernel(DeviceModel d)
   }
 }
 
-// Level 2: candidates of the crossing bucket, next 12 bits of the ratio
-__global__ void chuzc_hist2_kernel(DeviceModel d)
-{
-  if (!iter_active(d.st))
-    return;
-  const int b1 = d.st->bucket1;
-  if (b1 < 0)
-    return;
-  const int sigma = d.st->sigma;
-  const double infeas = d.st->infeas;
-  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < d.nm; j += gridDim.x * blockDim.x) {
-    const double alpha = d.alphaRow[j];
-    if (alpha == 0.0)
-      continue;
-    double a, dtil, range;
-    bool boxed;
-    if (!candidate(d, j, alpha, sigma, a, dtil, boxed, range))
-      continue;
-    const double ratio = dtil / a;
-    const unsigned long long bits = (unsigned long long)__double_as_longlong(ratio);
-    if (((int)(bits >> 48) & (kHistBuckets - 1)) != b1)
-      continue;
-    const int sb = (int)(bits >> 36) & (kHist2Buckets - 1);
-    unsigned long long w = kFixCap;
-    if (boxed) {
-      double v = a * range / infeas * 1099511627776.0;
-      w = v >= 2199023255552.0 ? kFixCap : (unsigned long long)v;
-      if (w == 0ull)
-        w = 1ull;
-    }
-    atomicAdd(d.hist2Weight + sb, w);
-    atomicMin(d.hist2Min + sb, bits);
-  }
-}
-
 // Level-2 scan (single CTA, 4 sub-buckets per thread) -> theta*; also ||rho||^2 in a fixed order
-__global__ void __launch_bounds__(1024) chuzc_scan2_kernel(DeviceModel d)
+__device__ __forceinline__ void chuzc_scan2_body(const DeviceModel &d)
 {
-  if (!iter_active(d.st))
-    return;
   __shared__ unsigned long long sTot[32];
   __shared__ int sLast[32];
   __shared__ double sNorm[32];
@@ -607,8 +571,8 @@ __global__ void __launch_bounds__(1024) chuzc_scan2_kernel(DeviceModel d)
 #pragma unroll
     for (int q = 0; q < 4; q++) {
       const int b = tid * 4 + q;
-      w[q] = d.hist2Weight[b];
-      mn[q] = d.hist2Min[b];
+      w[q] = __ldcg(d.hist2Weight + b); // written by the other CTAs of this kernel (L2)
+      mn[q] = __ldcg(d.hist2Min + b);
       tot += w[q];
       if (mn[q] != kSentinel)
         last = b;
@@ -675,8 +639,41 @@ __global__ void __launch_bounds__(1024) chuzc_scan2_kernel(DeviceModel d)
     int lastAll = -1;
     for (int q = 0; q < 32; q++)
       lastAll = max(lastAll, sLast[q]);
-    st->thetaStar = __longlong_as_double((long long)d.hist2Min[lastAll]);
+    st->thetaStar = __longlong_as_double((long long)__ldcg(d.hist2Min + lastAll));
   }
+}
+
+// Level 2: candidates of the crossing bucket, next 12 bits of the ratio (all CTAs); the last CTA
+// then scans the 4096 sub-buckets (chuzc_scan2_body).  1024 threads per CTA.
+__global__ void __launch_bounds__(1024) chuzc_hist2_kernel(DeviceModel d)
+{
+  if (!iter_active(d.st))
+    return;
+  const int b1 = d.st->bucket1;
+  if (b1 >= 0) {
+    const int sigma = d.st->sigma;
+    const double infeas = d.st->infeas;
+    for (int base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31; base < d.nm; base += gridDim.x * blockDim.x) {
+      const int j = base + (threadIdx.x & 31);
+      bool cand = false;
+      double a = 1.0, dtil = 0.0, range = 0.0;
+      bool boxed = false;
+      unsigned long long bits = 0ull;
+      if (j < d.nm) {
+        const double alpha = d.alphaRow[j];
+        if (alpha != 0.0 && candidate(d, j, alpha, sigma, a, dtil, boxed, range)) {
+          bits = (unsigned long long)__double_as_longlong(dtil / a);
+          cand = ((int)(bits >> 48) & (kHistBuckets - 1)) == b1;
+        }
+      }
+      const int sb = (int)(bits >> 36) & (kHist2Buckets - 1);
+      hist_add_aggregated(d.hist2Weight, sb, cand ? slope_weight(a, boxed, range, infeas) : 0ull, cand);
+      hist_min_aggregated(d.hist2Min, sb, bits, cand);
+    }
+  }
+  if (!last_block_done(d.tailCounter + TAIL_HIST2))
+    return;
+  chuzc_scan2_body(d);
 }
 
 // Harris bound over candidates with ratio >= theta*  (ClpSimplexDual.cpp:4331-4395 upperTheta)
@@ -737,14 +734,13 @@ __global__ void chuzc_select_kernel(DeviceModel d)
     best = max(best, __shfl_xor_sync(0xffffffffu, best, o));
   if ((threadIdx.x & 31) == 0 && best != 0ull)
     atomicMax(&d.st->chuzcKey, best);
-}
-
-__global__ void chuzc_finish_kernel(DeviceModel d)
-{
-  IterState *st = d.st;
-  if (!iter_active(st))
+  // tail (last CTA, one thread): decode the winner
+  if (!last_block_done(d.tailCounter + TAIL_SELECT))
     return;
-  const unsigned long long key = st->chuzcKey;
+  if (threadIdx.x != 0)
+    return;
+  IterState *st = d.st;
+  const unsigned long long key = atomicMax(&st->chuzcKey, 0ull);
   if (key == 0ull) {
     st->stop = STOP_NO_COLUMN;
     return;
@@ -763,12 +759,13 @@ void launch_chuzc(const DeviceModel &d, cudaStream_t s)
   int blocks = (d.nm + 255) / 256;
   if (blocks > 148 * 4)
     blocks = 148 * 4;
+  int blocks2 = (d.nm + 1023) / 1024;
+  if (blocks2 > 148)
+    blocks2 = 148;
   chuzc_scan1_kernel<<<kHistBuckets / 1024, 1024, 0, s>>>(d);
-  chuzc_hist2_kernel<<<blocks, 256, 0, s>>>(d);
-  chuzc_scan2_kernel<<<1, 1024, 0, s>>>(d);
+  chuzc_hist2_kernel<<<blocks2, 1024, 0, s>>>(d); // + level-2 scan in its tail
   chuzc_harris_kernel<<<blocks, 256, 0, s>>>(d);
-  chuzc_select_kernel<<<blocks, 256, 0, s>>>(d);
-  chuzc_finish_kernel<<<1, 1, 0, s>>>(d);
+  chuzc_select_kernel<<<blocks, 256, 0, s>>>(d); // + decode of the winner in its tail
 }
 
 // ---------------------------------------------------------------------------------------

@@ -13,26 +13,11 @@
 //                           rho_N = Ninv^T * s                    (GEMV, HBM stream of NinvT)
 // Up to three right-hand sides share one pass over Ninv / W (the reference's
 // updateTwoColumnsFT fusion, plus the bound-flip column of ClpSimplexDual.cpp:1533).
-#include "engine.cuh"
+#include "kernels_common.cuh"
 
 namespace clpb {
 
-__device__ __forceinline__ int decode_row(unsigned long long key) { return (int)(key & 0xFFFFFull); }
-
-__device__ __forceinline__ bool iter_active(const IterState *st)
-{
-  return st->stop == 0;
-}
-
 static inline int roundUp8(int v) { return (v + 7) / 8 * 8; }
-
-__device__ __forceinline__ double warp_sum(double v)
-{
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1)
-    v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
 
 // ---------------------------------------------------------------------------------------
 // gather b_N : xg[c][j] = b_c[nucRow[j]]
@@ -206,43 +191,50 @@ __global__ void pfi_mu_kernel(DeviceModel d, const double *__restrict__ x, int x
       d.mu[(size_t)c * d.tmax + i] = acc[c];
 }
 
-// x_c[p] -= sum_{i<t} W[p][i] * mu_c[i]   (one warp per position)
+// x_c[p] -= sum_{i<t} W[p][i] * mu_c[i]   (one warp per position).  pivotTail: the last CTA then
+// evaluates the accuracy gate and the primal step (pivot_scalars_body) on the finished columns.
 template <int NRHS>
 __global__ void pfi_apply_kernel(DeviceModel d, double *__restrict__ x, int xstride,
-                                 bool checkState)
+                                 bool checkState, bool pivotTail)
 {
   if (checkState && !iter_active(d.st))
     return;
   const int t = d.st->numEtas;
-  if (t == 0)
-    return;
-  const int lane = threadIdx.x & 31;
-  const int warpsPerBlock = blockDim.x >> 5;
-  for (int p = blockIdx.x * warpsPerBlock + (threadIdx.x >> 5); p < d.m;
-       p += gridDim.x * warpsPerBlock) {
-    const double *wrow = d.W + (size_t)p * d.tmax;
-    double acc[NRHS];
-#pragma unroll
-    for (int c = 0; c < NRHS; c++)
-      acc[c] = 0.0;
-    for (int i = lane; i < t; i += 32) {
-      double w = wrow[i];
+  if (t > 0) {
+    const int lane = threadIdx.x & 31;
+    const int warpsPerBlock = blockDim.x >> 5;
+    for (int p = blockIdx.x * warpsPerBlock + (threadIdx.x >> 5); p < d.m;
+         p += gridDim.x * warpsPerBlock) {
+      const double *wrow = d.W + (size_t)p * d.tmax;
+      double acc[NRHS];
 #pragma unroll
       for (int c = 0; c < NRHS; c++)
-        acc[c] = fma(w, d.mu[(size_t)c * d.tmax + i], acc[c]);
+        acc[c] = 0.0;
+      for (int i = lane; i < t; i += 32) {
+        double w = wrow[i];
+#pragma unroll
+        for (int c = 0; c < NRHS; c++)
+          acc[c] = fma(w, d.mu[(size_t)c * d.tmax + i], acc[c]);
+      }
+#pragma unroll
+      for (int c = 0; c < NRHS; c++)
+        acc[c] = warp_sum(acc[c]);
+      if (lane == 0)
+        for (int c = 0; c < NRHS; c++)
+          x[(size_t)c * xstride + p] -= acc[c];
     }
-#pragma unroll
-    for (int c = 0; c < NRHS; c++)
-      acc[c] = warp_sum(acc[c]);
-    if (lane == 0)
-      for (int c = 0; c < NRHS; c++)
-        x[(size_t)c * xstride + p] -= acc[c];
   }
+  if (!pivotTail)
+    return;
+  if (!last_block_done(d.tailCounter + TAIL_PFI_APPLY))
+    return;
+  if (threadIdx.x == 0)
+    pivot_scalars_body(d);
 }
 
 template <int NRHS>
 static void ftran_impl(const DeviceModel &d, double *b, bool applyEtas, bool checkState,
-                       cudaStream_t s)
+                       cudaStream_t s, bool pivotTail = false)
 {
   const int m = d.m;
   // fixed launch shapes (grid-stride kernels read k from the device-side FactorDesc)
@@ -264,7 +256,7 @@ static void ftran_impl(const DeviceModel &d, double *b, bool applyEtas, bool che
     int pblocks = (m + 7) / 8;
     if (pblocks > 148 * 8)
       pblocks = 148 * 8;
-    pfi_apply_kernel<NRHS><<<pblocks, 256, 0, s>>>(d, b, m, checkState);
+    pfi_apply_kernel<NRHS><<<pblocks, 256, 0, s>>>(d, b, m, checkState, pivotTail);
   }
 }
 
@@ -279,6 +271,13 @@ void launch_ftran(const DeviceModel &d, int nrhs, bool applyEtas, cudaStream_t s
     ftran_impl<3>(d, d.rhs3, applyEtas, applyEtas, s);
 }
 
+// The three FTRANs of a simplex iteration (a_q, rho -> tau, bound-flip column) with the eta panel
+// and, as the tail of the last kernel, the pivot accuracy gate / primal step length.
+void launch_ftran_iteration(const DeviceModel &d, cudaStream_t s)
+{
+  ftran_impl<3>(d, d.rhs3, true, true, s, true);
+}
+
 // ---------------------------------------------------------------------------------------
 // out[j] = scale * sum_{i>=j, i<t} Ginv[i][j] * W[row][i]   for j < t
 //   mode 0 : nu (BTRAN eta transposes), vec = W[pivot row][:]
@@ -286,40 +285,10 @@ void launch_ftran(const DeviceModel &d, int nrhs, bool applyEtas, cudaStream_t s
 //   mode 2 : nu for a general BTRAN, vec = d.mu (the t dot products W_i . v)
 __global__ void __launch_bounds__(256) eta_rowvec_kernel(DeviceModel d, int mode, bool checkState)
 {
+  __shared__ double part[8][33];
   if (checkState && !iter_active(d.st))
     return;
-  const int t = d.st->numEtas;
-  const int j0 = blockIdx.x * 32;
-  if (j0 >= t && !(mode == 1 && blockIdx.x == 0))
-    return;
-  const int r = d.st->pivotRow;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int j = j0 + lane;
-  __shared__ double part[8][33];
-  const double *wrow = mode == 2 ? d.mu : d.W + (size_t)r * d.tmax;
-  double acc = 0.0;
-  if (j < t)
-    for (int i = j0 + warp; i < t; i += 8) // rows below j0 contribute nothing (lower triangular)
-      if (i >= j)
-        acc = fma(d.Ginv[(size_t)i * d.tmax + j], wrow[i], acc);
-  part[warp][lane] = acc;
-  __syncthreads();
-  if (warp == 0) {
-    double s = 0.0;
-#pragma unroll
-    for (int w = 0; w < 8; w++)
-      s += part[w][lane];
-    if (mode != 1) {
-      if (j < t)
-        d.nu[j] = s;
-    } else {
-      const double dinv = 1.0 / d.st->alphaCol;
-      if (j < t)
-        d.Ginv[(size_t)t * d.tmax + j] = -s * dinv;
-      if (blockIdx.x == 0 && lane == 0)
-        d.Ginv[(size_t)t * d.tmax + t] = dinv;
-    }
-  }
+  eta_rowvec_body(d, mode, blockIdx.x, part);
 }
 void launch_eta_rowvec(const DeviceModel &d, int mode, bool checkState, cudaStream_t s)
 {
@@ -385,12 +354,68 @@ __global__ void btran_s_kernel(DeviceModel d, bool checkState)
     d.swork[k + threadIdx.x] = 0.0;
 }
 
+// u_p = [p == r] - sum of nu over the etas that pivoted on position p (newest first: fixed order)
+__device__ __forceinline__ double btran_u_of(const DeviceModel &d, int p, int r, int t)
+{
+  double u = (p == r) ? 1.0 : 0.0;
+  if (t > 0) {
+    double sum = 0.0;
+    for (int e = d.etaLastOfPos[p]; e >= 0; e = d.etaPrevSame[e])
+      sum += d.nu[e];
+    u -= sum;
+  }
+  return u;
+}
+
+// Simplex BTRAN prelude in one kernel (u is sparse: nonzero only on r and the eta positions, so it
+// is evaluated where needed instead of being materialised first):
+//   rho_C = -u_C                                      (thread per position)
+//   s_j = u[nucRow[j]] + sum_{i in C} a_{i,col j} u_i (warp per nucleus column)
+__global__ void __launch_bounds__(256) btran_us_kernel(DeviceModel d, double *__restrict__ rhoOut)
+{
+  if (!iter_active(d.st))
+    return;
+  const int r = d.st->pivotRow, t = d.st->numEtas;
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < d.m; p += gridDim.x * blockDim.x)
+    if (d.posToNuc[p] < 0)
+      rhoOut[p] = -btran_u_of(d, p, r, t);
+  const int lane = threadIdx.x & 31;
+  const int k = d.fd->k, ldk = d.fd->ldk;
+  const int warpsPerBlock = blockDim.x >> 5;
+  for (int j = blockIdx.x * warpsPerBlock + (threadIdx.x >> 5); j < k; j += gridDim.x * warpsPerBlock) {
+    const int col = d.nucCol[j];
+    double acc = 0.0;
+    const int e1 = d.colStart[col + 1];
+    for (int e = d.colStart[col] + lane; e < e1; e += 32) {
+      const int i = d.rowIdx[e];
+      if (d.posToNuc[i] < 0) {
+        const double u = btran_u_of(d, i, r, t);
+        if (u != 0.0)
+          acc = fma(d.val[e], u, acc);
+      }
+    }
+    acc = warp_sum(acc);
+    if (lane == 0)
+      d.swork[j] = acc + btran_u_of(d, d.nucRow[j], r, t);
+  }
+  // zero the padding so the GEMV can run over ldk
+  if (blockIdx.x == 0 && threadIdx.x < 8 && k + threadIdx.x < ldk)
+    d.swork[k + threadIdx.x] = 0.0;
+}
+
+static void btran_gemv(const DeviceModel &d, double *rhoOut, bool checkState, cudaStream_t s);
+
 static void btran_tail(const DeviceModel &d, double *rhoOut, bool checkState, cudaStream_t s)
 {
   int sblocks = (d.m + 7) / 8;
   if (sblocks > 148 * 8)
     sblocks = 148 * 8;
   btran_s_kernel<<<sblocks, 256, 0, s>>>(d, checkState);
+  btran_gemv(d, rhoOut, checkState, s);
+}
+
+static void btran_gemv(const DeviceModel &d, double *rhoOut, bool checkState, cudaStream_t s)
+{
   int blocks = d.m < 148 * 8 ? d.m : 148 * 8;
   if (g_kernelTimers && checkState)
     cudaEventRecord(g_kernelTimers->btranGemv[0], s);
@@ -403,9 +428,13 @@ static void btran_tail(const DeviceModel &d, double *rhoOut, bool checkState, cu
 // rho = B_t^-T e_r with r = st->pivotRow ; result in d.rho
 void launch_btran_unit(const DeviceModel &d, bool checkState, cudaStream_t s)
 {
-  launch_eta_rowvec(d, 0, checkState, s); // no-op when numEtas == 0
-  btran_build_u_kernel<<<(d.m + 255) / 256, 256, 0, s>>>(d, d.rho, checkState, nullptr);
-  btran_tail(d, d.rho, checkState, s);
+  (void)checkState;
+  launch_eta_rowvec(d, 0, true, s); // no-op when numEtas == 0
+  int sblocks = (d.m + 7) / 8;
+  if (sblocks > 148 * 8)
+    sblocks = 148 * 8;
+  btran_us_kernel<<<sblocks, 256, 0, s>>>(d, d.rho);
+  btran_gemv(d, d.rho, true, s);
 }
 
 // s_i = W[:,i] . v   (one warp per eta; general BTRAN only -- the simplex BTRAN starts from a

@@ -10,15 +10,14 @@
 //   ClpSimplex::computePrimals / computeDuals  src/ClpSimplex.cpp:914 / :1164
 // All reductions are order independent (packed-key atomicMax/Min, integer atomics) or done
 // in a fixed order, so replicated ranks of a column-sharded run stay bit-identical.
-#include "engine.cuh"
+#include "kernels_common.cuh"
 
 namespace clpb {
 
-__device__ __forceinline__ bool iter_active(const IterState *st) { return st->stop == 0; }
-
-constexpr int kFlipScanLimit = 24; // above this many flips a CSR row pass builds the flip rhs
-
 // ------------------------------------------------------------------ CHUZR
+// Stand-alone row choice: used at the start of a batch of iterations (after a refresh the primal
+// values are new).  Inside a batch the row of the next iteration is chosen by the update kernel
+// of the previous one (iteration_update_kernel), which has every x_B and weight in registers.
 __global__ void chuzr_kernel(DeviceModel d)
 {
   if (!iter_active(d.st))
@@ -37,20 +36,7 @@ __global__ void chuzr_kernel(DeviceModel d)
     d.flipBits[w] = 0u;
   for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < d.m; p += gridDim.x * blockDim.x) {
     const int seq = d.pivotVariable[p];
-    const double v = d.sol[seq];
-    double inf = 0.0;
-    const double lo = d.lower[seq], up = d.upper[seq];
-    if (v < lo - tol)
-      inf = lo - v;
-    else if (v > up + tol)
-      inf = v - up;
-    if (inf > 0.0) {
-      double w = d.weights[p];
-      double score = inf * inf / w;
-      unsigned long long key =
-          ((unsigned long long)__double_as_longlong(score) & ~0xFFFFFull) | (unsigned long long)(0xFFFFF - p);
-      best = max(best, key);
-    }
+    best = max(best, chuzr_key(d.sol[seq], d.lower[seq], d.upper[seq], d.weights[p], tol, p));
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1)
@@ -59,24 +45,22 @@ __global__ void chuzr_kernel(DeviceModel d)
     atomicMax(&d.st->chuzrKey, best);
 }
 
-__global__ void chuzr_finish_kernel(DeviceModel d)
+// decode the packed argmax into pivotRow / seqOut / sigma / infeas (single thread).
+// coherentSol: the caller runs as the tail of a kernel that wrote d.sol in other CTAs.
+__device__ __forceinline__ void chuzr_finish_body(const DeviceModel &d, unsigned long long key, bool coherentSol)
 {
   IterState *st = d.st;
-  if (!iter_active(st))
-    return;
   if (st->numEtas >= d.tmax) {
     st->stop = STOP_ETAS_FULL;
     return;
   }
-  const unsigned long long key = st->chuzrKey;
-  st->chuzrKey = 0ull;
   if (key == 0ull) {
     st->stop = STOP_NO_ROW;
     return;
   }
   const int r = 0xFFFFF - (int)(key & 0xFFFFFull);
   const int seq = d.pivotVariable[r];
-  const double v = d.sol[seq];
+  const double v = coherentSol ? __ldcg(d.sol + seq) : d.sol[seq];
   st->pivotRow = r;
   st->seqOut = seq;
   if (v < d.lower[seq]) {
@@ -88,6 +72,16 @@ __global__ void chuzr_finish_kernel(DeviceModel d)
   }
   st->numFlips = 0;
   st->seqIn = -1;
+}
+
+__global__ void chuzr_finish_kernel(DeviceModel d)
+{
+  IterState *st = d.st;
+  if (!iter_active(st))
+    return;
+  const unsigned long long key = st->chuzrKey;
+  st->chuzrKey = 0ull;
+  chuzr_finish_body(d, key, false);
 }
 
 void launch_chuzr(const DeviceModel &d, cudaStream_t s)
@@ -102,72 +96,24 @@ void launch_chuzr(const DeviceModel &d, cudaStream_t s)
 }
 
 // ------------------------------------------------------------------ dual update + flips
-// dj -= thetaDual * sigma * alpha over the pivot row; variables whose dj changes sign flip to
-// the other bound when boxed, otherwise their cost is shifted (ClpSimplexDual.cpp:4705-4772).
-// flipFlag[j] (stored in d.fake's neighbour array, see engine.cu) marks flipped variables.
-__global__ void dual_update_kernel(DeviceModel d, unsigned int *__restrict__ flipBits)
+// Tail of dual_update_kernel (last CTA, 256 threads): ordered expansion of the flip bit mask into
+// flipList, numFlips, and the fixed-point scale of the bound-flip right-hand side.
+__device__ __forceinline__ void flip_collect_tail(const DeviceModel &d, const unsigned int *flipBits)
 {
-  if (!iter_active(d.st))
-    return;
-  const double theta = d.st->thetaDual;
-  const int sigma = d.st->sigma;
-  const int seqIn = d.st->seqIn;
-  const double tol = d.dualTolerance;
-  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < d.nm; j += gridDim.x * blockDim.x) {
-    const double alpha = d.alphaRow[j];
-    if (alpha != 0.0 && j != seqIn) {
-      const unsigned char st = d.status[j];
-      if (st != basic && st != isFixed) {
-        double dnew = d.dj[j] - theta * (sigma * alpha);
-        bool wrong = (st == atLowerBound && dnew < -tol) || (st == atUpperBound && dnew > tol);
-        if (wrong) {
-          const double lo = d.lower[j], up = d.upper[j];
-          if (up - lo < 1.0e29) {
-            if (st == atLowerBound) {
-              d.status[j] = atUpperBound;
-              d.sol[j] = up;
-            } else {
-              d.status[j] = atLowerBound;
-              d.sol[j] = lo;
-            }
-            atomicOr(flipBits + (j >> 5), 1u << (j & 31));
-          } else {
-            d.cost[j] -= dnew;
-            dnew = 0.0;
-            atomicAdd(&d.st->costShifts, 1);
-          }
-        } else if ((st == isFree || st == superBasic) && fabs(dnew) > tol) {
-          d.cost[j] -= dnew;
-          dnew = 0.0;
-          atomicAdd(&d.st->costShifts, 1);
-        }
-        d.dj[j] = dnew;
-      }
-    }
-  }
-}
-
-// single CTA: ordered expansion of the flip bit mask into flipList (ascending sequence => the
-// flip right-hand side is summed in a fixed order)
-__global__ void __launch_bounds__(1024) flip_collect_kernel(DeviceModel d,
-                                                           const unsigned int *__restrict__ flipBits)
-{
-  if (!iter_active(d.st))
-    return;
-  __shared__ int warpCount[32];
+  __shared__ int warpCount[8];
   __shared__ int base;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nwords = (d.nm + 31) >> 5;
   if (tid == 0)
     base = 0;
   __syncthreads();
-  for (int start = 0; start < nwords; start += 1024 * 4) {
+  for (int start = 0; start < nwords; start += 256 * 4) {
     unsigned int w[4];
     int cnt = 0;
 #pragma unroll
     for (int q = 0; q < 4; q++) {
       const int wi = start + tid * 4 + q;
-      w[q] = wi < nwords ? flipBits[wi] : 0u;
+      w[q] = wi < nwords ? __ldcg(flipBits + wi) : 0u;
       cnt += __popc(w[q]);
     }
     int inc = cnt;
@@ -194,21 +140,118 @@ __global__ void __launch_bounds__(1024) flip_collect_kernel(DeviceModel d,
       }
     }
     __syncthreads();
-    if (tid == 1023) {
+    if (tid == 255) {
       int tot = 0;
-      for (int q = 0; q < 32; q++)
+      for (int q = 0; q < 8; q++)
         tot += warpCount[q];
       base += tot;
     }
     __syncthreads();
   }
-  if (tid == 0)
-    d.st->numFlips = base;
+  if (tid == 0) {
+    IterState *st = d.st;
+    const int nf = base;
+    st->numFlips = nf;
+    if (nf > 0) {
+      // every contribution |a_ij * delta_j| <= amax * maxRange < 2^E; nf < 2^bitsN of them per row at
+      // most: with Q = 62 - bitsN fractional bits the int64 sums cannot overflow
+      const unsigned long long mb = atomicMax(&st->flipMaxBits, 0ull);
+      const double bound = d.amax * __longlong_as_double((long long)mb);
+      int E = 0;
+      frexp(bound, &E);
+      const int bitsN = 32 - __clz(nf);
+      const int Q = 62 - bitsN;
+      st->flipScale = ldexp(1.0, Q - E);
+      st->flipInvScale = ldexp(1.0, E - Q);
+    }
+    st->flipMaxBits = 0ull;
+  }
 }
 
-// rhs3[0] = a_q (entering column of [A|-I]); rhs3[1] = rho; rhs3[2] = -sum_flips a_j * delta_j.
-// Each thread owns one row and scans the (few) columns involved in ascending flip order, so
-// the sums are formed in a fixed order without atomics.
+// dj -= thetaDual * sigma * alpha over the pivot row; variables whose dj changes sign flip to
+// the other bound when boxed, otherwise their cost is shifted (ClpSimplexDual.cpp:4705-4772).
+// flipBits marks flipped variables; the last CTA expands it into the ordered flipList.
+__global__ void __launch_bounds__(256) dual_update_kernel(DeviceModel d, unsigned int *__restrict__ flipBits)
+{
+  if (!iter_active(d.st))
+    return;
+  const double theta = d.st->thetaDual;
+  const int sigma = d.st->sigma;
+  const int seqIn = d.st->seqIn;
+  const double tol = d.dualTolerance;
+  unsigned long long maxRange = 0ull;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < d.nm; j += gridDim.x * blockDim.x) {
+    const double alpha = d.alphaRow[j];
+    if (alpha != 0.0 && j != seqIn) {
+      const unsigned char st = d.status[j];
+      if (st != basic && st != isFixed) {
+        double dnew = d.dj[j] - theta * (sigma * alpha);
+        bool wrong = (st == atLowerBound && dnew < -tol) || (st == atUpperBound && dnew > tol);
+        if (wrong) {
+          const double lo = d.lower[j], up = d.upper[j];
+          if (up - lo < 1.0e29) {
+            if (st == atLowerBound) {
+              d.status[j] = atUpperBound;
+              d.sol[j] = up;
+            } else {
+              d.status[j] = atLowerBound;
+              d.sol[j] = lo;
+            }
+            atomicOr(flipBits + (j >> 5), 1u << (j & 31));
+            maxRange = max(maxRange, (unsigned long long)__double_as_longlong(up - lo));
+          } else {
+            d.cost[j] -= dnew;
+            dnew = 0.0;
+            atomicAdd(&d.st->costShifts, 1);
+          }
+        } else if ((st == isFree || st == superBasic) && fabs(dnew) > tol) {
+          d.cost[j] -= dnew;
+          dnew = 0.0;
+          atomicAdd(&d.st->costShifts, 1);
+        }
+        d.dj[j] = dnew;
+      }
+    }
+  }
+  if (maxRange != 0ull)
+    atomicMax(&d.st->flipMaxBits, maxRange);
+  if (!last_block_done(d.tailCounter + TAIL_DUAL_UPDATE))
+    return;
+  flip_collect_tail(d, flipBits);
+}
+
+// flipAcc[i] += fixed-point( -a_ij * delta_j ) for every flipped variable j (one warp per flip;
+// the slack of row i contributes +delta).  Integer atomics: the sums do not depend on the order.
+// Replaces the reference's sparse "matrix_->add" of the flipped columns
+// (ClpSimplexDual::updateDualsInDual, src/ClpSimplexDual.cpp:2430 -> ClpPackedMatrix::add :4874).
+__global__ void __launch_bounds__(256) flip_scatter_kernel(DeviceModel d)
+{
+  if (!iter_active(d.st))
+    return;
+  const int nf = d.st->numFlips;
+  if (nf == 0)
+    return;
+  const double scale = d.st->flipScale;
+  const int lane = threadIdx.x & 31;
+  const int warpsPerBlock = blockDim.x >> 5;
+  unsigned long long *acc = reinterpret_cast<unsigned long long *>(d.flipAcc);
+  for (int f = blockIdx.x * warpsPerBlock + (threadIdx.x >> 5); f < nf; f += gridDim.x * warpsPerBlock) {
+    const int j = d.flipList[f];
+    const double range = d.upper[j] - d.lower[j];
+    const double delta = d.status[j] == atUpperBound ? range : -range;
+    if (j >= d.n) {
+      if (lane == 0)
+        atomicAdd(acc + (j - d.n), (unsigned long long)__double2ll_rn(delta * scale));
+    } else {
+      const int e1 = d.colStart[j + 1];
+      for (int e = d.colStart[j] + lane; e < e1; e += 32)
+        atomicAdd(acc + d.rowIdx[e], (unsigned long long)__double2ll_rn(-delta * d.val[e] * scale));
+    }
+  }
+}
+
+// rhs3[0] = a_q (entering column of [A|-I]); rhs3[1] = rho; rhs3[2] = bound-flip right-hand side
+// (fixed point -> double; the accumulator is left zero for the next iteration).
 __global__ void __launch_bounds__(256) build_rhs3_kernel(DeviceModel d)
 {
   if (!iter_active(d.st))
@@ -237,85 +280,17 @@ __global__ void __launch_bounds__(256) build_rhs3_kernel(DeviceModel d)
       __syncthreads();
     }
   }
-  // flipped columns (few flips: scan them here; many flips: flip_rhs_rows_kernel does a row pass)
-  const int nfAll = d.st->numFlips;
-  const int nf = nfAll <= kFlipScanLimit ? nfAll : 0;
-  for (int f = 0; f < nf; f++) {
-    const int j = d.flipList[f];
-    const double range = d.upper[j] - d.lower[j];
-    const double delta = d.status[j] == atUpperBound ? range : -range;
-    if (j >= d.n) {
-      if (live && row == j - d.n)
-        fl += delta;
-      continue;
-    }
-    const int e0 = d.colStart[j], e1 = d.colStart[j + 1];
-    for (int c0 = e0; c0 < e1; c0 += 256) {
-      int e = c0 + threadIdx.x;
-      sRow[threadIdx.x] = e < e1 ? d.rowIdx[e] : -1;
-      sVal[threadIdx.x] = e < e1 ? d.val[e] : 0.0;
-      __syncthreads();
-      int cnt = min(256, e1 - c0);
-      for (int t = 0; t < cnt; t++)
-        if (sRow[t] == row)
-          fl -= delta * sVal[t];
-      __syncthreads();
-    }
-  }
   if (live) {
+    if (d.st->numFlips > 0) {
+      const long long a = d.flipAcc[row];
+      if (a != 0ll) {
+        fl = (double)a * d.st->flipInvScale;
+        d.flipAcc[row] = 0ll;
+      }
+    }
     d.rhs3[row] = aq;
     d.rhs3[(size_t)d.m + row] = d.rho[row];
     d.rhs3[(size_t)2 * d.m + row] = fl;
-  }
-}
-
-// Many flips: rhs3[2][i] = -sum_j a_ij delta_j over flipped j, one warp per row of the CSR copy
-// (streams the column indices once, 4 B per nonzero; fixed summation order).  The flip bit mask
-// (n+m bits) is staged in shared memory so the per-entry test costs no global gather.
-__global__ void __launch_bounds__(256)
-    flip_rhs_rows_kernel(DeviceModel d, const unsigned int *__restrict__ flipBits)
-{
-  extern __shared__ unsigned int sbits[];
-  if (!iter_active(d.st))
-    return;
-  if (d.st->numFlips <= kFlipScanLimit)
-    return;
-  const int nwords = (d.nm + 31) >> 5;
-  for (int i = threadIdx.x; i < nwords; i += blockDim.x)
-    sbits[i] = flipBits[i];
-  __syncthreads();
-  const int lane = threadIdx.x & 31;
-  const int warpsPerBlock = blockDim.x >> 5;
-  for (int i = blockIdx.x * warpsPerBlock + (threadIdx.x >> 5); i < d.m;
-       i += gridDim.x * warpsPerBlock) {
-    double acc = 0.0;
-    const int e1 = d.rowStart[i + 1];
-    for (int e = d.rowStart[i] + lane; e < e1; e += 256) {
-      int jj[8];
-#pragma unroll
-      for (int q = 0; q < 8; q++)
-        jj[q] = (e + 32 * q < e1) ? __ldcs(d.colIdx + e + 32 * q) : -1;
-#pragma unroll
-      for (int q = 0; q < 8; q++) {
-        const int j = jj[q];
-        if (j >= 0 && ((sbits[j >> 5] >> (j & 31)) & 1u)) {
-          const double range = d.upper[j] - d.lower[j];
-          const double delta = d.status[j] == atUpperBound ? range : -range;
-          acc = fma(-delta, d.rval[e + 32 * q], acc);
-        }
-      }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1)
-      acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (lane == 0) {
-      const int js = d.n + i;
-      if ((sbits[js >> 5] >> (js & 31)) & 1u) {
-        const double range = d.upper[js] - d.lower[js];
-        acc += d.status[js] == atUpperBound ? range : -range;
-      }
-      d.rhs3[(size_t)2 * d.m + i] = acc;
-    }
   }
 }
 
@@ -325,96 +300,23 @@ void launch_dual_update_and_flips(const DeviceModel &d, unsigned int *flipBits, 
   if (blocks > 148 * 8)
     blocks = 148 * 8;
   dual_update_kernel<<<blocks, 256, 0, s>>>(d, flipBits);
-  flip_collect_kernel<<<1, 1024, 0, s>>>(d, flipBits);
+  flip_scatter_kernel<<<148, 256, 0, s>>>(d);
   build_rhs3_kernel<<<(d.m + 255) / 256, 256, 0, s>>>(d);
-  {
-    int rb = (d.m + 7) / 8;
-    if (rb > 148 * 8)
-      rb = 148 * 8;
-    const size_t sb = sizeof(unsigned int) * (size_t)((d.nm + 31) >> 5);
-    static bool attrSet = false;
-    if (!attrSet) {
-      cudaFuncSetAttribute(flip_rhs_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-      attrSet = true;
-    }
-    flip_rhs_rows_kernel<<<rb, 256, sb, s>>>(d, flipBits);
-  }
 }
 
 // ------------------------------------------------------------------ after the FTRANs
-// accuracy gate (ClpSimplexDual.cpp:1447-1501) and primal step length
 __global__ void pivot_scalars_kernel(DeviceModel d)
 {
-  IterState *st = d.st;
-  if (!iter_active(st))
+  if (!iter_active(d.st))
     return;
-  const int r = st->pivotRow;
-  const double ac = d.rhs3[r];
-  st->alphaCol = ac;
-  const double ar = st->alphaRow;
-  const double err = fabs(ar - ac) / (1.0 + fabs(ac));
-  const bool bad = !(fabs(ac) >= 1.0e-9) || !(err <= 1.0e-6);
-  if (bad) {
-    if (st->numEtas > 0) {
-      st->stop = STOP_INACCURATE; // the host refactorizes, recomputes and retries
-      return;
-    }
-    if (!(fabs(ac) >= 1.0e-11) || !(err <= 1.0e-3)) {
-      st->stop = STOP_TINY_PIVOT; // fresh factors and still no usable pivot
-      return;
-    }
-  }
-  const int seqOut = st->seqOut;
-  double valueOut = d.sol[seqOut];
-  if (st->numFlips > 0)
-    valueOut += d.rhs3[(size_t)2 * d.m + r];
-  const double bound = st->sigma < 0 ? d.lower[seqOut] : d.upper[seqOut];
-  st->thetaPrimal = (valueOut - bound) / ac;
+  pivot_scalars_body(d);
 }
 
-// x_B, DSE weights and the new eta column, one thread per position
-__global__ void pivot_update_kernel(DeviceModel d)
-{
-  const IterState *st = d.st;
-  if (!iter_active(st))
-    return;
-  int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= d.m)
-    return;
-  const int r = st->pivotRow;
-  const int t = st->numEtas;
-  const double a = d.rhs3[p];
-  const double alphaR = st->alphaCol;
-  // eta column W_t = alpha_q with (alpha_r - 1) on the pivot position
-  d.W[(size_t)p * d.tmax + t] = (p == r) ? a - 1.0 : a;
-  const int seq = d.pivotVariable[p];
-  if (p != r) {
-    double x = d.sol[seq];
-    if (st->numFlips > 0)
-      x += d.rhs3[(size_t)2 * d.m + p];
-    x -= st->thetaPrimal * a;
-    d.sol[seq] = x;
-    if (a != 0.0) {
-      // w_i += (a_i/a_r) * ((a_i/a_r) * w_r - 2 tau_i)   clipped at DEVEX_TRY_NORM
-      const double ratio = a / alphaR;
-      double w = d.weights[p] + ratio * (ratio * st->rhoNorm2 - 2.0 * d.rhs3[(size_t)d.m + p]);
-      d.weights[p] = w < kDevexTryNorm ? kDevexTryNorm : w;
-    }
-  } else {
-    double w = st->rhoNorm2 / (alphaR * alphaR);
-    d.weights[p] = w < kDevexTryNorm ? kDevexTryNorm : w;
-  }
-}
-
-// status / pivotVariable swap and per-iteration record (ClpSimplex::housekeeping)
-__global__ void pivot_fixup_kernel(DeviceModel d)
+// status / pivotVariable swap and per-iteration record (ClpSimplex::housekeeping), single thread
+__device__ __forceinline__ void pivot_fixup_body(const DeviceModel &d)
 {
   IterState *st = d.st;
   IterRecord &rec = d.rec[st->iterations % d.recCap];
-  if (!iter_active(st)) {
-    rec.stop = st->stop;
-    return;
-  }
   const int r = st->pivotRow, q = st->seqIn, out = st->seqOut;
   const double bound = st->sigma < 0 ? d.lower[out] : d.upper[out];
   d.sol[q] += st->thetaPrimal;
@@ -447,12 +349,89 @@ __global__ void pivot_fixup_kernel(DeviceModel d)
   st->iterations += 1;
 }
 
+// End of an iteration in one kernel:
+//   CTAs [0, etaBlocks)      : new row of Ginv (eta_rowvec mode 1)
+//   CTAs [etaBlocks, grid)   : x_B, DSE weights (ClpDualRowSteepest.cpp:501-538) and the new eta
+//                              column, one thread per position; clear the ratio-test histograms and
+//                              the flip mask; score every position for the NEXT iteration's CHUZR
+//   tail (last CTA, thread 0): housekeeping of this iteration, then decode the next pivot row.
+__global__ void __launch_bounds__(256) iteration_update_kernel(DeviceModel d, int etaBlocks)
+{
+  __shared__ double part[8][33];
+  IterState *st = d.st;
+  if (!iter_active(st)) {
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+      d.rec[st->iterations % d.recCap].stop = st->stop;
+    return;
+  }
+  if ((int)blockIdx.x < etaBlocks) {
+    eta_rowvec_body(d, 1, blockIdx.x, part);
+  } else {
+    const int posBlocks = gridDim.x - etaBlocks;
+    const int gtid = (blockIdx.x - etaBlocks) * 256 + threadIdx.x;
+    const int gthreads = posBlocks * 256;
+    for (int b = gtid; b < kHistBuckets; b += gthreads) {
+      d.histWeight[b] = 0ull;
+      if (b < kHist2Buckets) {
+        d.hist2Weight[b] = 0ull;
+        d.hist2Min[b] = 0xFFFFFFFFFFFFFFFFull;
+      }
+    }
+    for (int w = gtid; w < ((d.nm + 31) >> 5); w += gthreads)
+      d.flipBits[w] = 0u;
+    unsigned long long best = 0ull;
+    const int p = gtid;
+    if (p < d.m) {
+      const int r = st->pivotRow;
+      const int t = st->numEtas;
+      const double a = d.rhs3[p];
+      const double alphaR = st->alphaCol;
+      // eta column W_t = alpha_q with (alpha_r - 1) on the pivot position
+      d.W[(size_t)p * d.tmax + t] = (p == r) ? a - 1.0 : a;
+      if (p != r) {
+        const int seq = d.pivotVariable[p];
+        double x = d.sol[seq];
+        if (st->numFlips > 0)
+          x += d.rhs3[(size_t)2 * d.m + p];
+        x -= st->thetaPrimal * a;
+        d.sol[seq] = x;
+        double w = d.weights[p];
+        if (a != 0.0) {
+          // w_i += (a_i/a_r) * ((a_i/a_r) * w_r - 2 tau_i)   clipped at DEVEX_TRY_NORM
+          const double ratio = a / alphaR;
+          w += ratio * (ratio * st->rhoNorm2 - 2.0 * d.rhs3[(size_t)d.m + p]);
+          w = w < kDevexTryNorm ? kDevexTryNorm : w;
+          d.weights[p] = w;
+        }
+        best = chuzr_key(x, d.lower[seq], d.upper[seq], w, d.primalTolerance, p);
+      } else {
+        double w = st->rhoNorm2 / (alphaR * alphaR);
+        w = w < kDevexTryNorm ? kDevexTryNorm : w;
+        d.weights[p] = w;
+        const int q = st->seqIn; // becomes basic at this position (housekeeping in the tail)
+        best = chuzr_key(d.sol[q] + st->thetaPrimal, d.lowerTrue[q], d.upperTrue[q], w, d.primalTolerance, p);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+      best = max(best, __shfl_xor_sync(0xffffffffu, best, o));
+    if ((threadIdx.x & 31) == 0 && best != 0ull)
+      atomicMax(&st->chuzrKey, best);
+  }
+  if (!last_block_done(d.tailCounter + TAIL_ITER_UPDATE))
+    return;
+  if (threadIdx.x == 0) {
+    pivot_fixup_body(d);
+    const unsigned long long key = atomicExch(&st->chuzrKey, 0ull);
+    chuzr_finish_body(d, key, true);
+  }
+}
+
 void launch_pivot_updates(const DeviceModel &d, cudaStream_t s)
 {
-  pivot_scalars_kernel<<<1, 1, 0, s>>>(d);
-  launch_eta_rowvec(d, 1, true, s); // new row of Ginv (reads old W[r][:], alphaCol)
-  pivot_update_kernel<<<(d.m + 255) / 256, 256, 0, s>>>(d);
-  pivot_fixup_kernel<<<1, 1, 0, s>>>(d);
+  const int etaBlocks = (d.tmax + 31) / 32;
+  const int posBlocks = (d.m + 255) / 256;
+  iteration_update_kernel<<<etaBlocks + posBlocks, 256, 0, s>>>(d, etaBlocks);
 }
 
 // ------------------------------------------------------------------ refresh kernels

@@ -48,6 +48,10 @@ def main():
     from oracle.oracle import OracleSimplex
 
     cases = [G.unit_test_3x5()] + G.racing_suite()
+    # reduced shapes of BASELINE.json configs[3] (staircase) and configs[4] (degenerate transportation);
+    # no reference value exists for them: pinned by HiGHS dual simplex, cross-checked by the oracle
+    cases += [G.staircase_lp(8, 60, 3), G.staircase_lp(10, 100, 4), G.transportation_lp(10, 200, 5),
+              G.transportation_lp(20, 500, 6)]
     # in-tree MPS files through our own reader (host-only code path, no GPU needed)
     ref = "/root/reference/examples"
     if os.path.isdir(ref):
