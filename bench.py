@@ -253,7 +253,9 @@ def main():
 
     if rank == 0 and world == 1:
         # ---------------- per-kernel timing (CUDA events around single kernels, no graph replay)
-        p = new_model(batch=16, timing=1, maximumIterations=min(2 * cycle, 600), factorizationFrequency=cycle)
+        # one full factorization cycle, so that the eta-panel costs (which grow with the number of
+        # updates since the last refactorization) are averaged the way the timed window sees them
+        p = new_model(batch=16, timing=1, maximumIterations=cycle, factorizationFrequency=cycle)
         p.dual()
         ph = p.phaseTimes()
         ns = max(1.0, ph["samples"])

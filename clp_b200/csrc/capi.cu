@@ -142,11 +142,26 @@ int Clpb_setParameter(Clpb_Simplex *model, const char *key, double value)
     e.usePriceTma = value != 0.0;
   else if (k == "useGraph")
     e.useGraph = value != 0.0;
+  else if (k == "useRowPass")
+    e.useRowPass = value != 0.0;
   else if (k == "objectiveOffset")
     e.objectiveOffset = value;
+  else if (k == "scaling")
+    e.scalingFlag = (int)value;
   else
     return -1;
   return 0;
+}
+void Clpb_scaling(Clpb_Simplex *model, int mode) { model->e.scalingFlag = mode; }
+int Clpb_scaleFactors(Clpb_Simplex *model, double *rowScale, double *columnScale)
+{
+  clpb::Engine &e = model->e;
+  const int rc = e.computeScaling(); // host only
+  for (int i = 0; i < e.m; i++)
+    rowScale[i] = rc == 0 ? e.rowScale[i] : 1.0;
+  for (int j = 0; j < e.n; j++)
+    columnScale[j] = rc == 0 ? e.columnScale[j] : 1.0;
+  return rc;
 }
 void Clpb_copyinStatus(Clpb_Simplex *model, const unsigned char *statusArray)
 {

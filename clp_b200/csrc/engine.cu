@@ -137,6 +137,201 @@ void Engine::setStatus(const unsigned char *st)
   haveUserStatus = true;
 }
 
+void Engine::buildRowCopy(const std::vector<double> &val, std::vector<int> &rowStart,
+                          std::vector<int> &colIdx, std::vector<double> &rval) const
+{
+  const long long nnz = hColStart[n];
+  rowStart.assign(m + 1, 0);
+  colIdx.resize(nnz);
+  rval.resize(nnz);
+  for (long long e = 0; e < nnz; e++)
+    rowStart[hRow[e] + 1]++;
+  for (int i = 0; i < m; i++)
+    rowStart[i + 1] += rowStart[i];
+  std::vector<int> fill(rowStart.begin(), rowStart.end() - 1);
+  for (int j = 0; j < n; j++)
+    for (int e = hColStart[j]; e < hColStart[j + 1]; e++) {
+      int at = fill[hRow[e]]++;
+      colIdx[at] = j;
+      rval[at] = val[e];
+    }
+}
+
+// Row and column scale factors, restating ClpPackedMatrix::scale (src/ClpPackedMatrix.cpp:4120-4640):
+// scaled a_ij = a_ij * rowScale[i] * columnScale[j].  Mode 1 equilibrium (row maxima), 2 geometric
+// (three passes of sqrt(min*max), the last column round skipped), 3/4 "auto": equilibrium first,
+// then geometric, keeping geometric only if its smallest/largest ratio is more than twice as good
+// (:4493-4513).  The final column pass (:4531-4581) makes the largest entry of every useful column
+// overallLargest.  Returns 1 (and leaves the problem unscaled) when the matrix entries already lie
+// in [0.5, 2] (:4262), 0 otherwise.  Tiny elements (<= 1e-20) are ignored rather than deleted.
+int Engine::computeScaling()
+{
+  rowScale.clear();
+  columnScale.clear();
+  if (scalingFlag <= 0 || m == 0 || n == 0)
+    return 1;
+  std::vector<char> useful(n, 0);
+  double largest = 0.0, smallest = 1.0e50;
+  for (int j = 0; j < n; j++) {
+    if (hUpper[j] > hLower[j] + 1.0e-12 || (haveUserStatus && hStatus[j] == basic)) {
+      for (int e = hColStart[j]; e < hColStart[j + 1]; e++) {
+        const double v = std::fabs(hVal[e]);
+        if (v > 1.0e-20) {
+          useful[j] = 1;
+          largest = std::max(largest, v);
+          smallest = std::min(smallest, v);
+        }
+      }
+    }
+  }
+  if (smallest >= 0.5 && largest <= 2.0)
+    return 1; // CLP_PACKEDSCALE_FORGET
+  std::vector<int> rowStart, colIdx;
+  std::vector<double> rval;
+  buildRowCopy(hVal, rowStart, colIdx, rval);
+  int scalingMethod = scalingFlag;
+  if (scalingMethod == 4)
+    scalingMethod = 3;
+  else if (scalingMethod >= 5)
+    scalingMethod = 2;
+  double savedOverallRatio = 0.0;
+  const double tolerance = 5.0 * primalTolerance;
+  double overallSmallest = 1.0e20;
+  bool finished = false;
+  rowScale.assign(m, 1.0);
+  columnScale.assign(n, 1.0);
+  while (!finished) {
+    int numberPass = 3;
+    std::fill(rowScale.begin(), rowScale.end(), 1.0);
+    std::fill(columnScale.begin(), columnScale.end(), 1.0);
+    if (scalingMethod == 1 || scalingMethod == 3) {
+      for (int i = 0; i < m; i++) { // maximum in each row
+        double big = 1.0e-10;
+        for (int e = rowStart[i]; e < rowStart[i + 1]; e++)
+          if (useful[colIdx[e]])
+            big = std::max(big, std::fabs(rval[e]));
+        rowScale[i] = 1.0 / big;
+      }
+    } else {
+      while (numberPass) {
+        numberPass--;
+        for (int i = 0; i < m; i++) { // geometric mean on row scales
+          double big = 1.0e-50, small = 1.0e50;
+          for (int e = rowStart[i]; e < rowStart[i + 1]; e++) {
+            const int j = colIdx[e];
+            if (useful[j]) {
+              const double v = std::fabs(rval[e]) * columnScale[j];
+              big = std::max(big, v);
+              small = std::min(small, v);
+            }
+          }
+          rowScale[i] = 1.0 / std::sqrt(small * big);
+        }
+        if (numberPass == 1)
+          break; // skip last column round
+        for (int j = 0; j < n; j++) { // geometric mean on column scales
+          if (!useful[j])
+            continue;
+          double big = 1.0e-50, small = 1.0e50;
+          for (int e = hColStart[j]; e < hColStart[j + 1]; e++) {
+            const double v = std::fabs(hVal[e]) * rowScale[hRow[e]];
+            big = std::max(big, v);
+            small = std::min(small, v);
+          }
+          columnScale[j] = 1.0 / std::sqrt(small * big);
+        }
+      }
+    }
+    // if ranges will make horrid then scale (:4459)
+    for (int i = 0; i < m; i++) {
+      const double difference = hUpper[n + i] - hLower[n + i];
+      const double scaledDifference = difference * rowScale[i];
+      if (scaledDifference > tolerance && scaledDifference < 1.0e-4) {
+        rowScale[i] *= 1.0e-4 / scaledDifference;
+        rowScale[i] = std::max(1.0e-10, std::min(1.0e10, rowScale[i]));
+      }
+    }
+    // what the smallest entry will be if the largest of its column is 1 (:4471)
+    overallSmallest = 1.0e50;
+    for (int j = 0; j < n; j++) {
+      if (!useful[j])
+        continue;
+      double big = 1.0e-20, small = 1.0e50;
+      for (int e = hColStart[j]; e < hColStart[j + 1]; e++) {
+        const double v = std::fabs(hVal[e] * rowScale[hRow[e]]);
+        big = std::max(big, v);
+        small = std::min(small, v);
+      }
+      if (overallSmallest * big > small)
+        overallSmallest = small / big;
+    }
+    if (scalingMethod == 1 || scalingMethod == 2) {
+      finished = true;
+    } else if (savedOverallRatio == 0.0 && scalingMethod != 4) {
+      savedOverallRatio = overallSmallest;
+      scalingMethod = 4;
+    } else {
+      if (overallSmallest > 2.0 * savedOverallRatio)
+        finished = true; // geometric was better
+      else
+        scalingMethod = 1; // redo equilibrium
+    }
+  }
+  double overallLargest = 1.0;
+  if (overallSmallest < 1.0e-1)
+    overallLargest = 1.0 / std::sqrt(overallSmallest);
+  overallLargest = std::min(100.0, overallLargest);
+  std::vector<char> usedRow(m, 0);
+  for (int j = 0; j < n; j++) {
+    if (hUpper[j] > hLower[j] + 1.0e-12 && hColStart[j + 1] > hColStart[j]) {
+      double big = 1.0e-20;
+      for (int e = hColStart[j]; e < hColStart[j + 1]; e++) {
+        usedRow[hRow[e]] = 1;
+        big = std::max(big, std::fabs(hVal[e] * rowScale[hRow[e]]));
+      }
+      columnScale[j] = overallLargest / big;
+      const double difference = hUpper[j] - hLower[j];
+      if (difference < 1.0e-5 * columnScale[j])
+        columnScale[j] = difference / 1.0e-5; // make gap larger
+    } else {
+      columnScale[j] = 1.0;
+    }
+  }
+  for (int i = 0; i < m; i++)
+    if (!usedRow[i])
+      rowScale[i] = 1.0;
+  return 0;
+}
+
+// ClpSimplex::createRim (src/ClpSimplex.cpp:7895ff) for the scaled problem: columns x' = x/c,
+// bounds/c, cost*c; rows activity' = r*activity, bounds*r.  Infinite bounds stay infinite.
+void Engine::prepareWorkingProblem()
+{
+  wVal = hVal;
+  wLower = hLower;
+  wUpper = hUpper;
+  wCost = hCost;
+  if (computeScaling() != 0)
+    return;
+  for (int j = 0; j < n; j++) {
+    const double c = columnScale[j];
+    for (int e = hColStart[j]; e < hColStart[j + 1]; e++)
+      wVal[e] = hVal[e] * rowScale[hRow[e]] * c;
+    if (wLower[j] > -kInf)
+      wLower[j] /= c;
+    if (wUpper[j] < kInf)
+      wUpper[j] /= c;
+    wCost[j] *= c;
+  }
+  for (int i = 0; i < m; i++) {
+    const double r = rowScale[i];
+    if (wLower[n + i] > -kInf)
+      wLower[n + i] *= r;
+    if (wUpper[n + i] < kInf)
+      wUpper[n + i] *= r;
+  }
+}
+
 int Engine::setupDevice()
 {
   if (deviceReady)
@@ -148,22 +343,11 @@ int Engine::setupDevice()
   }
   CUDA_OK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
   const long long nnz = hColStart[n];
+  prepareWorkingProblem(); // scaling (if asked for) -> wVal / wLower / wUpper / wCost
   // row copy (CSR) built on the host once
-  std::vector<int> rowStart(m + 1, 0), colIdx(nnz);
-  std::vector<double> rval(nnz);
-  for (long long e = 0; e < nnz; e++)
-    rowStart[hRow[e] + 1]++;
-  for (int i = 0; i < m; i++)
-    rowStart[i + 1] += rowStart[i];
-  {
-    std::vector<int> fill(rowStart.begin(), rowStart.end() - 1);
-    for (int j = 0; j < n; j++)
-      for (int e = hColStart[j]; e < hColStart[j + 1]; e++) {
-        int at = fill[hRow[e]]++;
-        colIdx[at] = j;
-        rval[at] = hVal[e];
-      }
-  }
+  std::vector<int> rowStart, colIdx;
+  std::vector<double> rval;
+  buildRowCopy(wVal, rowStart, colIdx, rval);
   d.m = m;
   d.n = n;
   d.nm = nm;
@@ -179,7 +363,7 @@ int Engine::setupDevice()
   d.rowIdx = p;
   q = dalloc<double>(nnz + 16);
   CUDA_OK(cudaMemset(q, 0, sizeof(double) * (nnz + 16)));
-  CUDA_OK(cudaMemcpy(q, hVal.data(), sizeof(double) * nnz, cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemcpy(q, wVal.data(), sizeof(double) * nnz, cudaMemcpyHostToDevice));
   d.val = q;
   {
     // cut this rank's column range into tiles of whole columns, <= kPriceTile entries each
@@ -261,6 +445,8 @@ int Engine::setupDevice()
   d.etaPrevSame = dalloc<int>(d.tmax);
   d.etaLastOfPos = dalloc<int>(m);
   d.Ginv = dalloc<double>((size_t)d.tmax * d.tmax);
+  d.GinvT = dalloc<double>((size_t)d.tmax * d.tmax);
+  d.xp = dalloc<double>((size_t)3 * d.tmax);
   d.rho = dalloc<double>(m);
   d.alphaRow = dalloc<double>(nm);
   d.rhs3 = dalloc<double>((size_t)3 * m);
@@ -271,9 +457,13 @@ int Engine::setupDevice()
   CUDA_OK(cudaMemset(d.flipAcc, 0, sizeof(long long) * m));
   d.tailCounter = dalloc<unsigned int>(16);
   CUDA_OK(cudaMemset(d.tailCounter, 0, sizeof(unsigned int) * 16));
+  d.gridBar = dalloc<unsigned int>(2);
+  CUDA_OK(cudaMemset(d.gridBar, 0, sizeof(unsigned int) * 2));
+  d.aqBuf = dalloc<double>(m);
+  CUDA_OK(cudaMemset(d.aqBuf, 0, sizeof(double) * m));
   d.amax = 1.0;
   for (long long e = 0; e < nnz; e++)
-    d.amax = std::max(d.amax, std::fabs(hVal[e]));
+    d.amax = std::max(d.amax, std::fabs(wVal[e]));
   d.mu = dalloc<double>((size_t)3 * d.tmax);
   d.nu = dalloc<double>(d.tmax);
   d.histWeight = dalloc<unsigned long long>(kHistBuckets);
@@ -314,12 +504,12 @@ int Engine::setupDevice()
   d.acceptablePivot = acceptablePivot;
   d.zeroTolerance = zeroTolerance;
 
-  CUDA_OK(cudaMemcpy(d.costTrue, hCost.data(), sizeof(double) * nm, cudaMemcpyHostToDevice));
-  CUDA_OK(cudaMemcpy(d.cost, hCost.data(), sizeof(double) * nm, cudaMemcpyHostToDevice));
-  CUDA_OK(cudaMemcpy(d.lowerTrue, hLower.data(), sizeof(double) * nm, cudaMemcpyHostToDevice));
-  CUDA_OK(cudaMemcpy(d.upperTrue, hUpper.data(), sizeof(double) * nm, cudaMemcpyHostToDevice));
-  CUDA_OK(cudaMemcpy(d.lower, hLower.data(), sizeof(double) * nm, cudaMemcpyHostToDevice));
-  CUDA_OK(cudaMemcpy(d.upper, hUpper.data(), sizeof(double) * nm, cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemcpy(d.costTrue, wCost.data(), sizeof(double) * nm, cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemcpy(d.cost, wCost.data(), sizeof(double) * nm, cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemcpy(d.lowerTrue, wLower.data(), sizeof(double) * nm, cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemcpy(d.upperTrue, wUpper.data(), sizeof(double) * nm, cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemcpy(d.lower, wLower.data(), sizeof(double) * nm, cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemcpy(d.upper, wUpper.data(), sizeof(double) * nm, cudaMemcpyHostToDevice));
   CUDA_OK(cudaMemset(d.fake, 0, nm));
   CUDA_OK(cudaMemset(d.dj, 0, sizeof(double) * nm));
   CUDA_OK(cudaMemset(d.histWeight, 0, sizeof(unsigned long long) * kHistBuckets));
@@ -357,7 +547,7 @@ void Engine::resetStateForRun()
   for (int j = 0; j < nm; j++) {
     if (hStatus[j] == basic)
       continue;
-    double lo = hLower[j], up = hUpper[j];
+    double lo = wLower[j], up = wUpper[j];
     if (lo > -kInf && up < kInf) {
       if (lo == up) {
         hStatus[j] = isFixed;
@@ -388,13 +578,15 @@ void Engine::resetStateForRun()
   CUDA_OK(cudaMemcpy(d.pivotVariable, hPivot.data(), sizeof(int) * m, cudaMemcpyHostToDevice));
   std::vector<double> w(m, 1.0);
   CUDA_OK(cudaMemcpy(d.weights, w.data(), sizeof(double) * m, cudaMemcpyHostToDevice));
-  CUDA_OK(cudaMemcpy(d.cost, hCost.data(), sizeof(double) * nm, cudaMemcpyHostToDevice));
-  CUDA_OK(cudaMemcpy(d.lower, hLower.data(), sizeof(double) * nm, cudaMemcpyHostToDevice));
-  CUDA_OK(cudaMemcpy(d.upper, hUpper.data(), sizeof(double) * nm, cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemcpy(d.cost, wCost.data(), sizeof(double) * nm, cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemcpy(d.lower, wLower.data(), sizeof(double) * nm, cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemcpy(d.upper, wUpper.data(), sizeof(double) * nm, cudaMemcpyHostToDevice));
   CUDA_OK(cudaMemset(d.fake, 0, nm));
   CUDA_OK(cudaMemset(d.st, 0, sizeof(IterState)));
   CUDA_OK(cudaMemset(d.flipAcc, 0, sizeof(long long) * m));
   CUDA_OK(cudaMemset(d.tailCounter, 0, sizeof(unsigned int) * 16));
+  CUDA_OK(cudaMemset(d.gridBar, 0, sizeof(unsigned int) * 2));
+  CUDA_OK(cudaMemset(d.aqBuf, 0, sizeof(double) * m));
   d.primalTolerance = primalTolerance;
   d.dualTolerance = dualTolerance;
   d.acceptablePivot = acceptablePivot;
@@ -480,7 +672,7 @@ int Engine::refactor()
           if (posToNuc[i] < 0) {
             int at = fill[i]++;
             s1Col[at] = j;
-            s1Val[at] = hVal[e];
+            s1Val[at] = wVal[e];
           }
         }
     }
@@ -577,7 +769,7 @@ int Engine::refactor()
     // make srcPos consistent: treat as a fresh basis for weights of the new slack
     hPivot = newPivot;
     hStatus[n + rowEnter] = basic;
-    double lo = hLower[seqLeave], up = hUpper[seqLeave];
+    double lo = wLower[seqLeave], up = wUpper[seqLeave];
     unsigned char st;
     double x;
     if (lo > -kInf) {
@@ -629,6 +821,7 @@ void Engine::enqueueIteration(bool timed, int slot)
   launch_btran_unit(d, true, stream);
   if (timed)
     cudaEventRecord(ev[2], stream);
+  bool rowPassed = false;
   if (worldSize > 1) {
     int per = (n + worldSize - 1) / worldSize;
     int c0 = std::min(n, rank * per), c1 = std::min(n, c0 + per);
@@ -639,26 +832,40 @@ void Engine::enqueueIteration(bool timed, int slot)
     allGatherFn(ncclComm, d.alphaRow, sizeof(double) * per, stream);
     launch_price_slacks(d, 0, 0, false, stream);
     launch_histogram(d, stream);
+  } else if (useRowPass) {
+    launch_price(d, 0, n, false, stream);
+    rowPassed = true;
   } else {
     launch_price(d, 0, n, true, stream);
     launch_price_slacks(d, 0, n, true, stream);
   }
   if (timed)
     cudaEventRecord(ev[3], stream);
-  launch_chuzc(d, stream);
-  if (timed)
-    cudaEventRecord(ev[4], stream);
-  launch_dual_update_and_flips(d, d.flipBits, stream);
-  if (timed)
-    cudaEventRecord(ev[5], stream);
-  launch_ftran_iteration(d, stream);
+  if (rowPassed) {
+    // row finalize, ratio test, dual update, flips and the FTRAN right-hand sides in one
+    // cooperative kernel (rowpass.cu)
+    if (!launch_row_pass(d, stream))
+      throw std::runtime_error("row pass launch failed");
+    if (timed) {
+      cudaEventRecord(ev[4], stream);
+      cudaEventRecord(ev[5], stream);
+    }
+  } else {
+    launch_chuzc(d, stream);
+    if (timed)
+      cudaEventRecord(ev[4], stream);
+    launch_dual_update_and_flips(d, d.flipBits, stream);
+    if (timed)
+      cudaEventRecord(ev[5], stream);
+  }
+  launch_ftran_iteration(d, rowPassed, stream);
   if (timed)
     cudaEventRecord(ev[6], stream);
   launch_pivot_updates(d, stream);
   if (timed)
     cudaEventRecord(ev[7], stream);
   g_kernelTimers = nullptr;
-  kernelLaunches += 3 + 2 + 4 + 3 + 5 + 1 + (worldSize > 1 ? 3 : 0);
+  kernelLaunches += rowPassed ? 3 + 1 + 1 + 4 + 1 : 3 + 2 + 4 + 3 + 5 + 1 + (worldSize > 1 ? 3 : 0);
 }
 
 // start of a batch: stand-alone CHUZR (2 kernels)
@@ -672,17 +879,47 @@ void Engine::buildIterationGraph()
 {
   if (iterGraph)
     return;
-  cudaGraph_t graph = nullptr;
-  const long before = kernelLaunches;
-  CUDA_OK(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
-  enqueueIteration(false, 0);
-  CUDA_OK(cudaStreamEndCapture(stream, &graph));
-  kernelLaunches = before;
-  size_t numNodes = 0;
-  CUDA_OK(cudaGraphGetNodes(graph, nullptr, &numNodes));
-  kernelsPerIteration = (int)numNodes;
-  CUDA_OK(cudaGraphInstantiate(&iterGraph, graph, 0));
-  cudaGraphDestroy(graph);
+  // Capture one iteration.  If the cooperative row-pass launch cannot be captured on this driver,
+  // capture again with the separate kernels; if that fails too, run without a graph.
+  for (int attempt = 0; attempt < 2 && !iterGraph; attempt++) {
+    cudaGraph_t graph = nullptr;
+    const long before = kernelLaunches;
+    bool ok = cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+    if (ok) {
+      try {
+        enqueueIteration(false, 0);
+      } catch (const std::exception &) {
+        ok = false;
+      }
+      if (cudaStreamEndCapture(stream, &graph) != cudaSuccess || graph == nullptr)
+        ok = false;
+    }
+    kernelLaunches = before;
+    if (ok) {
+      size_t numNodes = 0;
+      cudaGraphGetNodes(graph, nullptr, &numNodes);
+      kernelsPerIteration = (int)numNodes;
+      if (cudaGraphInstantiate(&iterGraph, graph, 0) != cudaSuccess) {
+        iterGraph = nullptr;
+        ok = false;
+      }
+    }
+    if (graph)
+      cudaGraphDestroy(graph);
+    if (!ok) {
+      cudaGetLastError(); // clear the sticky capture error
+      if (useRowPass && worldSize == 1) {
+        fprintf(stderr, "clp_b200: cooperative row pass not capturable, using the separate kernels\n");
+        useRowPass = false;
+      } else {
+        fprintf(stderr, "clp_b200: CUDA graph capture failed, launching kernels directly\n");
+        useGraph = false;
+        return;
+      }
+    }
+  }
+  if (!iterGraph)
+    useGraph = false;
 }
 
 void Engine::fetchState()
@@ -710,6 +947,18 @@ void Engine::downloadSolution()
   objectiveValue = obj[0] + objectiveOffset;
   sumPrimalInfeasibilities = obj[1];
   hStatus = status;
+  if (!rowScale.empty()) {
+    // back to the user's units (ClpSimplex::deleteRim / unscale, src/ClpSimplex.cpp:9430ff)
+    for (int j = 0; j < n; j++) {
+      solution[j] *= columnScale[j];
+      reducedCost[j] /= columnScale[j];
+    }
+    for (int i = 0; i < m; i++) {
+      solution[n + i] /= rowScale[i];
+      reducedCost[n + i] *= rowScale[i];
+      rowPrice[i] *= rowScale[i];
+    }
+  }
 }
 
 int Engine::startup()
@@ -779,8 +1028,9 @@ int Engine::dual()
     if (timing)
       cudaEventRecord(evChuzr0, stream);
     enqueueBatchStart();
+    if (useGraph && !timing)
+      buildIterationGraph(); // may clear useGraph
     if (useGraph && !timing) {
-      buildIterationGraph();
       for (int b = 0; b < count; b++)
         CUDA_OK(cudaGraphLaunch(iterGraph, stream));
       kernelLaunches += (long)count * kernelsPerIteration;

@@ -128,6 +128,8 @@ struct DeviceModel {
   int *etaPrevSame;   // [tmax] previous eta with the same position or -1
   int *etaLastOfPos;  // [m]    last eta index for a position or -1
   double *Ginv;       // [tmax x tmax] row-major lower triangular
+  double *GinvT;      // [tmax x tmax] its transpose (row j = column j of Ginv, entries i >= j)
+  double *xp;         // [3 x tmax] FTRAN right-hand sides gathered at the eta positions
   // work vectors
   double *rho;        // [m]
   double *alphaRow;   // [n+m] tableau row (dense)
@@ -138,6 +140,8 @@ struct DeviceModel {
   long long *flipAcc; // [m] fixed-point accumulator of the bound-flip right-hand side (zero when idle)
   double amax;        // max(1, max |a_ij|): bound for the fixed-point scale of flipAcc
   unsigned int *tailCounter; // [16] last-block-done tickets (one per kernel that has a tail)
+  unsigned int *gridBar;     // [2] arrival count / generation of the row-pass grid barrier
+  double *aqBuf;      // [m] entering column scattered by the row pass (zero when idle)
   double *mu;         // [3 x tmax]
   double *nu;         // [tmax]
   // ratio test
@@ -166,7 +170,9 @@ extern KernelTimers *g_kernelTimers; // nullptr outside timing mode (engine.cu)
 // solve.cu
 void launch_ftran(const DeviceModel &d, int nrhs, bool applyEtas, cudaStream_t s);
 void launch_btran_unit(const DeviceModel &d, bool checkState, cudaStream_t s); // rho = B^-T e_r (r = st->pivotRow)
-void launch_ftran_iteration(const DeviceModel &d, cudaStream_t s); // 3 rhs + etas + pivot scalars (tail)
+void launch_ftran_iteration(const DeviceModel &d, bool pregathered, cudaStream_t s); // 3 rhs + etas + pivot scalars (tail)
+// rowpass.cu
+bool launch_row_pass(const DeviceModel &d, cudaStream_t s);
 void launch_eta_rowvec(const DeviceModel &d, int mode, bool checkState, cudaStream_t s);
 void launch_ftran_buffer(const DeviceModel &d, double *buf, int nrhs, bool applyEtas, cudaStream_t s);
 void launch_btran_dense(const DeviceModel &d, double *vec, bool applyEtas, cudaStream_t s); // vec(m) in/out

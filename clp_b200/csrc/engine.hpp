@@ -42,10 +42,16 @@ public:
   bool timing = false;
   bool useGraph = true;
   bool usePriceTma = true;        // TMA-staged price kernel (false: warp-per-column kernel)
+  bool useRowPass = true;         // cooperative row-pass kernel (false / column-sharded: separate kernels)
   int warmupIterations = 0;       // device-timed window starts once this many iterations ran
   double timedMilliseconds = 0.0; // CUDA-event time of the window (iterations + refactorizations)
   int timedIterations = 0;
   double objectiveOffset = 0.0;
+  // ClpModel::scaling(mode) (src/ClpModel.hpp): 0 off, 1 equilibrium, 2 geometric, 3 auto, 4 auto
+  // (dynamic).  Clp's own default is 3; the benchmark configuration states "scaling off".
+  int scalingFlag = 0;
+  std::vector<double> rowScale, columnScale; // empty: the problem is solved unscaled
+  int computeScaling();                      // ClpPackedMatrix::scale (src/ClpPackedMatrix.cpp:4120)
   // column sharding of the pricing pass (multi-GPU): this rank prices [colBegin,colEnd)
   int rank = 0, worldSize = 1;
   void *ncclComm = nullptr; // ncclComm_t when worldSize > 1
@@ -92,7 +98,9 @@ public:
   int m = 0, n = 0, nm = 0;
   std::vector<int> hColStart, hRow;
   std::vector<double> hVal;
-  std::vector<double> hLower, hUpper, hCost; // n+m, true bounds/costs
+  std::vector<double> hLower, hUpper, hCost; // n+m, true bounds/costs (as loaded)
+  // what the device works on: the loaded problem, scaled when scalingFlag asks for it
+  std::vector<double> wVal, wLower, wUpper, wCost;
   std::string problemName;
 
 private:
@@ -134,6 +142,9 @@ private:
   void downloadSolution();
   int defaultFactorizationFrequency() const;
   void resetStateForRun();
+  void buildRowCopy(const std::vector<double> &val, std::vector<int> &rowStart,
+                    std::vector<int> &colIdx, std::vector<double> &rval) const;
+  void prepareWorkingProblem();
 };
 
 // mps_reader.cpp

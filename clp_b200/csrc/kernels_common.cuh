@@ -16,7 +16,7 @@ __device__ __forceinline__ double warp_sum(double v)
 
 // indices into DeviceModel::tailCounter
 enum : int { TAIL_DUAL_UPDATE = 0, TAIL_ITER_UPDATE = 1, TAIL_PFI_APPLY = 2, TAIL_HIST2 = 3,
-             TAIL_SELECT = 4 };
+             TAIL_SELECT = 4, TAIL_SPREAD = 5 };
 
 // "last block done": returns true in exactly one CTA of a 1-D grid, after every other CTA of the
 // grid has passed this point (and hence finished the work before it).  What the tail then reads
@@ -39,44 +39,19 @@ __device__ __forceinline__ bool last_block_done(unsigned int *counter)
   return sIsLast != 0;
 }
 
-// out[j] = scale * sum_{i>=j, i<t} Ginv[i][j] * vec[i]   for j in [32*jblock, 32*jblock+32), j < t
-//   mode 0 : nu (BTRAN eta transposes), vec = W[pivot row][:]
-//   mode 1 : new row t of Ginv = -out / alphaCol, diagonal 1/alphaCol, vec = W[pivot row][:]
-//   mode 2 : nu for a general BTRAN, vec = d.mu (the t dot products W_i . v)
-// 256 threads; 'part' is 8 x 33 doubles of shared memory.
-__device__ __forceinline__ void eta_rowvec_body(const DeviceModel &d, int mode, int jblock,
-                                                double (*part)[33])
+// Row t of Ginv (and column t of its transposed copy) for the eta that is being appended:
+//   Ginv[t][j] = -nu_j / alpha_r (j < t),  Ginv[t][t] = 1 / alpha_r,
+// where nu = Ginv^T W[r][0..t) is exactly what the BTRAN of this iteration computed for the same
+// pivot row r and the same t (eta_rowvec_kernel mode 0), so nothing is recomputed here.
+// Grid-stride over j by the calling threads (jt = linear thread index, jn = number of threads).
+__device__ __forceinline__ void eta_append_row(const DeviceModel &d, int jt, int jn)
 {
   const int t = d.st->numEtas;
-  const int j0 = jblock * 32;
-  if (j0 >= t && !(mode == 1 && jblock == 0))
-    return;
-  const int r = d.st->pivotRow;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int j = j0 + lane;
-  const double *wrow = mode == 2 ? d.mu : d.W + (size_t)r * d.tmax;
-  double acc = 0.0;
-  if (j < t)
-    for (int i = j0 + warp; i < t; i += 8) // rows below j0 contribute nothing (lower triangular)
-      if (i >= j)
-        acc = fma(d.Ginv[(size_t)i * d.tmax + j], wrow[i], acc);
-  part[warp][lane] = acc;
-  __syncthreads();
-  if (warp == 0) {
-    double s = 0.0;
-#pragma unroll
-    for (int w = 0; w < 8; w++)
-      s += part[w][lane];
-    if (mode != 1) {
-      if (j < t)
-        d.nu[j] = s;
-    } else {
-      const double dinv = 1.0 / d.st->alphaCol;
-      if (j < t)
-        d.Ginv[(size_t)t * d.tmax + j] = -s * dinv;
-      if (jblock == 0 && lane == 0)
-        d.Ginv[(size_t)t * d.tmax + t] = dinv;
-    }
+  const double dinv = 1.0 / d.st->alphaCol;
+  for (int j = jt; j <= t; j += jn) {
+    const double v = j < t ? -d.nu[j] * dinv : dinv;
+    d.Ginv[(size_t)t * d.tmax + j] = v;
+    d.GinvT[(size_t)j * d.tmax + t] = v;
   }
 }
 
@@ -124,12 +99,71 @@ __device__ __forceinline__ void pivot_scalars_body(const DeviceModel &d)
   st->thetaPrimal = (valueOut - bound) / ac;
 }
 
+// ---- ratio test (CHUZC) helpers shared by price.cu and rowpass.cu
+constexpr unsigned long long kFixOne = 1ull << 40; // fixed-point 1.0 (== infeasibility)
+constexpr unsigned long long kFixCap = 1ull << 41;
+constexpr unsigned long long kSentinel = 0xFFFFFFFFFFFFFFFFull;
+
+__device__ __forceinline__ int ratio_bucket(double r)
+{
+  return (int)((unsigned long long)__double_as_longlong(r) >> 48) & (kHistBuckets - 1);
+}
+
+// Ratio-test candidate test for nonbasic variable j with tableau entry alpha.
+// Returns false if j cannot bound the dual step.  abar = sigma*alpha.
+__device__ __forceinline__ bool candidate(const DeviceModel &d, int j, double alpha, int sigma,
+                                          double &a, double &dtil, bool &boxed, double &range)
+{
+  const unsigned char st = d.status[j];
+  if (st == basic || st == isFixed)
+    return false;
+  const double ab = sigma * alpha;
+  a = fabs(ab);
+  if (a <= 1.0e-12)
+    return false;
+  const double dj = d.dj[j];
+  boxed = false;
+  range = 0.0;
+  if (st == atLowerBound) {
+    if (ab <= 0.0)
+      return false;
+    dtil = dj > 0.0 ? dj : 0.0;
+  } else if (st == atUpperBound) {
+    if (ab >= 0.0)
+      return false;
+    dtil = dj < 0.0 ? -dj : 0.0;
+  } else {
+    dtil = 0.0;
+    return true;
+  }
+  range = d.upper[j] - d.lower[j];
+  boxed = range < 1.0e29;
+  return true;
+}
+
+// slope contribution of a candidate in 2^-40 fixed point relative to the primal infeasibility
+__device__ __forceinline__ unsigned long long slope_weight(double a, bool boxed, double range, double infeas)
+{
+  unsigned long long w = kFixCap;
+  if (boxed) {
+    double v = a * range / infeas * 1099511627776.0;
+    w = v >= 2199023255552.0 ? kFixCap : (unsigned long long)v;
+    if (w == 0ull)
+      w = 1ull; // a bucket with a candidate is never "empty"
+  }
+  return w;
+}
+
+
 // order independent histogram add with warp aggregation: lanes of a warp that hit the same bucket
 // are summed first (one atomic per distinct bucket and warp).  Degenerate LPs put thousands of
 // candidates into the ratio-0 bucket; without aggregation those atomics serialise in L2.
 // Must be called by all 32 lanes of a converged warp; w < 2^42.
+// sHot (optional): shared-memory accumulator of the CTA for bucket 0 (ratio exactly 0: the dual
+// degenerate candidates); the caller flushes it with one global atomic per CTA.
 __device__ __forceinline__ void hist_add_aggregated(unsigned long long *hist, int bucket,
-                                                    unsigned long long w, bool valid)
+                                                    unsigned long long w, bool valid,
+                                                    unsigned long long *sHot = nullptr)
 {
   const unsigned act = __ballot_sync(0xffffffffu, valid);
   if (!valid)
@@ -137,12 +171,18 @@ __device__ __forceinline__ void hist_add_aggregated(unsigned long long *hist, in
   const unsigned peers = __match_any_sync(act, bucket);
   const unsigned lo = (unsigned)(w & 0xFFFFFull), hi = (unsigned)(w >> 20);
   const unsigned slo = __reduce_add_sync(peers, lo), shi = __reduce_add_sync(peers, hi);
-  if ((int)(threadIdx.x & 31) == __ffs(peers) - 1)
-    atomicAdd(hist + bucket, ((unsigned long long)shi << 20) + (unsigned long long)slo);
+  if ((int)(threadIdx.x & 31) == __ffs(peers) - 1) {
+    const unsigned long long sum = ((unsigned long long)shi << 20) + (unsigned long long)slo;
+    if (sHot != nullptr && bucket == 0)
+      atomicAdd(sHot, sum);
+    else
+      atomicAdd(hist + bucket, sum);
+  }
 }
 // same for atomicMin of 64-bit keys (called by the lanes with valid == true of the call above)
 __device__ __forceinline__ void hist_min_aggregated(unsigned long long *hist, int bucket,
-                                                    unsigned long long key, bool valid)
+                                                    unsigned long long key, bool valid,
+                                                    unsigned long long *sHotMin = nullptr)
 {
   const unsigned act = __ballot_sync(0xffffffffu, valid);
   if (!valid)
@@ -152,8 +192,13 @@ __device__ __forceinline__ void hist_min_aggregated(unsigned long long *hist, in
   const unsigned mh = __reduce_min_sync(peers, hi);
   const unsigned lo = hi == mh ? (unsigned)key : 0xFFFFFFFFu;
   const unsigned ml = __reduce_min_sync(peers, lo);
-  if ((int)(threadIdx.x & 31) == __ffs(peers) - 1)
-    atomicMin(hist + bucket, ((unsigned long long)mh << 32) | (unsigned long long)ml);
+  if ((int)(threadIdx.x & 31) == __ffs(peers) - 1) {
+    const unsigned long long mn = ((unsigned long long)mh << 32) | (unsigned long long)ml;
+    if (sHotMin != nullptr && bucket == 0)
+      atomicMin(sHotMin, mn);
+    else
+      atomicMin(hist + bucket, mn);
+  }
 }
 
 } // namespace clpb

@@ -20,60 +20,6 @@
 
 namespace clpb {
 
-constexpr unsigned long long kFixOne = 1ull << 40; // fixed-point 1.0 (== infeasibility)
-constexpr unsigned long long kFixCap = 1ull << 41;
-constexpr unsigned long long kSentinel = 0xFFFFFFFFFFFFFFFFull;
-
-__device__ __forceinline__ int ratio_bucket(double r)
-{
-  return (int)((unsigned long long)__double_as_longlong(r) >> 48) & (kHistBuckets - 1);
-}
-
-// Ratio-test candidate test for nonbasic variable j with tableau entry alpha.
-// Returns false if j cannot bound the dual step.  abar = sigma*alpha.
-__device__ __forceinline__ bool candidate(const DeviceModel &d, int j, double alpha, int sigma,
-                                          double &a, double &dtil, bool &boxed, double &range)
-{
-  const unsigned char st = d.status[j];
-  if (st == basic || st == isFixed)
-    return false;
-  const double ab = sigma * alpha;
-  a = fabs(ab);
-  if (a <= 1.0e-12)
-    return false;
-  const double dj = d.dj[j];
-  boxed = false;
-  range = 0.0;
-  if (st == atLowerBound) {
-    if (ab <= 0.0)
-      return false;
-    dtil = dj > 0.0 ? dj : 0.0;
-  } else if (st == atUpperBound) {
-    if (ab >= 0.0)
-      return false;
-    dtil = dj < 0.0 ? -dj : 0.0;
-  } else {
-    dtil = 0.0;
-    return true;
-  }
-  range = d.upper[j] - d.lower[j];
-  boxed = range < 1.0e29;
-  return true;
-}
-
-// slope contribution of a candidate in 2^-40 fixed point relative to the primal infeasibility
-__device__ __forceinline__ unsigned long long slope_weight(double a, bool boxed, double range, double infeas)
-{
-  unsigned long long w = kFixCap;
-  if (boxed) {
-    double v = a * range / infeas * 1099511627776.0;
-    w = v >= 2199023255552.0 ? kFixCap : (unsigned long long)v;
-    if (w == 0ull)
-      w = 1ull; // a bucket with a candidate is never "empty"
-  }
-  return w;
-}
-
 __device__ __forceinline__ void histogram_add(const DeviceModel &d, double a, double dtil,
                                               bool boxed, double range, double infeas)
 {
@@ -303,8 +249,12 @@ __global__ void __launch_bounds__(1024, 1)
 // candidate test + level-1 histogram (coalesced reads of status / dj / bounds).
 __global__ void __launch_bounds__(256) row_finalize_kernel(DeviceModel d, int colBegin, int colEnd, bool fuseHist)
 {
+  __shared__ unsigned long long sHot;
   if (!iter_active(d.st))
     return;
+  if (threadIdx.x == 0)
+    sHot = 0ull;
+  __syncthreads();
   const int sigma = d.st->sigma;
   const double infeas = d.st->infeas;
   // warp-uniform trip count: the aggregated histogram add is a warp collective
@@ -327,8 +277,11 @@ __global__ void __launch_bounds__(256) row_finalize_kernel(DeviceModel d, int co
     }
     if (fuseHist)
       hist_add_aggregated(d.histWeight, cand ? ratio_bucket(dtil / a) : 0,
-                          cand ? slope_weight(a, boxed, range, infeas) : 0ull, cand);
+                          cand ? slope_weight(a, boxed, range, infeas) : 0ull, cand, &sHot);
   }
+  __syncthreads();
+  if (threadIdx.x == 0 && sHot != 0ull)
+    atomicAdd(d.histWeight, sHot);
 }
 
 // slack part of the row: alpha_{n+i} = -rho_i for nonbasic rows
@@ -647,8 +600,14 @@ __device__ __forceinline__ void chuzc_scan2_body(const DeviceModel &d)
 // then scans the 4096 sub-buckets (chuzc_scan2_body).  1024 threads per CTA.
 __global__ void __launch_bounds__(1024) chuzc_hist2_kernel(DeviceModel d)
 {
+  __shared__ unsigned long long sHot, sHotMin;
   if (!iter_active(d.st))
     return;
+  if (threadIdx.x == 0) {
+    sHot = 0ull;
+    sHotMin = kSentinel;
+  }
+  __syncthreads();
   const int b1 = d.st->bucket1;
   if (b1 >= 0) {
     const int sigma = d.st->sigma;
@@ -667,8 +626,13 @@ __global__ void __launch_bounds__(1024) chuzc_hist2_kernel(DeviceModel d)
         }
       }
       const int sb = (int)(bits >> 36) & (kHist2Buckets - 1);
-      hist_add_aggregated(d.hist2Weight, sb, cand ? slope_weight(a, boxed, range, infeas) : 0ull, cand);
-      hist_min_aggregated(d.hist2Min, sb, bits, cand);
+      hist_add_aggregated(d.hist2Weight, sb, cand ? slope_weight(a, boxed, range, infeas) : 0ull, cand, &sHot);
+      hist_min_aggregated(d.hist2Min, sb, bits, cand, &sHotMin);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && sHot != 0ull) {
+      atomicAdd(d.hist2Weight, sHot);
+      atomicMin(d.hist2Min, sHotMin);
     }
   }
   if (!last_block_done(d.tailCounter + TAIL_HIST2))

@@ -1,0 +1,603 @@
+// rowpass.cu -- everything the iteration does with the tableau row, in ONE cooperative kernel.
+//
+// Replaces (single-GPU path) nine dependent launches -- row_finalize, chuzc_scan1, chuzc_hist2,
+// chuzc_harris, chuzc_select, dual_update, flip_scatter, build_rhs3, gather_nucleus -- i.e. the
+// second half of ClpPackedMatrix::transposeTimes (status mask / zero tolerance,
+// /root/reference/src/ClpPackedMatrix.cpp:1860-1900), ClpSimplexDual::dualColumn0 / dualColumn
+// (src/ClpSimplexDual.cpp:3665 / :4192), ClpSimplexDual::updateDualsInDual (:2430) with its
+// bound flips, and the unpack of the entering column (ClpPackedMatrix::unpack :4803).
+//
+// One CTA per SM (cooperative launch => co-resident), 1024 threads; every thread owns E entries
+// of the row and keeps (alpha, |alpha|, d~, range, flags) in registers across the phases, so the
+// row is read from memory once.  Phases are separated by grid barriers (~1-2 us each) instead of
+// kernel boundaries; the small scans are done redundantly by every CTA, which saves a barrier.
+//   P0 finalize row + level-1 ratio histogram      | barrier
+//   P1 segment totals (32 CTAs)                    | barrier
+//      crossing bucket (every CTA)  P2 level-2 histogram of that bucket | barrier
+//   P3 theta* (every CTA)           P4 Harris bound (atomicMin)         | barrier
+//   P5 largest |alpha| in [theta*, harris] (atomicMax)                  | barrier
+//   P6 decode winner, dual update + bound flips (bit mask)              | barrier
+//   P7 ordered flip list + fixed-point scale (CTA 0)                    | barrier
+//   P8 flip columns -> fixed-point accumulator; entering column -> aqBuf| barrier
+//   P9 three FTRAN right-hand sides rhs3 and their nucleus gather xg
+// All reductions are order independent (integer atomics, min/max of packed keys) or done in a
+// fixed order, exactly as in the separate kernels (price.cu / update.cu), which remain the path
+// of column-sharded runs.
+#include "kernels_common.cuh"
+
+namespace clpb {
+
+// generation barrier over all CTAs of a cooperative grid; bar[0] = arrival count, bar[1] = generation
+__device__ __forceinline__ void grid_barrier(unsigned int *bar)
+{
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    volatile unsigned int *gen = bar + 1;
+    const unsigned int g = *gen; // read BEFORE arriving
+    __threadfence();
+    if (atomicAdd(bar, 1u) == gridDim.x - 1) {
+      bar[0] = 0u;
+      __threadfence();
+      atomicAdd(bar + 1, 1u);
+    } else {
+      while (*gen == g)
+        __nanosleep(32);
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ unsigned long long block_min_u64(unsigned long long v, unsigned long long *sm)
+{
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+    v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0)
+    sm[threadIdx.x >> 5] = v;
+  __syncthreads();
+  v = sm[threadIdx.x & 31];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+    v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v; // same value in every thread
+}
+__device__ __forceinline__ unsigned long long block_max_u64(unsigned long long v, unsigned long long *sm)
+{
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+    v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0)
+    sm[threadIdx.x >> 5] = v;
+  __syncthreads();
+  v = sm[threadIdx.x & 31];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+    v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+enum : unsigned { F_CAND = 1u, F_BOXED = 2u, F_VALID = 4u };
+
+template <int E>
+__global__ void __launch_bounds__(1024, 1) row_pass_kernel(DeviceModel d)
+{
+  IterState *st = d.st;
+  if (!iter_active(st))
+    return; // uniform over the grid
+  __shared__ unsigned long long sU64[32];
+  __shared__ unsigned long long sHot, sHotMin, sResidual, sThetaBits;
+  __shared__ int sI32[32];
+  __shared__ double sF64[32];
+  __shared__ int sSeg, sLastAll, sBucket1, sCross;
+  __shared__ unsigned long long sPrefix;
+  __shared__ int warpCount[32];
+  __shared__ int sBase;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int gtid = blockIdx.x * 1024 + tid, gthreads = gridDim.x * 1024;
+  const int sigma = st->sigma;
+  const double infeas = st->infeas;
+  const int n = d.n, nm = d.nm;
+  if (gtid == 0) { // consumed after barrier 3 / 4
+    st->harrisBits = 0x7FF0000000000000ull;
+    st->chuzcKey = 0ull;
+  }
+  if (tid == 0)
+    sHot = 0ull;
+  __syncthreads();
+
+  // ---------------------------------------------------------------- P0 finalize + histogram
+  double alpha[E], aabs[E], dtil[E], range[E];
+  unsigned flags[E];
+#pragma unroll
+  for (int e = 0; e < E; e++) {
+    const int j = gtid + e * gthreads; // gthreads is a multiple of 32: warp-uniform validity pattern
+    flags[e] = 0u;
+    alpha[e] = 0.0;
+    aabs[e] = 1.0;
+    dtil[e] = 0.0;
+    range[e] = 0.0;
+    bool cand = false, boxed = false;
+    if (j < nm) {
+      flags[e] = F_VALID;
+      const unsigned char s = d.status[j];
+      double al;
+      if (j < n)
+        al = (s == basic || s == isFixed) ? 0.0 : d.alphaRow[j];
+      else
+        al = (s == basic || s == isFixed) ? 0.0 : -d.rho[j - n];
+      if (fabs(al) < d.zeroTolerance)
+        al = 0.0;
+      d.alphaRow[j] = al;
+      alpha[e] = al;
+      cand = al != 0.0 && candidate(d, j, al, sigma, aabs[e], dtil[e], boxed, range[e]);
+      if (cand)
+        flags[e] |= F_CAND | (boxed ? F_BOXED : 0u);
+    }
+    hist_add_aggregated(d.histWeight, cand ? ratio_bucket(dtil[e] / aabs[e]) : 0,
+                        cand ? slope_weight(aabs[e], boxed, range[e], infeas) : 0ull, cand, &sHot);
+  }
+  __syncthreads();
+  if (tid == 0 && sHot != 0ull)
+    atomicAdd(d.histWeight, sHot);
+  grid_barrier(d.gridBar);
+
+  // ---------------------------------------------------------------- P1a segment totals
+  constexpr int NSEG = kHistBuckets / 1024;
+  if ((int)blockIdx.x < NSEG) {
+    const int b = blockIdx.x * 1024 + tid;
+    unsigned long long w = __ldcg(d.histWeight + b);
+    int last = w != 0ull ? b : -1;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      w += __shfl_xor_sync(0xffffffffu, w, o);
+      last = max(last, __shfl_xor_sync(0xffffffffu, last, o));
+    }
+    if (lane == 0) {
+      sU64[warp] = w;
+      sI32[warp] = last;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      unsigned long long t = 0;
+      int l = -1;
+      for (int q = 0; q < 32; q++) {
+        t += sU64[q];
+        l = max(l, sI32[q]);
+      }
+      d.segTotal[blockIdx.x] = t;
+      d.segLast[blockIdx.x] = l;
+    }
+  }
+  grid_barrier(d.gridBar);
+
+  // ---------------------------------------------------------------- P1b crossing bucket (every CTA)
+  if (tid == 0) {
+    unsigned long long c = 0;
+    int seg = -1, lastAll = -1;
+    unsigned long long pre = 0;
+    for (int q = 0; q < NSEG; q++) {
+      const unsigned long long t = __ldcg(d.segTotal + q);
+      if (seg < 0 && c + t >= kFixOne) {
+        seg = q;
+        pre = c;
+      }
+      c += t;
+      lastAll = max(lastAll, __ldcg(d.segLast + q));
+    }
+    sSeg = seg;
+    sLastAll = lastAll;
+    sPrefix = pre;
+    sBucket1 = -1;
+    sResidual = 0xFFFFFFFFFFFFFFFFull;
+  }
+  __syncthreads();
+  if (sLastAll < 0) { // no candidate at all
+    if (gtid == 0) {
+      st->stop = STOP_NO_COLUMN;
+      st->bucket1 = -1;
+    }
+    return;
+  }
+  if (sSeg < 0) {
+    // slope never exhausted: stop at the last break point group
+    if (tid == 0)
+      sBucket1 = sLastAll;
+    __syncthreads();
+  } else {
+    const int b = sSeg * 1024 + tid;
+    const unsigned long long w = __ldcg(d.histWeight + b);
+    unsigned long long inc = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      unsigned long long t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o)
+        inc += t;
+    }
+    if (lane == 31)
+      sU64[warp] = inc;
+    __syncthreads();
+    unsigned long long base = sPrefix;
+    for (int q = 0; q < warp; q++)
+      base += sU64[q];
+    const unsigned long long excl = base + inc - w;
+    if (excl < kFixOne && excl + w >= kFixOne) { // exactly one thread
+      sBucket1 = b;
+      sResidual = kFixOne - excl;
+    }
+    __syncthreads();
+  }
+  const int bucket1 = sBucket1;
+  const unsigned long long residual = sResidual;
+  if (gtid == 0) {
+    st->bucket1 = bucket1;
+    st->residual = residual;
+  }
+
+  // ---------------------------------------------------------------- P2 level-2 histogram
+  if (tid == 0) {
+    sHot = 0ull;
+    sHotMin = kSentinel;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int e = 0; e < E; e++) {
+    bool in = false;
+    unsigned long long bits = 0ull;
+    if (flags[e] & F_CAND) {
+      bits = (unsigned long long)__double_as_longlong(dtil[e] / aabs[e]);
+      in = ((int)(bits >> 48) & (kHistBuckets - 1)) == bucket1;
+    }
+    const int sb = (int)(bits >> 36) & (kHist2Buckets - 1);
+    hist_add_aggregated(d.hist2Weight, sb,
+                        in ? slope_weight(aabs[e], (flags[e] & F_BOXED) != 0u, range[e], infeas) : 0ull, in, &sHot);
+    hist_min_aggregated(d.hist2Min, sb, bits, in, &sHotMin);
+  }
+  __syncthreads();
+  if (tid == 0 && sHot != 0ull) {
+    atomicAdd(d.hist2Weight, sHot);
+    atomicMin(d.hist2Min, sHotMin);
+  }
+  grid_barrier(d.gridBar);
+
+  // ---------------------------------------------------------------- P3 theta* (every CTA)
+  {
+    unsigned long long w[4], mn[4], tot = 0;
+    int last = -1;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      const int b = tid * 4 + q;
+      w[q] = __ldcg(d.hist2Weight + b);
+      mn[q] = __ldcg(d.hist2Min + b);
+      tot += w[q];
+      if (mn[q] != kSentinel)
+        last = b;
+    }
+    unsigned long long inc = tot;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      unsigned long long t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o)
+        inc += t;
+    }
+    int wl = last;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+      wl = max(wl, __shfl_xor_sync(0xffffffffu, wl, o));
+    if (lane == 31)
+      sU64[warp] = inc;
+    if (lane == 0)
+      sI32[warp] = wl;
+    if (tid == 0)
+      sCross = -1;
+    __syncthreads();
+    unsigned long long base = 0;
+    for (int q = 0; q < warp; q++)
+      base += sU64[q];
+    const unsigned long long excl = base + inc - tot;
+    if (excl < residual && excl + tot >= residual) {
+      unsigned long long c = excl;
+      int found = -1;
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        c += w[q];
+        if (found < 0 && c >= residual)
+          found = q;
+      }
+      sCross = tid * 4 + found;
+      sThetaBits = mn[found];
+    }
+    __syncthreads();
+    if (sCross < 0 && tid == 0) {
+      // numerically possible only through fixed-point truncation: take the last sub-bucket
+      int lastAll = -1;
+      for (int q = 0; q < 32; q++)
+        lastAll = max(lastAll, sI32[q]);
+      sThetaBits = __ldcg(d.hist2Min + lastAll);
+    }
+    __syncthreads();
+  }
+  const double thetaStar = __longlong_as_double((long long)sThetaBits);
+  if (blockIdx.x == 0) {
+    // ||rho||^2 in a fixed order (DSE weight of the pivot row)
+    double nrm = 0.0;
+    for (int i = tid; i < d.m; i += 1024) {
+      const double r = d.rho[i];
+      nrm = fma(r, r, nrm);
+    }
+    nrm = warp_sum(nrm);
+    if (lane == 0)
+      sF64[warp] = nrm;
+    __syncthreads();
+    if (tid == 0) {
+      double nsum = 0.0;
+      for (int q = 0; q < 32; q++)
+        nsum += sF64[q];
+      st->rhoNorm2 = nsum;
+      st->thetaStar = thetaStar;
+    }
+  }
+
+  // ---------------------------------------------------------------- P4 Harris bound
+  {
+    unsigned long long best = 0x7FF0000000000000ull;
+#pragma unroll
+    for (int e = 0; e < E; e++)
+      if ((flags[e] & F_CAND) && aabs[e] >= d.acceptablePivot && dtil[e] / aabs[e] >= thetaStar)
+        best = min(best, (unsigned long long)__double_as_longlong((dtil[e] + d.dualTolerance) / aabs[e]));
+    best = block_min_u64(best, sU64);
+    if (tid == 0 && best != 0x7FF0000000000000ull)
+      atomicMin(&st->harrisBits, best);
+  }
+  grid_barrier(d.gridBar);
+
+  // ---------------------------------------------------------------- P5 largest |alpha| in [theta*, harris]
+  const unsigned long long harrisBits = __ldcg(&st->harrisBits);
+  const double harris = __longlong_as_double((long long)harrisBits);
+  {
+    unsigned long long best = 0ull;
+#pragma unroll
+    for (int e = 0; e < E; e++) {
+      if (!(flags[e] & F_CAND) || aabs[e] < d.acceptablePivot)
+        continue;
+      const double ratio = dtil[e] / aabs[e];
+      if (ratio < thetaStar || ratio > harris)
+        continue;
+      const int j = gtid + e * gthreads;
+      best = max(best, ((unsigned long long)__double_as_longlong(aabs[e]) & ~0xFFFFFull) |
+                           (unsigned long long)(0xFFFFF - j));
+    }
+    best = block_max_u64(best, sU64);
+    if (tid == 0 && best != 0ull)
+      atomicMax(&st->chuzcKey, best);
+  }
+  grid_barrier(d.gridBar);
+
+  // ---------------------------------------------------------------- P6 winner, dual update, flips
+  const unsigned long long key = __ldcg(&st->chuzcKey);
+  if (key == 0ull) {
+    if (gtid == 0)
+      st->stop = STOP_NO_COLUMN;
+    return; // uniform
+  }
+  const int seqIn = 0xFFFFF - (int)(key & 0xFFFFFull);
+  const double alphaQ = __ldcg(d.alphaRow + seqIn);
+  double theta = d.dj[seqIn] / (sigma * alphaQ); // dj[seqIn] is not touched below
+  theta = theta > 0.0 ? theta : 0.0;
+  if (gtid == 0) {
+    st->seqIn = seqIn;
+    st->alphaRow = alphaQ;
+    st->thetaDual = theta;
+    st->harrisTheta = harris;
+  }
+  {
+    const double tol = d.dualTolerance;
+    unsigned long long maxRange = 0ull;
+#pragma unroll
+    for (int e = 0; e < E; e++) {
+      const int j = gtid + e * gthreads;
+      const double al = alpha[e];
+      if (!(flags[e] & F_VALID) || al == 0.0 || j == seqIn)
+        continue;
+      const unsigned char s = d.status[j];
+      if (s == basic || s == isFixed)
+        continue;
+      double dnew = d.dj[j] - theta * (sigma * al);
+      const bool wrong = (s == atLowerBound && dnew < -tol) || (s == atUpperBound && dnew > tol);
+      if (wrong) {
+        const double lo = d.lower[j], up = d.upper[j];
+        if (up - lo < 1.0e29) {
+          if (s == atLowerBound) {
+            d.status[j] = atUpperBound;
+            d.sol[j] = up;
+          } else {
+            d.status[j] = atLowerBound;
+            d.sol[j] = lo;
+          }
+          atomicOr(d.flipBits + (j >> 5), 1u << (j & 31));
+          maxRange = max(maxRange, (unsigned long long)__double_as_longlong(up - lo));
+        } else {
+          d.cost[j] -= dnew;
+          dnew = 0.0;
+          atomicAdd(&st->costShifts, 1);
+        }
+      } else if ((s == isFree || s == superBasic) && fabs(dnew) > tol) {
+        d.cost[j] -= dnew;
+        dnew = 0.0;
+        atomicAdd(&st->costShifts, 1);
+      }
+      d.dj[j] = dnew;
+    }
+    maxRange = block_max_u64(maxRange, sU64);
+    if (tid == 0 && maxRange != 0ull)
+      atomicMax(&st->flipMaxBits, maxRange);
+  }
+  grid_barrier(d.gridBar);
+
+  // ---------------------------------------------------------------- P7 ordered flip list (CTA 0)
+  if (blockIdx.x == 0) {
+    const int nwords = (nm + 31) >> 5;
+    if (tid == 0)
+      sBase = 0;
+    __syncthreads();
+    for (int start = 0; start < nwords; start += 1024 * 4) {
+      unsigned int w[4];
+      int cnt = 0;
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        const int wi = start + tid * 4 + q;
+        w[q] = wi < nwords ? __ldcg(d.flipBits + wi) : 0u;
+        cnt += __popc(w[q]);
+      }
+      int inc = cnt;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o)
+          inc += t;
+      }
+      if (lane == 31)
+        warpCount[warp] = inc;
+      __syncthreads();
+      int off = sBase + inc - cnt;
+      for (int q = 0; q < warp; q++)
+        off += warpCount[q];
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        unsigned int bits = w[q];
+        const int j0 = (start + tid * 4 + q) << 5;
+        while (bits) {
+          const int b = __ffs(bits) - 1;
+          bits &= bits - 1;
+          d.flipList[off++] = j0 + b;
+        }
+      }
+      __syncthreads();
+      if (tid == 1023) {
+        int tot = 0;
+        for (int q = 0; q < 32; q++)
+          tot += warpCount[q];
+        sBase += tot;
+      }
+      __syncthreads();
+    }
+    if (tid == 0) {
+      const int nf = sBase;
+      st->numFlips = nf;
+      if (nf > 0) {
+        const unsigned long long mb = atomicMax(&st->flipMaxBits, 0ull);
+        const double bound = d.amax * __longlong_as_double((long long)mb);
+        int Ex = 0;
+        frexp(bound, &Ex);
+        const int bitsN = 32 - __clz(nf);
+        const int Q = 62 - bitsN;
+        st->flipScale = ldexp(1.0, Q - Ex);
+        st->flipInvScale = ldexp(1.0, Ex - Q);
+      }
+      st->flipMaxBits = 0ull;
+    }
+  }
+  grid_barrier(d.gridBar);
+
+  // ---------------------------------------------------------------- P8 scatter flips + entering column
+  const int nf = __ldcg(&st->numFlips);
+  if (nf > 0) {
+    const double scale = __ldcg(&st->flipScale);
+    unsigned long long *acc = reinterpret_cast<unsigned long long *>(d.flipAcc);
+    const int gw = gtid >> 5, GW = gthreads >> 5;
+    for (int f = gw; f < nf; f += GW) {
+      const int j = __ldcg(d.flipList + f);
+      const double rg = d.upper[j] - d.lower[j];
+      const double delta = __ldcg(d.status + j) == atUpperBound ? rg : -rg;
+      if (j >= n) {
+        if (lane == 0)
+          atomicAdd(acc + (j - n), (unsigned long long)__double2ll_rn(delta * scale));
+      } else {
+        const int e1 = d.colStart[j + 1];
+        for (int e = d.colStart[j] + lane; e < e1; e += 32)
+          atomicAdd(acc + d.rowIdx[e], (unsigned long long)__double2ll_rn(-delta * d.val[e] * scale));
+      }
+    }
+  }
+  if (seqIn < n && (int)blockIdx.x == (int)gridDim.x - 1) { // entering column -> aqBuf (zero when idle)
+    const int e1 = d.colStart[seqIn + 1];
+    for (int e = d.colStart[seqIn] + tid; e < e1; e += 1024)
+      d.aqBuf[d.rowIdx[e]] = d.val[e];
+  }
+  grid_barrier(d.gridBar);
+
+  // ---------------------------------------------------------------- P9 rhs3 and its nucleus gather
+  {
+    const double inv = nf > 0 ? __ldcg(&st->flipInvScale) : 0.0;
+    const int ldk = d.fd->ldk, k = d.fd->k;
+    const int maxk8 = (d.m + 7) / 8 * 8;
+    double *xg = d.ywork + (size_t)3 * maxk8;
+    for (int p = gtid; p < d.m; p += gthreads) {
+      double aq;
+      if (seqIn >= n) {
+        aq = (p == seqIn - n) ? -1.0 : 0.0;
+      } else {
+        aq = __ldcg(d.aqBuf + p);
+        if (aq != 0.0)
+          d.aqBuf[p] = 0.0;
+      }
+      double fl = 0.0;
+      if (nf > 0) {
+        const long long a = __ldcg(d.flipAcc + p);
+        if (a != 0ll) {
+          fl = (double)a * inv;
+          d.flipAcc[p] = 0ll;
+        }
+      }
+      const double rh = d.rho[p];
+      d.rhs3[p] = aq;
+      d.rhs3[(size_t)d.m + p] = rh;
+      d.rhs3[(size_t)2 * d.m + p] = fl;
+      const int ni = d.posToNuc[p];
+      if (ni >= 0) {
+        xg[ni] = aq;
+        xg[(size_t)ldk + ni] = rh;
+        xg[(size_t)2 * ldk + ni] = fl;
+      }
+    }
+    for (int j = k + gtid; j < ldk; j += gthreads) { // zero padding so the GEMV can run over ldk
+      xg[j] = 0.0;
+      xg[(size_t)ldk + j] = 0.0;
+      xg[(size_t)2 * ldk + j] = 0.0;
+    }
+  }
+}
+
+// Launch; returns false if the row is too long for the register-resident variant (caller falls
+// back to the separate kernels).
+bool launch_row_pass(const DeviceModel &d, cudaStream_t s)
+{
+  static int numSMs = 0;
+  if (numSMs == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&numSMs, cudaDevAttrMultiProcessorCount, dev);
+    if (numSMs <= 0)
+      numSMs = 148;
+  }
+  const long gthreads = (long)numSMs * 1024;
+  const int need = (int)((d.nm + gthreads - 1) / gthreads);
+  if (need > 8 || numSMs < kHistBuckets / 1024)
+    return false;
+  DeviceModel dm = d;
+  void *args[] = {&dm};
+  cudaError_t rc;
+  if (need <= 1)
+    rc = cudaLaunchCooperativeKernel((void *)row_pass_kernel<1>, dim3(numSMs), dim3(1024), args, 0, s);
+  else if (need <= 2)
+    rc = cudaLaunchCooperativeKernel((void *)row_pass_kernel<2>, dim3(numSMs), dim3(1024), args, 0, s);
+  else if (need <= 4)
+    rc = cudaLaunchCooperativeKernel((void *)row_pass_kernel<4>, dim3(numSMs), dim3(1024), args, 0, s);
+  else
+    rc = cudaLaunchCooperativeKernel((void *)row_pass_kernel<8>, dim3(numSMs), dim3(1024), args, 0, s);
+  return rc == cudaSuccess;
+}
+
+} // namespace clpb

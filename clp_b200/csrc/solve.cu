@@ -112,116 +112,185 @@ __global__ void __launch_bounds__(256)
   }
 }
 
-// x_N = yN ; x_C = S1*yN - b_C   (in place on b, 8 lanes per position)
+// x_N = yN ; x_C = S1*yN - b_C   (in place on b, 8 lanes per position).  etaTail: the last CTA
+// then gathers the finished columns at the eta positions, xp[c][j] = b_c[etaPos[j]], the compact
+// right-hand side of the t x t system G mu = v0[P] (pfi_mu_kernel reads it coalesced).
 template <int NRHS>
-__global__ void ftran_spread_kernel(DeviceModel d, double *__restrict__ b, int bstride,
-                                    const double *__restrict__ y, bool checkState)
+__global__ void __launch_bounds__(256)
+    ftran_spread_kernel(DeviceModel d, double *__restrict__ b, int bstride,
+                        const double *__restrict__ y, bool checkState, bool etaTail)
 {
   if (checkState && !iter_active(d.st))
     return;
   const int sub = threadIdx.x & 7;
-  int p = (blockIdx.x * blockDim.x + threadIdx.x) >> 3;
-  if (p >= d.m)
-    return; // whole 8-lane group exits together
-  const unsigned gmask = 0xFFu << ((threadIdx.x & 31) & ~7);
-  const int ldk = d.fd->ldk;
-  const int *__restrict__ s1Col = d.fd->s1Col;
-  const double *__restrict__ s1Val = d.fd->s1Val;
-  int ni = d.posToNuc[p];
-  if (ni >= 0) {
-    if (sub == 0)
+  const int p = (blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+  if (p < d.m) { // whole 8-lane groups take the same branch
+    const unsigned gmask = 0xFFu << ((threadIdx.x & 31) & ~7);
+    const int ldk = d.fd->ldk;
+    const int *__restrict__ s1Col = d.fd->s1Col;
+    const double *__restrict__ s1Val = d.fd->s1Val;
+    const int ni = d.posToNuc[p];
+    if (ni >= 0) {
+      if (sub == 0)
+        for (int c = 0; c < NRHS; c++)
+          b[(size_t)c * bstride + p] = y[(size_t)c * ldk + ni];
+    } else {
+      double acc[NRHS];
+#pragma unroll
       for (int c = 0; c < NRHS; c++)
-        b[(size_t)c * bstride + p] = y[(size_t)c * ldk + ni];
-    return;
+        acc[c] = 0.0;
+      if (d.fd->k > 0) {
+        int e0 = d.s1RowStart[p], e1 = d.s1RowStart[p + 1];
+        for (int e = e0 + sub; e < e1; e += 8) {
+          double v = s1Val[e];
+          int j = s1Col[e];
+#pragma unroll
+          for (int c = 0; c < NRHS; c++)
+            acc[c] = fma(v, y[(size_t)c * ldk + j], acc[c]);
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < NRHS; c++) {
+        acc[c] += __shfl_xor_sync(gmask, acc[c], 4);
+        acc[c] += __shfl_xor_sync(gmask, acc[c], 2);
+        acc[c] += __shfl_xor_sync(gmask, acc[c], 1);
+      }
+      if (sub == 0)
+        for (int c = 0; c < NRHS; c++)
+          b[(size_t)c * bstride + p] = acc[c] - b[(size_t)c * bstride + p];
+    }
   }
+  if (!etaTail)
+    return;
+  if (!last_block_done(d.tailCounter + TAIL_SPREAD))
+    return;
+  const int t = d.st->numEtas;
+  for (int j0 = threadIdx.x; j0 < t; j0 += 8 * 256) { // eight independent gathers in flight per thread
+    int pj[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++)
+      pj[u] = (j0 + 256 * u < t) ? d.etaPos[j0 + 256 * u] : 0;
+    double v[8][NRHS];
+#pragma unroll
+    for (int u = 0; u < 8; u++)
+#pragma unroll
+      for (int c = 0; c < NRHS; c++)
+        v[u][c] = __ldcg(b + (size_t)c * bstride + pj[u]);
+#pragma unroll
+    for (int u = 0; u < 8; u++)
+      if (j0 + 256 * u < t)
+#pragma unroll
+        for (int c = 0; c < NRHS; c++)
+          d.xp[(size_t)c * d.tmax + j0 + 256 * u] = v[u][c];
+  }
+}
+
+// mu[c][i] = sum_{j<=i} Ginv[i][j] * xp_c[j]   (one CTA per eta i: the whole row is in flight at once,
+// the kernel is a single wave of t CTAs -- latency, not bandwidth, is what matters for 8 t^2/2 bytes)
+template <int NRHS>
+__global__ void __launch_bounds__(256) pfi_mu_kernel(DeviceModel d, bool checkState)
+{
+  __shared__ double part[8][NRHS];
+  if (checkState && !iter_active(d.st))
+    return;
+  const int t = d.st->numEtas;
+  const int i = blockIdx.x;
+  if (i >= t)
+    return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const double *__restrict__ grow = d.Ginv + (size_t)i * d.tmax;
+  const double *__restrict__ xp = d.xp;
   double acc[NRHS];
 #pragma unroll
   for (int c = 0; c < NRHS; c++)
     acc[c] = 0.0;
-  if (d.fd->k > 0) {
-    int e0 = d.s1RowStart[p], e1 = d.s1RowStart[p + 1];
-    for (int e = e0 + sub; e < e1; e += 8) {
-      double v = s1Val[e];
-      int j = s1Col[e];
+  for (int j = threadIdx.x; j <= i; j += 1024) {
+    double g[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++)
+      g[u] = (j + 256 * u <= i) ? __ldcs(grow + j + 256 * u) : 0.0;
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int jj = min(j + 256 * u, i);
 #pragma unroll
       for (int c = 0; c < NRHS; c++)
-        acc[c] = fma(v, y[(size_t)c * ldk + j], acc[c]);
+        acc[c] = fma(g[u], __ldg(xp + (size_t)c * d.tmax + jj), acc[c]);
     }
   }
 #pragma unroll
   for (int c = 0; c < NRHS; c++) {
-    acc[c] += __shfl_xor_sync(gmask, acc[c], 4);
-    acc[c] += __shfl_xor_sync(gmask, acc[c], 2);
-    acc[c] += __shfl_xor_sync(gmask, acc[c], 1);
-  }
-  if (sub == 0)
-    for (int c = 0; c < NRHS; c++)
-      b[(size_t)c * bstride + p] = acc[c] - b[(size_t)c * bstride + p];
-}
-
-// mu[c][i] = sum_{j<=i} Ginv[i][j] * x_c[etaPos[j]]   (one warp per eta i)
-template <int NRHS>
-__global__ void pfi_mu_kernel(DeviceModel d, const double *__restrict__ x, int xstride,
-                              bool checkState)
-{
-  if (checkState && !iter_active(d.st))
-    return;
-  const int t = d.st->numEtas;
-  const int lane = threadIdx.x & 31;
-  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (i >= t)
-    return;
-  const double *grow = d.Ginv + (size_t)i * d.tmax;
-  double acc[NRHS];
-#pragma unroll
-  for (int c = 0; c < NRHS; c++)
-    acc[c] = 0.0;
-  for (int j = lane; j <= i; j += 32) {
-    double g = grow[j];
-    int p = d.etaPos[j];
-#pragma unroll
-    for (int c = 0; c < NRHS; c++)
-      acc[c] = fma(g, x[(size_t)c * xstride + p], acc[c]);
-  }
-#pragma unroll
-  for (int c = 0; c < NRHS; c++)
     acc[c] = warp_sum(acc[c]);
-  if (lane == 0)
-    for (int c = 0; c < NRHS; c++)
-      d.mu[(size_t)c * d.tmax + i] = acc[c];
+    if (lane == 0)
+      part[warp][c] = acc[c];
+  }
+  __syncthreads();
+  if (threadIdx.x < NRHS) {
+    double sum = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; w++)
+      sum += part[w][threadIdx.x];
+    d.mu[(size_t)threadIdx.x * d.tmax + i] = sum;
+  }
 }
 
-// x_c[p] -= sum_{i<t} W[p][i] * mu_c[i]   (one warp per position).  pivotTail: the last CTA then
-// evaluates the accuracy gate and the primal step (pivot_scalars_body) on the finished columns.
+// x_c[p] -= sum_{i<t} W[p][i] * mu_c[i].  One warp per group of four positions: the four panel rows
+// are streamed together (eight 8-byte loads in flight per lane) and every mu value is reused four
+// times.  pivotTail: the last CTA then evaluates the accuracy gate and the primal step
+// (pivot_scalars_body) on the finished columns.
 template <int NRHS>
-__global__ void pfi_apply_kernel(DeviceModel d, double *__restrict__ x, int xstride,
-                                 bool checkState, bool pivotTail)
+__global__ void __launch_bounds__(256) pfi_apply_kernel(DeviceModel d, double *__restrict__ x, int xstride,
+                                                        bool checkState, bool pivotTail)
 {
   if (checkState && !iter_active(d.st))
     return;
   const int t = d.st->numEtas;
   if (t > 0) {
+    constexpr int R = 4;
     const int lane = threadIdx.x & 31;
     const int warpsPerBlock = blockDim.x >> 5;
-    for (int p = blockIdx.x * warpsPerBlock + (threadIdx.x >> 5); p < d.m;
-         p += gridDim.x * warpsPerBlock) {
-      const double *wrow = d.W + (size_t)p * d.tmax;
-      double acc[NRHS];
+    const int ngroups = (d.m + R - 1) / R;
+    for (int g = blockIdx.x * warpsPerBlock + (threadIdx.x >> 5); g < ngroups; g += gridDim.x * warpsPerBlock) {
+      const int p0 = g * R;
+      const double *wrow[R];
 #pragma unroll
-      for (int c = 0; c < NRHS; c++)
-        acc[c] = 0.0;
-      for (int i = lane; i < t; i += 32) {
-        double w = wrow[i];
+      for (int r = 0; r < R; r++)
+        wrow[r] = d.W + (size_t)min(p0 + r, d.m - 1) * d.tmax;
+      double acc[R][NRHS];
+#pragma unroll
+      for (int r = 0; r < R; r++)
 #pragma unroll
         for (int c = 0; c < NRHS; c++)
-          acc[c] = fma(w, d.mu[(size_t)c * d.tmax + i], acc[c]);
+          acc[r][c] = 0.0;
+      for (int i = lane; i < t; i += 64) {
+        double w[2][R];
+#pragma unroll
+        for (int u = 0; u < 2; u++)
+#pragma unroll
+          for (int r = 0; r < R; r++)
+            w[u][r] = (i + 32 * u < t) ? __ldcs(wrow[r] + i + 32 * u) : 0.0;
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+          const int ii = min(i + 32 * u, t - 1);
+#pragma unroll
+          for (int c = 0; c < NRHS; c++) {
+            const double muv = __ldg(d.mu + (size_t)c * d.tmax + ii);
+#pragma unroll
+            for (int r = 0; r < R; r++)
+              acc[r][c] = fma(w[u][r], muv, acc[r][c]);
+          }
+        }
       }
 #pragma unroll
-      for (int c = 0; c < NRHS; c++)
-        acc[c] = warp_sum(acc[c]);
-      if (lane == 0)
+      for (int r = 0; r < R; r++)
+#pragma unroll
         for (int c = 0; c < NRHS; c++)
-          x[(size_t)c * xstride + p] -= acc[c];
+          acc[r][c] = warp_sum(acc[r][c]);
+      if (lane == 0)
+#pragma unroll
+        for (int r = 0; r < R; r++)
+          if (p0 + r < d.m)
+            for (int c = 0; c < NRHS; c++)
+              x[(size_t)c * xstride + p0 + r] -= acc[r][c];
     }
   }
   if (!pivotTail)
@@ -234,7 +303,7 @@ __global__ void pfi_apply_kernel(DeviceModel d, double *__restrict__ x, int xstr
 
 template <int NRHS>
 static void ftran_impl(const DeviceModel &d, double *b, bool applyEtas, bool checkState,
-                       cudaStream_t s, bool pivotTail = false)
+                       cudaStream_t s, bool pivotTail = false, bool pregathered = false)
 {
   const int m = d.m;
   // fixed launch shapes (grid-stride kernels read k from the device-side FactorDesc)
@@ -243,17 +312,18 @@ static void ftran_impl(const DeviceModel &d, double *b, bool applyEtas, bool che
   if (gblocks > 148)
     gblocks = 148;
   double *xg = d.ywork + (size_t)3 * roundUp8(maxk);
-  gather_nucleus_kernel<<<gblocks, 256, 0, s>>>(d, b, m, xg, NRHS, checkState);
+  if (!pregathered) // the row pass (rowpass.cu) writes xg together with the right-hand sides
+    gather_nucleus_kernel<<<gblocks, 256, 0, s>>>(d, b, m, xg, NRHS, checkState);
   int blocks = maxk < 148 * 8 ? maxk : 148 * 8;
   if (g_kernelTimers && checkState)
     cudaEventRecord(g_kernelTimers->ftranGemv[0], s);
   gemv_rows_kernel<NRHS><<<blocks, 256, 0, s>>>(d.fd, 0, xg, d.ywork, -1, nullptr, d.st, checkState);
   if (g_kernelTimers && checkState)
     cudaEventRecord(g_kernelTimers->ftranGemv[1], s);
-  ftran_spread_kernel<NRHS><<<(m * 8 + 255) / 256, 256, 0, s>>>(d, b, m, d.ywork, checkState);
+  ftran_spread_kernel<NRHS><<<(m * 8 + 255) / 256, 256, 0, s>>>(d, b, m, d.ywork, checkState, applyEtas);
   if (applyEtas) {
-    pfi_mu_kernel<NRHS><<<(d.tmax + 7) / 8, 256, 0, s>>>(d, b, m, checkState);
-    int pblocks = (m + 7) / 8;
+    pfi_mu_kernel<NRHS><<<d.tmax, 256, 0, s>>>(d, checkState);
+    int pblocks = ((m + 3) / 4 + 7) / 8;
     if (pblocks > 148 * 8)
       pblocks = 148 * 8;
     pfi_apply_kernel<NRHS><<<pblocks, 256, 0, s>>>(d, b, m, checkState, pivotTail);
@@ -273,26 +343,54 @@ void launch_ftran(const DeviceModel &d, int nrhs, bool applyEtas, cudaStream_t s
 
 // The three FTRANs of a simplex iteration (a_q, rho -> tau, bound-flip column) with the eta panel
 // and, as the tail of the last kernel, the pivot accuracy gate / primal step length.
-void launch_ftran_iteration(const DeviceModel &d, cudaStream_t s)
+void launch_ftran_iteration(const DeviceModel &d, bool pregathered, cudaStream_t s)
 {
-  ftran_impl<3>(d, d.rhs3, true, true, s, true);
+  ftran_impl<3>(d, d.rhs3, true, true, s, true, pregathered);
 }
 
 // ---------------------------------------------------------------------------------------
 // out[j] = scale * sum_{i>=j, i<t} Ginv[i][j] * W[row][i]   for j < t
 //   mode 0 : nu (BTRAN eta transposes), vec = W[pivot row][:]
-//   mode 1 : new row t of Ginv = -out / alphaCol, diagonal 1/alphaCol, vec = W[pivot row][:]
+//   (the new row t of Ginv is -nu / alphaCol for the same vec: eta_append_row, kernels_common.cuh)
 //   mode 2 : nu for a general BTRAN, vec = d.mu (the t dot products W_i . v)
+// nu[j] = sum_{i=j}^{t-1} Ginv[i][j] * vec[i] = (row j of GinvT) . vec : one CTA per j, coalesced
 __global__ void __launch_bounds__(256) eta_rowvec_kernel(DeviceModel d, int mode, bool checkState)
 {
-  __shared__ double part[8][33];
+  __shared__ double part[8];
   if (checkState && !iter_active(d.st))
     return;
-  eta_rowvec_body(d, mode, blockIdx.x, part);
+  const int t = d.st->numEtas;
+  const int j = blockIdx.x;
+  if (j >= t)
+    return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const double *__restrict__ vec = mode == 2 ? d.mu : d.W + (size_t)d.st->pivotRow * d.tmax;
+  const double *__restrict__ grow = d.GinvT + (size_t)j * d.tmax;
+  double acc = 0.0;
+  for (int i = j + threadIdx.x; i < t; i += 1024) {
+    double g[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++)
+      g[u] = (i + 256 * u < t) ? __ldcs(grow + i + 256 * u) : 0.0;
+#pragma unroll
+    for (int u = 0; u < 4; u++)
+      acc = fma(g[u], __ldg(vec + min(i + 256 * u, t - 1)), acc);
+  }
+  acc = warp_sum(acc);
+  if (lane == 0)
+    part[warp] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double sum = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; w++)
+      sum += part[w];
+    d.nu[j] = sum;
+  }
 }
 void launch_eta_rowvec(const DeviceModel &d, int mode, bool checkState, cudaStream_t s)
 {
-  eta_rowvec_kernel<<<(d.tmax + 31) / 32, 256, 0, s>>>(d, mode, checkState);
+  eta_rowvec_kernel<<<d.tmax, 256, 0, s>>>(d, mode, checkState);
 }
 
 // u = e_r - sum_j e_{p_j} nu_j ; rho_C = -u_C    (thread per position)

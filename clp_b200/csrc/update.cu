@@ -350,14 +350,13 @@ __device__ __forceinline__ void pivot_fixup_body(const DeviceModel &d)
 }
 
 // End of an iteration in one kernel:
-//   CTAs [0, etaBlocks)      : new row of Ginv (eta_rowvec mode 1)
+//   CTAs [0, etaBlocks)      : new row of Ginv / column of GinvT from the BTRAN's nu (eta_append_row)
 //   CTAs [etaBlocks, grid)   : x_B, DSE weights (ClpDualRowSteepest.cpp:501-538) and the new eta
 //                              column, one thread per position; clear the ratio-test histograms and
 //                              the flip mask; score every position for the NEXT iteration's CHUZR
 //   tail (last CTA, thread 0): housekeeping of this iteration, then decode the next pivot row.
 __global__ void __launch_bounds__(256) iteration_update_kernel(DeviceModel d, int etaBlocks)
 {
-  __shared__ double part[8][33];
   IterState *st = d.st;
   if (!iter_active(st)) {
     if (blockIdx.x == 0 && threadIdx.x == 0)
@@ -365,7 +364,7 @@ __global__ void __launch_bounds__(256) iteration_update_kernel(DeviceModel d, in
     return;
   }
   if ((int)blockIdx.x < etaBlocks) {
-    eta_rowvec_body(d, 1, blockIdx.x, part);
+    eta_append_row(d, blockIdx.x * 256 + threadIdx.x, etaBlocks * 256);
   } else {
     const int posBlocks = gridDim.x - etaBlocks;
     const int gtid = (blockIdx.x - etaBlocks) * 256 + threadIdx.x;
@@ -429,7 +428,7 @@ __global__ void __launch_bounds__(256) iteration_update_kernel(DeviceModel d, in
 
 void launch_pivot_updates(const DeviceModel &d, cudaStream_t s)
 {
-  const int etaBlocks = (d.tmax + 31) / 32;
+  const int etaBlocks = (d.tmax + 1023) / 1024;
   const int posBlocks = (d.m + 255) / 256;
   iteration_update_kernel<<<etaBlocks + posBlocks, 256, 0, s>>>(d, etaBlocks);
 }
@@ -665,10 +664,15 @@ __global__ void eta_append_finish_kernel(DeviceModel d, int seqIn)
   d.status[seqIn] = basic;
   d.pivotVariable[r] = seqIn;
 }
+__global__ void eta_append_row_kernel(DeviceModel d)
+{
+  eta_append_row(d, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
+}
 void launch_eta_append_test(const DeviceModel &d, int pivotRow, int seqIn, cudaStream_t s)
 {
   eta_append_prepare_kernel<<<1, 1, 0, s>>>(d, pivotRow);
-  launch_eta_rowvec(d, 1, false, s);
+  launch_eta_rowvec(d, 0, false, s); // nu for this pivot row
+  eta_append_row_kernel<<<(d.tmax + 255) / 256, 256, 0, s>>>(d);
   eta_append_column_kernel<<<(d.m + 255) / 256, 256, 0, s>>>(d);
   eta_append_finish_kernel<<<1, 1, 0, s>>>(d, seqIn);
 }

@@ -117,6 +117,16 @@ class ClpSimplex:
     def setFactorizationFrequency(self, v): self._set("factorizationFrequency", v)
     def setParameter(self, key, v): self._set(key, v)
 
+    def scaling(self, mode):
+        """ClpModel::scaling(mode): 0 off, 1 equilibrium, 2 geometric, 3 automatic, 4 dynamic."""
+        self._L.Clpb_scaling(self._h, int(mode))
+
+    def scaleFactors(self):
+        """(rc, rowScale, columnScale) of ClpPackedMatrix::scale for the current mode (host only)."""
+        r = np.ones(self.numberRows()); c = np.ones(self.numberColumns())
+        rc = self._L.Clpb_scaleFactors(self._h, _dp(r), _dp(c))
+        return rc, r, c
+
     def copyinStatus(self, status):
         st = np.ascontiguousarray(status, dtype=np.uint8)
         self._L.Clpb_copyinStatus(self._h, _up(st))

@@ -1,0 +1,15 @@
+cd $GRAFT_REPO_ROOT; mkdir -p gpurun_out
+export PATH=$PATH:/usr/local/cuda/bin
+( time timeout 900 python -m pytest tests -m gpu -q --timeout 300 -x 2>&1 | tail -5 ) > gpurun_out/t15.log 2>&1
+tail -8 gpurun_out/t15.log
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k 'regex:^(?!lu_|trsm|gemm_sub|set_perm|transpose|zero_pad|gather_nucleus_matrix).*' -s 17300 -c 80 --csv --log-file gpurun_out/launches15.csv python tests/ncu_target.py c2 1012 > gpurun_out/ncu15.log 2>&1; tail -2 gpurun_out/ncu14.log
+timeout 600 python bench.py --steps 4 --warmup 3 > gpurun_out/bench15.json 2> gpurun_out/bench15.err; python - <<'PY'
+import json
+try:
+    r=json.load(open('gpurun_out/bench15.json'))
+    print({k:r[k] for k in ('value','ms_per_step')}, r['config']['timed_iterations'], r['config']['nucleus_size'])
+    print(r['roofline']['all']); print(r['roofline']['phase_us_per_iteration'], r['roofline']['refactor_ms_total'])
+    print(r['e2e']['value'], r['cpu_baseline']['value'])
+except Exception as e: print('bench parse fail', e)
+PY
+tail -3 gpurun_out/bench15.err

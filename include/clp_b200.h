@@ -44,9 +44,18 @@ void Clpb_getProblem(Clpb_Simplex *model, int *start, int *index, double *value,
    Clp_setMaximumIterations :199, Clp_setMaximumSeconds :202, Clp_setLogLevel :314,
    ClpFactorization::maximumPivots (src/ClpFactorization.hpp:149).  Keys: "primalTolerance",
    "dualTolerance", "dualBound", "maximumIterations", "maximumSeconds", "logLevel",
-   "factorizationFrequency", "batch" (iterations enqueued per host sync), "timing" (0/1: per-phase
+   "factorizationFrequency", "scaling", "batch" (iterations enqueued per host sync), "timing" (0/1: per-phase
    CUDA events, no graph replay), "useGraph" (0/1), "warmupIterations", "objectiveOffset". */
 int Clpb_setParameter(Clpb_Simplex *model, const char *key, double value);
+/* Clp_scaling :268 (ClpModel::scaling(int mode), src/ClpModel.hpp): 0 off (default here; the
+   benchmark configuration is unscaled), 1 equilibrium, 2 geometric, 3 automatic (Clp's default),
+   4 automatic-dynamic (treated as 3).  The same value can be set with the key "scaling".
+   Clpb_scaleFactors runs ClpPackedMatrix::scale (src/ClpPackedMatrix.cpp:4120) on the host and
+   copies rowScale[m] / columnScale[n] out (all 1 and return value 1 when the matrix is not
+   worth scaling, :4262); dual() applies them to the matrix and the rim and returns the solution
+   in the caller's units. */
+void Clpb_scaling(Clpb_Simplex *model, int mode);
+int Clpb_scaleFactors(Clpb_Simplex *model, double *rowScale, double *columnScale);
 /* Clp_copyinStatus :280 : status[n+m], columns first */
 void Clpb_copyinStatus(Clpb_Simplex *model, const unsigned char *statusArray);
 /* Clp_dual :346 (ClpSimplex::dual src/ClpSimplex.cpp:5631).  Returns Clp_status :212:

@@ -271,6 +271,37 @@ def test_planted_random_lp(shape):
     assert abs(s.objectiveValue() - o.objective_value) <= 1e-8 * (1 + abs(o.objective_value))
 
 
+@pytest.mark.parametrize("mode", [1, 2, 3])
+@pytest.mark.parametrize("name", ["TSP-MTZ-40", "UFL-30x100", "modified_afiro", "staircase-480", "SetCover-50x200",
+                                  "NQueens-20", "hello"])
+def test_scaled_solve_matches_unscaled(name, mode):
+    """ClpModel::scaling(mode): the scaled problem is solved on the device, the answer comes back
+    in the caller's units: same optimum (CoinRelFltEq 1e-8 of the reference's tests), KKT audit
+    on the UNSCALED data."""
+    lp = load_golden(name)
+    s = engine(lp)
+    s.scaling(mode)
+    assert s.dual() == 0
+    assert abs(s.objectiveValue() - lp.known_objective) <= 1e-7 * (1 + abs(lp.known_objective))
+    ref = MANIFEST[name]["oracle_objective"]
+    assert abs(s.objectiveValue() - ref) <= 1e-7 * (1 + abs(ref))
+    assert kkt(lp, s) == 0
+    assert int((s.statusArray() == 1).sum()) == lp.m
+
+
+def test_scaled_planted_random_lp():
+    lp = G.random_sparse_lp(500, 5000, 0.01, 77)
+    lp.element = lp.element * np.repeat(10.0 ** np.random.default_rng(5).uniform(-3, 3, size=lp.n), np.diff(lp.col_start))
+    o = O.OracleSimplex(lp)
+    assert o.dual() == 0
+    for mode in (0, 3):
+        s = engine(lp)
+        s.scaling(mode)
+        assert s.dual() == 0, mode
+        assert abs(s.objectiveValue() - o.objective_value) <= 1e-7 * (1 + abs(o.objective_value))
+        assert kkt(lp, s) == 0
+
+
 def test_batch_size_does_not_change_result():
     lp = load_golden("TSP-MTZ-20")
     objs = []
