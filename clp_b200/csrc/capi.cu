@@ -148,6 +148,8 @@ int Clpb_setParameter(Clpb_Simplex *model, const char *key, double value)
     e.objectiveOffset = value;
   else if (k == "scaling")
     e.scalingFlag = (int)value;
+  else if (k == "perturbation")
+    e.perturbation = (int)value;
   else
     return -1;
   return 0;

@@ -332,6 +332,184 @@ void Engine::prepareWorkingProblem()
   }
 }
 
+// Dual (cost) perturbation before the first iteration, restating ClpSimplexDual::perturb
+// (src/ClpSimplexDual.cpp:6533-6964) for the default setting perturbation_ = 50 / 100: every
+// nonbasic, non-fixed column gets a cost change of the sign that keeps its reduced cost on the
+// feasible side, of a size that grows with the column length (weight[] table :6790) and is kept
+// inside [smallestAllowed, largestAllowed] (:6800-6803, :6862-6874).  Row costs are not modified
+// (:6754).  The random factors come from a fixed splitmix64 stream instead of CoinThreadRandom
+// (CoinUtils, not in the reference tree), so the individual perturbations are not the reference's;
+// the optimum is: the perturbed costs are handled like cost shifts -- removed at the first
+// "optimal" basis, after which the dual simplex continues on the true costs (engine.cu dual(),
+// the branch the reference takes through statusOfProblemInDual :5415ff).
+int Engine::perturbCosts(std::vector<double> &cost) const
+{
+  const double dualTol = dualTolerance;
+  const double largeValue = 1.0e15; // ClpSimplex::largeValue_
+  double perturbationSize = 1.0e-20;
+  double maximumFraction = 1.0e-5;
+  const double constantPerturbation = 100.0 * dualTol;
+  int maxLength = 0, minLength = m;
+  double averageCost = 0.0;
+  int numberNonZero = 0;
+  {
+    std::vector<double> sort(n);
+    for (int j = 0; j < n; j++) {
+      const double v = std::fabs(hCost[j]); // objective BEFORE scaling
+      sort[j] = v;
+      averageCost += v;
+      if (v != 0.0)
+        numberNonZero++;
+    }
+    averageCost = numberNonZero ? averageCost / numberNonZero : 1.0;
+    std::sort(sort.begin(), sort.end());
+    int number = n > 0 ? 1 : 0;
+    for (int j = 1; j < n; j++)
+      if (sort[j] != sort[j - 1])
+        number++;
+    if (!numberNonZero && perturbation < 55)
+      return 1; // the reference says "safer to use primal"
+    if (perturbation >= 100 && number * 4 > n)
+      return 1; // good enough: many distinct costs
+  }
+  for (int j = 0; j < n; j++)
+    if (wLower[j] < wUpper[j]) {
+      const int length = hColStart[j + 1] - hColStart[j];
+      if (length > 2) {
+        maxLength = std::max(maxLength, length);
+        minLength = std::min(minLength, length);
+      }
+    }
+  double smallestNonZero = 1.0e100;
+  {
+    perturbationSize = 1.0e-8;
+    bool allSame = true;
+    double lastValue = 0.0, lastValue2 = 0.0;
+    auto track = [&](double b, double &last) {
+      b = std::fabs(b);
+      if (last == 0.0)
+        last = b;
+      else if (std::fabs(b - last) > 1.0e-7)
+        allSame = false;
+    };
+    for (int i = 0; i < m; i++) {
+      const double lo = wLower[n + i], up = wUpper[n + i];
+      if (lo != 0.0 && lo > -1.0e10)
+        track(lo, lastValue);
+      if (up != 0.0 && up < 1.0e10)
+        track(up, lastValue);
+    }
+    for (int j = 0; j < n; j++) {
+      const double lo = wLower[j], up = wUpper[j];
+      if (lo < up) {
+        const double v = std::fabs(cost[j]);
+        perturbationSize = std::max(perturbationSize, v);
+        if (v != 0.0)
+          smallestNonZero = std::min(smallestNonZero, v);
+      }
+      if (lo != 0.0 && lo > -1.0e10)
+        track(lo, lastValue2);
+      if (up != 0.0 && up < 1.0e10)
+        track(up, lastValue2);
+    }
+    if (allSame) {
+      // all bounds alike: if the matrix entries are alike too, "really hit perturbation" (:6703)
+      double sn = 0.0, ln = 0.0, sp = 0.0, lp = 0.0;
+      bool first = true, firstP = true;
+      for (size_t e = 0; e < wVal.size(); e++) {
+        const double v = wVal[e];
+        if (v < 0.0) {
+          sn = first ? v : std::max(sn, v);
+          ln = first ? v : std::min(ln, v);
+          first = false;
+        } else if (v > 0.0) {
+          sp = firstP ? v : std::min(sp, v);
+          lp = firstP ? v : std::max(lp, v);
+          firstP = false;
+        }
+      }
+      if (sn == ln && sp == lp) {
+        const double adjust = std::min(100.0 * maximumFraction, 1.0e-3 * std::max(lastValue, lastValue2));
+        maximumFraction = std::max(adjust, maximumFraction);
+      }
+    }
+    perturbationSize = std::min(perturbationSize, smallestNonZero / maximumFraction);
+  }
+  const double weight[] = {1.0e-4, 1.0e-2, 5.0e-1, 1.0, 2.0, 5.0, 10.0, 20.0, 30.0, 40.0, 100.0};
+  const double factor = maxLength ? 3.0 / (double)minLength : 1.0;
+  const double m1 = 0.5;
+  const double smallestAllowed = std::min(1.0e-2 * dualTol, maximumFraction);
+  const double largestAllowed = std::max(1.0e3 * dualTol, maximumFraction * averageCost);
+  unsigned long long rngState = 0x9E3779B97F4A7C15ull;
+  auto rnd = [&]() { // splitmix64 -> [0,1)
+    unsigned long long z = (rngState += 0x9E3779B97F4A7C15ull);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    return (double)(z >> 11) * (1.0 / 9007199254740992.0);
+  };
+  double largestZero = 0.0, largest = 0.0;
+  for (int j = 0; j < n; j++) {
+    const double r1 = rnd(), r2 = rnd(); // perturbationArray_[2j], [2j+1]
+    if (!(wLower[j] < wUpper[j]) || hStatus[j] == basic)
+      continue;
+    double value = perturbationSize;
+    const double currentValue = cost[j];
+    value = std::min(value, constantPerturbation +
+                                maximumFraction * (std::fabs(currentValue) + 1.0e-1 * perturbationSize + 1.0e-8));
+    double value2 = constantPerturbation + 1.0e-1 * smallestNonZero;
+    if (wLower[j] > -largeValue) {
+      if (std::fabs(wLower[j]) < std::fabs(wUpper[j])) {
+        value *= (1.0 - m1 + m1 * r1);
+        value2 *= (1.0 - m1 + m1 * r2);
+      } else {
+        value = 0.0;
+      }
+    } else if (wUpper[j] < largeValue) {
+      value *= -(1.0 - m1 + m1 * r1);
+      value2 *= -(1.0 - m1 + m1 * r2);
+    } else {
+      value = 0.0;
+    }
+    if (value == 0.0)
+      continue;
+    int length = hColStart[j + 1] - hColStart[j];
+    if (length > 3) {
+      length = (int)((double)length * factor);
+      length = std::max(3, length);
+    }
+    value *= length < 10 ? weight[length] : weight[10];
+    value = std::min(value, value2);
+    if (std::fabs(value) <= smallestAllowed) { // get in range
+      value *= 10.0;
+      while (std::fabs(value) <= smallestAllowed)
+        value *= 10.0;
+    } else if (std::fabs(value) > largestAllowed) {
+      value *= 0.1;
+      while (std::fabs(value) > largestAllowed)
+        value *= 0.1;
+    }
+    if (currentValue != 0.0)
+      largest = std::max(largest, std::fabs(value));
+    else
+      largestZero = std::max(largestZero, std::fabs(value));
+    if (hStatus[j] == atUpperBound)
+      value = -value; // but negative if at ub
+    cost[j] += value;
+  }
+  if (largestZero > largest && largest != 0.0) {
+    const double test = std::max(1.0e-8, largest);
+    for (int j = 0; j < n; j++)
+      if (hCost[j] == 0.0) {
+        double c = cost[j];
+        while (std::fabs(c) > test)
+          c *= 0.5;
+        cost[j] = c;
+      }
+  }
+  return 0;
+}
+
 int Engine::setupDevice()
 {
   if (deviceReady)
@@ -965,6 +1143,21 @@ int Engine::startup()
 {
   setupDevice();
   resetStateForRun();
+  largestPerturbation = 0.0;
+  if (perturbation <= 100) {
+    // perturbed costs go to d.cost (d.costTrue keeps the true ones); costShifts > 0 makes the
+    // optimality branch of dual() restore them and carry on
+    std::vector<double> pc(wCost.begin(), wCost.begin() + n);
+    if (perturbCosts(pc) == 0) {
+      for (int j = 0; j < n; j++)
+        largestPerturbation = std::max(largestPerturbation, std::fabs(pc[j] - wCost[j]));
+      if (largestPerturbation > 0.0) {
+        CUDA_OK(cudaMemcpy(d.cost, pc.data(), sizeof(double) * n, cudaMemcpyHostToDevice));
+        const int one = 1;
+        CUDA_OK(cudaMemcpy(&d.st->costShifts, &one, sizeof(int), cudaMemcpyHostToDevice));
+      }
+    }
+  }
   return refresh();
 }
 

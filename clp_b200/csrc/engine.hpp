@@ -52,6 +52,12 @@ public:
   int scalingFlag = 0;
   std::vector<double> rowScale, columnScale; // empty: the problem is solved unscaled
   int computeScaling();                      // ClpPackedMatrix::scale (src/ClpPackedMatrix.cpp:4120)
+  // ClpSimplex::setPerturbation (src/ClpSimplex.hpp): 50 perturb the costs before the first
+  // iteration, 100 only if few distinct cost values (Clp's default), 102 never (default here: the
+  // benchmark configuration states "perturbation off").  ClpSimplexDual::perturb, :6533.
+  int perturbation = 102;
+  int perturbCosts(std::vector<double> &cost) const; // 0 = perturbed (cost[n] modified in place)
+  double largestPerturbation = 0.0;
   // column sharding of the pricing pass (multi-GPU): this rank prices [colBegin,colEnd)
   int rank = 0, worldSize = 1;
   void *ncclComm = nullptr; // ncclComm_t when worldSize > 1

@@ -12,6 +12,9 @@
 // Everything is fp64 FMA; the matrix is column major with leading dimension ld.
 #include "engine.cuh"
 
+#include <cstdlib>
+#include <dlfcn.h>
+
 namespace clpb {
 
 constexpr int NB = 32;
@@ -323,87 +326,116 @@ __global__ void __launch_bounds__(128)
       col[i] = x[i];
 }
 
-// C[M x N] -= A[M x K] * B[K x N]  (column major, fp64 FMA).  128x128 tile per CTA, 256 threads as
-// 16 x 16, 8x8 register tile per thread (rows tx + 16a, columns ty + 16b), K in chunks of 16 staged
-// through shared memory with the next chunk prefetched into registers.  The reference's dense tail
-// uses an 8x8-blocked CoinAbcDgemm the same way (src/CoinAbcHelperFunctions.cpp:1658).
-constexpr int GT = 128, GK = 16;
+// C[M x N] -= A[M x K] * B[K x N]  (column major).  64x64 tile per CTA, 4x4 per thread.
 __global__ void __launch_bounds__(256)
     gemm_sub_kernel(double *__restrict__ C, int ldc, const double *__restrict__ A, int lda,
                     const double *__restrict__ B, int ldb, int M, int N, int K)
 {
-  __shared__ double As[GK][GT + 1];
-  __shared__ double Bs[GK][GT + 1];
+  __shared__ double As[16][64 + 1];
+  __shared__ double Bs[16][64 + 1];
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-  const int m0 = blockIdx.x * GT, n0 = blockIdx.y * GT;
-  double acc[8][8];
+  const int m0 = blockIdx.x * 64, n0 = blockIdx.y * 64;
+  double acc[4][4];
 #pragma unroll
-  for (int a = 0; a < 8; a++)
+  for (int a = 0; a < 4; a++)
 #pragma unroll
-    for (int b = 0; b < 8; b++)
+    for (int b = 0; b < 4; b++)
       acc[a][b] = 0.0;
-  // this thread's share of a chunk: 8 elements of the A tile, 8 of the B tile
-  double pa[8], pb[8];
-  auto fetch = [&](int k0) {
-#pragma unroll
-    for (int q = 0; q < 8; q++) {
-      const int e = threadIdx.x + 256 * q;
-      const int i = e & (GT - 1), l = e >> 7; // A tile: 128 rows x 16 k
-      const int gi = m0 + i, gl = k0 + l;
-      pa[q] = (gi < M && gl < K) ? A[(size_t)gl * lda + gi] : 0.0;
-      const int lb = e & (GK - 1), jn = e >> 4; // B tile: 16 k x 128 columns
-      const int glb = k0 + lb, gj = n0 + jn;
-      pb[q] = (glb < K && gj < N) ? B[(size_t)gj * ldb + glb] : 0.0;
+  for (int k0 = 0; k0 < K; k0 += 16) {
+    // A tile: 64 rows x 16 cols ; B tile: 16 rows x 64 cols
+    for (int e = threadIdx.x; e < 64 * 16; e += 256) {
+      int i = e & 63, l = e >> 6;
+      int gi = m0 + i, gl = k0 + l;
+      As[l][i] = (gi < M && gl < K) ? A[(size_t)gl * lda + gi] : 0.0;
     }
-  };
-  fetch(0);
-  for (int k0 = 0; k0 < K; k0 += GK) {
-#pragma unroll
-    for (int q = 0; q < 8; q++) {
-      const int e = threadIdx.x + 256 * q;
-      As[e >> 7][e & (GT - 1)] = pa[q];
-      Bs[e & (GK - 1)][e >> 4] = pb[q];
+    for (int e = threadIdx.x; e < 64 * 16; e += 256) {
+      int l = e & 15, jn = e >> 4;
+      int gl = k0 + l, gj = n0 + jn;
+      Bs[l][jn] = (gl < K && gj < N) ? B[(size_t)gj * ldb + gl] : 0.0;
     }
     __syncthreads();
-    if (k0 + GK < K)
-      fetch(k0 + GK);
 #pragma unroll
-    for (int l = 0; l < GK; l++) {
-      double av[8], bv[8];
+    for (int l = 0; l < 16; l++) {
+      double av[4], bv[4];
 #pragma unroll
-      for (int a = 0; a < 8; a++)
+      for (int a = 0; a < 4; a++)
         av[a] = As[l][tx + 16 * a];
 #pragma unroll
-      for (int b = 0; b < 8; b++)
+      for (int b = 0; b < 4; b++)
         bv[b] = Bs[l][ty + 16 * b];
 #pragma unroll
-      for (int a = 0; a < 8; a++)
+      for (int a = 0; a < 4; a++)
 #pragma unroll
-        for (int b = 0; b < 8; b++)
+        for (int b = 0; b < 4; b++)
           acc[a][b] = fma(av[a], bv[b], acc[a][b]);
     }
     __syncthreads();
   }
 #pragma unroll
-  for (int b = 0; b < 8; b++) {
-    const int gj = n0 + ty + 16 * b;
+  for (int b = 0; b < 4; b++) {
+    int gj = n0 + ty + 16 * b;
     if (gj >= N)
       continue;
 #pragma unroll
-    for (int a = 0; a < 8; a++) {
-      const int gi = m0 + tx + 16 * a;
+    for (int a = 0; a < 4; a++) {
+      int gi = m0 + tx + 16 * a;
       if (gi < M)
         C[(size_t)gj * ldc + gi] -= acc[a][b];
     }
   }
 }
 
+// cuBLAS (through dlopen, like NCCL in capi.cu: no link-time dependency) for the plain DGEMMs of
+// the refactorization -- the rank-32 trailing updates of the LU and the rank-128 updates of the
+// blocked inverse are ordinary C -= A*B with no fusion opportunity.  Falls back to gemm_sub_kernel
+// when the library cannot be loaded.
+namespace {
+typedef void *cublasHandle_t_;
+typedef int (*cublasCreate_t)(cublasHandle_t_ *);
+typedef int (*cublasSetStream_t)(cublasHandle_t_, cudaStream_t);
+typedef int (*cublasDgemm_t)(cublasHandle_t_, int, int, int, int, int, const double *, const double *, int,
+                             const double *, int, const double *, double *, int);
+cublasHandle_t_ g_blas = nullptr;
+cublasSetStream_t p_setStream = nullptr;
+cublasDgemm_t p_dgemm = nullptr;
+int g_blasState = 0; // 0 untried, 1 ready, -1 unavailable
+bool blas_ready()
+{
+  if (g_blasState != 0)
+    return g_blasState > 0;
+  g_blasState = -1;
+  if (getenv("CLPB_NO_CUBLAS"))
+    return false;
+  const char *names[] = {"libcublas.so.12", "/usr/local/cuda/lib64/libcublas.so.12", "libcublas.so", nullptr};
+  void *h = nullptr;
+  for (int i = 0; names[i] && !h; i++)
+    h = dlopen(names[i], RTLD_NOW | RTLD_GLOBAL);
+  if (!h)
+    return false;
+  cublasCreate_t p_create = (cublasCreate_t)dlsym(h, "cublasCreate_v2");
+  p_setStream = (cublasSetStream_t)dlsym(h, "cublasSetStream_v2");
+  p_dgemm = (cublasDgemm_t)dlsym(h, "cublasDgemm_v2");
+  if (!p_create || !p_setStream || !p_dgemm)
+    return false;
+  if (p_create(&g_blas) != 0 || !g_blas)
+    return false;
+  g_blasState = 1;
+  return true;
+}
+} // namespace
+
 static void gemm_sub(double *C, int ldc, const double *A, int lda, const double *B, int ldb, int M,
                      int N, int K, cudaStream_t s)
 {
   if (M <= 0 || N <= 0 || K <= 0)
     return;
-  dim3 grid((M + GT - 1) / GT, (N + GT - 1) / GT);
+  if ((long)M * N >= 256L * 256L && blas_ready()) {
+    const double minusOne = -1.0, one = 1.0;
+    p_setStream(g_blas, s);
+    if (p_dgemm(g_blas, 0 /* N */, 0 /* N */, M, N, K, &minusOne, A, lda, B, ldb, &one, C, ldc) == 0)
+      return;
+  }
+  dim3 grid((M + 63) / 64, (N + 63) / 64);
   gemm_sub_kernel<<<grid, 256, 0, s>>>(C, ldc, A, lda, B, ldb, M, N, K);
 }
 

@@ -108,6 +108,11 @@ __device__ __forceinline__ int ratio_bucket(double r)
 {
   return (int)((unsigned long long)__double_as_longlong(r) >> 48) & (kHistBuckets - 1);
 }
+// Storage slot of level-1 bucket b.  The candidates of one iteration fall into a few hundred
+// CONSECUTIVE buckets (ratios within ~20 octaves); stored consecutively those are ~20 cache lines,
+// i.e. ~20 L2 slices serialising tens of thousands of atomics.  Consecutive buckets are therefore
+// stored 128 bytes apart (bijection on 15 bits; slot 0 = bucket 0).
+__device__ __forceinline__ int hist1_slot(int b) { return ((b & 2047) << 4) | (b >> 11); }
 
 // Ratio-test candidate test for nonbasic variable j with tableau entry alpha.
 // Returns false if j cannot bound the dual step.  abar = sigma*alpha.
@@ -178,6 +183,17 @@ __device__ __forceinline__ void hist_add_aggregated(unsigned long long *hist, in
     else
       atomicAdd(hist + bucket, sum);
   }
+}
+// warp-aggregated atomicMax of an int per bucket (all 32 lanes call it; valid lanes take part)
+__device__ __forceinline__ void max_aggregated(int *arr, int bucket, int value, bool valid)
+{
+  const unsigned act = __ballot_sync(0xffffffffu, valid);
+  if (!valid)
+    return;
+  const unsigned peers = __match_any_sync(act, bucket);
+  const int mx = __reduce_max_sync(peers, value);
+  if ((int)(threadIdx.x & 31) == __ffs(peers) - 1)
+    atomicMax(arr + bucket, mx);
 }
 // same for atomicMin of 64-bit keys (called by the lanes with valid == true of the call above)
 __device__ __forceinline__ void hist_min_aggregated(unsigned long long *hist, int bucket,

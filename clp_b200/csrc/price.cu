@@ -23,7 +23,7 @@ namespace clpb {
 __device__ __forceinline__ void histogram_add(const DeviceModel &d, double a, double dtil,
                                               bool boxed, double range, double infeas)
 {
-  atomicAdd(d.histWeight + ratio_bucket(dtil / a), slope_weight(a, boxed, range, infeas));
+  atomicAdd(d.histWeight + hist1_slot(ratio_bucket(dtil / a)), slope_weight(a, boxed, range, infeas));
 }
 
 // alphaRow[j] = rho^T a_j for nonbasic, non-fixed columns j in [colBegin,colEnd) + histogram.
@@ -276,7 +276,7 @@ __global__ void __launch_bounds__(256) row_finalize_kernel(DeviceModel d, int co
       cand = fuseHist && alpha != 0.0 && candidate(d, j, alpha, sigma, a, dtil, boxed, range);
     }
     if (fuseHist)
-      hist_add_aggregated(d.histWeight, cand ? ratio_bucket(dtil / a) : 0,
+      hist_add_aggregated(d.histWeight, cand ? hist1_slot(ratio_bucket(dtil / a)) : 0,
                           cand ? slope_weight(a, boxed, range, infeas) : 0ull, cand, &sHot);
   }
   __syncthreads();
@@ -324,7 +324,7 @@ __global__ void __launch_bounds__(256) histogram_kernel(DeviceModel d)
       const double alpha = d.alphaRow[j];
       cand = alpha != 0.0 && candidate(d, j, alpha, sigma, a, dtil, boxed, range);
     }
-    hist_add_aggregated(d.histWeight, cand ? ratio_bucket(dtil / a) : 0,
+    hist_add_aggregated(d.histWeight, cand ? hist1_slot(ratio_bucket(dtil / a)) : 0,
                         cand ? slope_weight(a, boxed, range, infeas) : 0ull, cand);
   }
 }
@@ -418,7 +418,7 @@ __global__ void __launch_bounds__(1024) chuzc_scan1_kernel(DeviceModel d)
   const int nseg = gridDim.x; // kHistBuckets / 1024
   {
     const int b = blockIdx.x * 1024 + tid;
-    unsigned long long w = d.histWeight[b];
+    unsigned long long w = d.histWeight[hist1_slot(b)];
     int last = w != 0ull ? b : -1;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -485,7 +485,7 @@ __global__ void __launch_bounds__(1024) chuzc_scan1_kernel(DeviceModel d)
   }
   // ---- scan inside the crossing segment
   const int b = sSeg * 1024 + tid;
-  const unsigned long long w = d.histWeight[b];
+  const unsigned long long w = d.histWeight[hist1_slot(b)];
   unsigned long long inc = w;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {

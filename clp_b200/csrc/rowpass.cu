@@ -11,13 +11,11 @@
 // of the row and keeps (alpha, |alpha|, d~, range, flags) in registers across the phases, so the
 // row is read from memory once.  Phases are separated by grid barriers (~1-2 us each) instead of
 // kernel boundaries; the small scans are done redundantly by every CTA, which saves a barrier.
-//   P0 finalize row + level-1 ratio histogram      | barrier
-//   P1 segment totals (32 CTAs)                    | barrier
-//      crossing bucket (every CTA)  P2 level-2 histogram of that bucket | barrier
+//   P0 finalize row + level-1 ratio histogram + per-segment totals      | barrier
+//   P1 crossing bucket (every CTA)  P2 level-2 histogram of that bucket | barrier
 //   P3 theta* (every CTA)           P4 Harris bound (atomicMin)         | barrier
 //   P5 largest |alpha| in [theta*, harris] (atomicMax)                  | barrier
-//   P6 decode winner, dual update + bound flips (bit mask)              | barrier
-//   P7 ordered flip list + fixed-point scale (CTA 0)                    | barrier
+//   P6 decode winner, dual update + bound flips (unordered list)        | barrier
 //   P8 flip columns -> fixed-point accumulator; entering column -> aqBuf| barrier
 //   P9 three FTRAN right-hand sides rhs3 and their nucleus gather xg
 // All reductions are order independent (integer atomics, min/max of packed keys) or done in a
@@ -40,8 +38,8 @@ __device__ __forceinline__ void grid_barrier(unsigned int *bar)
       __threadfence();
       atomicAdd(bar + 1, 1u);
     } else {
-      while (*gen == g)
-        __nanosleep(32);
+      while (*gen == g) {
+      }
     }
     __threadfence();
   }
@@ -93,8 +91,8 @@ __global__ void __launch_bounds__(1024, 1) row_pass_kernel(DeviceModel d)
   __shared__ double sF64[32];
   __shared__ int sSeg, sLastAll, sBucket1, sCross;
   __shared__ unsigned long long sPrefix;
-  __shared__ int warpCount[32];
-  __shared__ int sBase;
+  __shared__ unsigned long long sSegTot[kHistBuckets / 1024];
+  __shared__ int sSegLast[kHistBuckets / 1024];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int gtid = blockIdx.x * 1024 + tid, gthreads = gridDim.x * 1024;
   const int sigma = st->sigma;
@@ -106,6 +104,10 @@ __global__ void __launch_bounds__(1024, 1) row_pass_kernel(DeviceModel d)
   }
   if (tid == 0)
     sHot = 0ull;
+  if (tid < kHistBuckets / 1024) {
+    sSegTot[tid] = 0ull;
+    sSegLast[tid] = -1;
+  }
   __syncthreads();
 
   // ---------------------------------------------------------------- P0 finalize + histogram
@@ -136,62 +138,48 @@ __global__ void __launch_bounds__(1024, 1) row_pass_kernel(DeviceModel d)
       if (cand)
         flags[e] |= F_CAND | (boxed ? F_BOXED : 0u);
     }
-    hist_add_aggregated(d.histWeight, cand ? ratio_bucket(dtil[e] / aabs[e]) : 0,
-                        cand ? slope_weight(aabs[e], boxed, range[e], infeas) : 0ull, cand, &sHot);
+    const int bkt = cand ? ratio_bucket(dtil[e] / aabs[e]) : 0;
+    const unsigned long long w = cand ? slope_weight(aabs[e], boxed, range[e], infeas) : 0ull;
+    hist_add_aggregated(d.histWeight, hist1_slot(bkt), w, cand, &sHot);
+    // per-segment totals / last non-empty bucket of this CTA (warp-aggregated shared-memory atomics)
+    hist_add_aggregated(sSegTot, bkt >> 10, w, cand);
+    max_aggregated(sSegLast, bkt >> 10, bkt, cand);
   }
   __syncthreads();
   if (tid == 0 && sHot != 0ull)
     atomicAdd(d.histWeight, sHot);
-  grid_barrier(d.gridBar);
-
-  // ---------------------------------------------------------------- P1a segment totals
-  constexpr int NSEG = kHistBuckets / 1024;
-  if ((int)blockIdx.x < NSEG) {
-    const int b = blockIdx.x * 1024 + tid;
-    unsigned long long w = __ldcg(d.histWeight + b);
-    int last = w != 0ull ? b : -1;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      w += __shfl_xor_sync(0xffffffffu, w, o);
-      last = max(last, __shfl_xor_sync(0xffffffffu, last, o));
-    }
-    if (lane == 0) {
-      sU64[warp] = w;
-      sI32[warp] = last;
-    }
-    __syncthreads();
-    if (tid == 0) {
-      unsigned long long t = 0;
-      int l = -1;
-      for (int q = 0; q < 32; q++) {
-        t += sU64[q];
-        l = max(l, sI32[q]);
-      }
-      d.segTotal[blockIdx.x] = t;
-      d.segLast[blockIdx.x] = l;
-    }
+  if (tid < kHistBuckets / 1024 && sSegLast[tid] >= 0) {
+    atomicAdd(d.segTotal + tid, sSegTot[tid]);
+    atomicMax(d.segLast + tid, sSegLast[tid]);
   }
   grid_barrier(d.gridBar);
 
-  // ---------------------------------------------------------------- P1b crossing bucket (every CTA)
-  if (tid == 0) {
-    unsigned long long c = 0;
-    int seg = -1, lastAll = -1;
-    unsigned long long pre = 0;
-    for (int q = 0; q < NSEG; q++) {
-      const unsigned long long t = __ldcg(d.segTotal + q);
-      if (seg < 0 && c + t >= kFixOne) {
-        seg = q;
-        pre = c;
-      }
-      c += t;
-      lastAll = max(lastAll, __ldcg(d.segLast + q));
+  // ---------------------------------------------------------------- P1 crossing bucket (every CTA)
+  constexpr int NSEG = kHistBuckets / 1024; // 32: one lane per segment
+  if (warp == 0) {
+    const unsigned long long t = __ldcg(d.segTotal + lane);
+    int lastAll = __ldcg(d.segLast + lane);
+    unsigned long long inc = t;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      unsigned long long u = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o)
+        inc += u;
     }
-    sSeg = seg;
-    sLastAll = lastAll;
-    sPrefix = pre;
-    sBucket1 = -1;
-    sResidual = 0xFFFFFFFFFFFFFFFFull;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+      lastAll = max(lastAll, __shfl_xor_sync(0xffffffffu, lastAll, o));
+    const unsigned long long excl = inc - t;
+    const bool cross = excl < kFixOne && inc >= kFixOne; // first segment where the total reaches 1
+    const unsigned cm = __ballot_sync(0xffffffffu, cross);
+    if (lane == 0) {
+      sSeg = cm ? __ffs(cm) - 1 : -1;
+      sLastAll = lastAll;
+      sBucket1 = -1;
+      sResidual = 0xFFFFFFFFFFFFFFFFull;
+    }
+    if (cross)
+      sPrefix = excl;
   }
   __syncthreads();
   if (sLastAll < 0) { // no candidate at all
@@ -208,7 +196,7 @@ __global__ void __launch_bounds__(1024, 1) row_pass_kernel(DeviceModel d)
     __syncthreads();
   } else {
     const int b = sSeg * 1024 + tid;
-    const unsigned long long w = __ldcg(d.histWeight + b);
+    const unsigned long long w = __ldcg(d.histWeight + hist1_slot(b));
     unsigned long long inc = w;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -416,7 +404,7 @@ __global__ void __launch_bounds__(1024, 1) row_pass_kernel(DeviceModel d)
             d.status[j] = atLowerBound;
             d.sol[j] = lo;
           }
-          atomicOr(d.flipBits + (j >> 5), 1u << (j & 31));
+          d.flipList[atomicAdd(&st->numFlips, 1)] = j; // order is irrelevant: fixed-point sums
           maxRange = max(maxRange, (unsigned long long)__double_as_longlong(up - lo));
         } else {
           d.cost[j] -= dnew;
@@ -436,75 +424,20 @@ __global__ void __launch_bounds__(1024, 1) row_pass_kernel(DeviceModel d)
   }
   grid_barrier(d.gridBar);
 
-  // ---------------------------------------------------------------- P7 ordered flip list (CTA 0)
-  if (blockIdx.x == 0) {
-    const int nwords = (nm + 31) >> 5;
-    if (tid == 0)
-      sBase = 0;
-    __syncthreads();
-    for (int start = 0; start < nwords; start += 1024 * 4) {
-      unsigned int w[4];
-      int cnt = 0;
-#pragma unroll
-      for (int q = 0; q < 4; q++) {
-        const int wi = start + tid * 4 + q;
-        w[q] = wi < nwords ? __ldcg(d.flipBits + wi) : 0u;
-        cnt += __popc(w[q]);
-      }
-      int inc = cnt;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        int t = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= o)
-          inc += t;
-      }
-      if (lane == 31)
-        warpCount[warp] = inc;
-      __syncthreads();
-      int off = sBase + inc - cnt;
-      for (int q = 0; q < warp; q++)
-        off += warpCount[q];
-#pragma unroll
-      for (int q = 0; q < 4; q++) {
-        unsigned int bits = w[q];
-        const int j0 = (start + tid * 4 + q) << 5;
-        while (bits) {
-          const int b = __ffs(bits) - 1;
-          bits &= bits - 1;
-          d.flipList[off++] = j0 + b;
-        }
-      }
-      __syncthreads();
-      if (tid == 1023) {
-        int tot = 0;
-        for (int q = 0; q < 32; q++)
-          tot += warpCount[q];
-        sBase += tot;
-      }
-      __syncthreads();
-    }
-    if (tid == 0) {
-      const int nf = sBase;
-      st->numFlips = nf;
-      if (nf > 0) {
-        const unsigned long long mb = atomicMax(&st->flipMaxBits, 0ull);
-        const double bound = d.amax * __longlong_as_double((long long)mb);
-        int Ex = 0;
-        frexp(bound, &Ex);
-        const int bitsN = 32 - __clz(nf);
-        const int Q = 62 - bitsN;
-        st->flipScale = ldexp(1.0, Q - Ex);
-        st->flipInvScale = ldexp(1.0, Ex - Q);
-      }
-      st->flipMaxBits = 0ull;
-    }
-  }
-  grid_barrier(d.gridBar);
-
   // ---------------------------------------------------------------- P8 scatter flips + entering column
+  // every contribution |a_ij * delta_j| <= amax * maxRange < 2^Ex, at most nf < 2^bitsN of them per
+  // row: with Q = 62 - bitsN fractional bits the int64 sums cannot overflow (same in every CTA)
   const int nf = __ldcg(&st->numFlips);
+  double scale = 0.0, invScale = 0.0;
   if (nf > 0) {
-    const double scale = __ldcg(&st->flipScale);
+    const double bound = d.amax * __longlong_as_double((long long)__ldcg(&st->flipMaxBits));
+    int Ex = 0;
+    frexp(bound, &Ex);
+    const int Q = 62 - (32 - __clz(nf));
+    scale = ldexp(1.0, Q - Ex);
+    invScale = ldexp(1.0, Ex - Q);
+  }
+  if (nf > 0) {
     unsigned long long *acc = reinterpret_cast<unsigned long long *>(d.flipAcc);
     const int gw = gtid >> 5, GW = gthreads >> 5;
     for (int f = gw; f < nf; f += GW) {
@@ -530,7 +463,9 @@ __global__ void __launch_bounds__(1024, 1) row_pass_kernel(DeviceModel d)
 
   // ---------------------------------------------------------------- P9 rhs3 and its nucleus gather
   {
-    const double inv = nf > 0 ? __ldcg(&st->flipInvScale) : 0.0;
+    const double inv = invScale;
+    if (gtid == 0)
+      st->flipMaxBits = 0ull; // every CTA read it before the last barrier
     const int ldk = d.fd->ldk, k = d.fd->k;
     const int maxk8 = (d.m + 7) / 8 * 8;
     double *xg = d.ywork + (size_t)3 * maxk8;

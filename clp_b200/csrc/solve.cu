@@ -233,10 +233,9 @@ __global__ void __launch_bounds__(256) pfi_mu_kernel(DeviceModel d, bool checkSt
   }
 }
 
-// x_c[p] -= sum_{i<t} W[p][i] * mu_c[i].  One warp per group of four positions: the four panel rows
-// are streamed together (eight 8-byte loads in flight per lane) and every mu value is reused four
-// times.  pivotTail: the last CTA then evaluates the accuracy gate and the primal step
-// (pivot_scalars_body) on the finished columns.
+// x_c[p] -= sum_{i<t} W[p][i] * mu_c[i]   (one warp per position, eight loads of the panel row in
+// flight per lane, 64 warps per SM).  pivotTail: the last CTA then evaluates the accuracy gate and
+// the primal step (pivot_scalars_body) on the finished columns.
 template <int NRHS>
 __global__ void __launch_bounds__(256) pfi_apply_kernel(DeviceModel d, double *__restrict__ x, int xstride,
                                                         bool checkState, bool pivotTail)
@@ -245,52 +244,34 @@ __global__ void __launch_bounds__(256) pfi_apply_kernel(DeviceModel d, double *_
     return;
   const int t = d.st->numEtas;
   if (t > 0) {
-    constexpr int R = 4;
     const int lane = threadIdx.x & 31;
     const int warpsPerBlock = blockDim.x >> 5;
-    const int ngroups = (d.m + R - 1) / R;
-    for (int g = blockIdx.x * warpsPerBlock + (threadIdx.x >> 5); g < ngroups; g += gridDim.x * warpsPerBlock) {
-      const int p0 = g * R;
-      const double *wrow[R];
+    for (int p = blockIdx.x * warpsPerBlock + (threadIdx.x >> 5); p < d.m;
+         p += gridDim.x * warpsPerBlock) {
+      const double *wrow = d.W + (size_t)p * d.tmax;
+      double acc[NRHS];
 #pragma unroll
-      for (int r = 0; r < R; r++)
-        wrow[r] = d.W + (size_t)min(p0 + r, d.m - 1) * d.tmax;
-      double acc[R][NRHS];
+      for (int c = 0; c < NRHS; c++)
+        acc[c] = 0.0;
+      for (int i = lane; i < t; i += 256) {
+        double w[8];
 #pragma unroll
-      for (int r = 0; r < R; r++)
+        for (int u = 0; u < 8; u++)
+          w[u] = (i + 32 * u < t) ? __ldcs(wrow + i + 32 * u) : 0.0;
 #pragma unroll
-        for (int c = 0; c < NRHS; c++)
-          acc[r][c] = 0.0;
-      for (int i = lane; i < t; i += 64) {
-        double w[2][R];
-#pragma unroll
-        for (int u = 0; u < 2; u++)
-#pragma unroll
-          for (int r = 0; r < R; r++)
-            w[u][r] = (i + 32 * u < t) ? __ldcs(wrow[r] + i + 32 * u) : 0.0;
-#pragma unroll
-        for (int u = 0; u < 2; u++) {
+        for (int u = 0; u < 8; u++) {
           const int ii = min(i + 32 * u, t - 1);
 #pragma unroll
-          for (int c = 0; c < NRHS; c++) {
-            const double muv = __ldg(d.mu + (size_t)c * d.tmax + ii);
-#pragma unroll
-            for (int r = 0; r < R; r++)
-              acc[r][c] = fma(w[u][r], muv, acc[r][c]);
-          }
+          for (int c = 0; c < NRHS; c++)
+            acc[c] = fma(w[u], __ldg(d.mu + (size_t)c * d.tmax + ii), acc[c]);
         }
       }
 #pragma unroll
-      for (int r = 0; r < R; r++)
-#pragma unroll
-        for (int c = 0; c < NRHS; c++)
-          acc[r][c] = warp_sum(acc[r][c]);
+      for (int c = 0; c < NRHS; c++)
+        acc[c] = warp_sum(acc[c]);
       if (lane == 0)
-#pragma unroll
-        for (int r = 0; r < R; r++)
-          if (p0 + r < d.m)
-            for (int c = 0; c < NRHS; c++)
-              x[(size_t)c * xstride + p0 + r] -= acc[r][c];
+        for (int c = 0; c < NRHS; c++)
+          x[(size_t)c * xstride + p] -= acc[c];
     }
   }
   if (!pivotTail)
@@ -323,7 +304,7 @@ static void ftran_impl(const DeviceModel &d, double *b, bool applyEtas, bool che
   ftran_spread_kernel<NRHS><<<(m * 8 + 255) / 256, 256, 0, s>>>(d, b, m, d.ywork, checkState, applyEtas);
   if (applyEtas) {
     pfi_mu_kernel<NRHS><<<d.tmax, 256, 0, s>>>(d, checkState);
-    int pblocks = ((m + 3) / 4 + 7) / 8;
+    int pblocks = (m + 7) / 8;
     if (pblocks > 148 * 8)
       pblocks = 148 * 8;
     pfi_apply_kernel<NRHS><<<pblocks, 256, 0, s>>>(d, b, m, checkState, pivotTail);

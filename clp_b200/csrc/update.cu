@@ -34,6 +34,10 @@ __global__ void chuzr_kernel(DeviceModel d)
   }
   for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < ((d.nm + 31) >> 5); w += gridDim.x * blockDim.x)
     d.flipBits[w] = 0u;
+  if (blockIdx.x == 0 && threadIdx.x < kHistBuckets / 1024) {
+    d.segTotal[threadIdx.x] = 0ull;
+    d.segLast[threadIdx.x] = -1;
+  }
   for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < d.m; p += gridDim.x * blockDim.x) {
     const int seq = d.pivotVariable[p];
     best = max(best, chuzr_key(d.sol[seq], d.lower[seq], d.upper[seq], d.weights[p], tol, p));
@@ -378,6 +382,10 @@ __global__ void __launch_bounds__(256) iteration_update_kernel(DeviceModel d, in
     }
     for (int w = gtid; w < ((d.nm + 31) >> 5); w += gthreads)
       d.flipBits[w] = 0u;
+    if (gtid < kHistBuckets / 1024) {
+      d.segTotal[gtid] = 0ull;
+      d.segLast[gtid] = -1;
+    }
     unsigned long long best = 0ull;
     const int p = gtid;
     if (p < d.m) {

@@ -117,6 +117,10 @@ class ClpSimplex:
     def setFactorizationFrequency(self, v): self._set("factorizationFrequency", v)
     def setParameter(self, key, v): self._set(key, v)
 
+    def setPerturbation(self, value):
+        """ClpSimplex::setPerturbation: 50 perturb costs, 100 automatic, 102 off (default here)."""
+        self._set("perturbation", value)
+
     def scaling(self, mode):
         """ClpModel::scaling(mode): 0 off, 1 equilibrium, 2 geometric, 3 automatic, 4 dynamic."""
         self._L.Clpb_scaling(self._h, int(mode))

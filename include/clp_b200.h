@@ -44,7 +44,8 @@ void Clpb_getProblem(Clpb_Simplex *model, int *start, int *index, double *value,
    Clp_setMaximumIterations :199, Clp_setMaximumSeconds :202, Clp_setLogLevel :314,
    ClpFactorization::maximumPivots (src/ClpFactorization.hpp:149).  Keys: "primalTolerance",
    "dualTolerance", "dualBound", "maximumIterations", "maximumSeconds", "logLevel",
-   "factorizationFrequency", "scaling", "batch" (iterations enqueued per host sync), "timing" (0/1: per-phase
+   "factorizationFrequency", "scaling", "perturbation" (Clp_setPerturbation :302: 50 on,
+   100 automatic, 102 off = default here; ClpSimplexDual::perturb src/ClpSimplexDual.cpp:6533), "batch" (iterations enqueued per host sync), "timing" (0/1: per-phase
    CUDA events, no graph replay), "useGraph" (0/1), "warmupIterations", "objectiveOffset". */
 int Clpb_setParameter(Clpb_Simplex *model, const char *key, double value);
 /* Clp_scaling :268 (ClpModel::scaling(int mode), src/ClpModel.hpp): 0 off (default here; the

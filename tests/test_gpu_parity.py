@@ -302,6 +302,26 @@ def test_scaled_planted_random_lp():
         assert kkt(lp, s) == 0
 
 
+@pytest.mark.parametrize("name", ["transport-10x200", "transport-20x500", "NQueens-50", "SetPart-40x200",
+                                  "UFL-30x100", "staircase-480", "Infeasible-50"])
+def test_perturbed_solve_reaches_the_true_optimum(name):
+    """ClpSimplex::setPerturbation(50): costs are perturbed before the first iteration
+    (ClpSimplexDual::perturb), removed at the first optimal basis, and the dual simplex finishes on
+    the true costs: same status, same optimum, KKT on the true data."""
+    lp = load_golden(name)
+    s = engine(lp)
+    s.setPerturbation(50)
+    st = s.dual()
+    assert st == lp.expect_status
+    if st == 0:
+        tol = 1e-4 if MANIFEST[name]["objective_source"] == "reference" else 1e-8
+        assert abs(s.objectiveValue() - lp.known_objective) <= tol * (1 + abs(lp.known_objective))
+        ref = MANIFEST[name]["oracle_objective"]
+        assert abs(s.objectiveValue() - ref) <= 1e-8 * (1 + abs(ref))
+        assert kkt(lp, s) == 0
+        assert int((s.statusArray() == 1).sum()) == lp.m
+
+
 def test_batch_size_does_not_change_result():
     lp = load_golden("TSP-MTZ-20")
     objs = []
