@@ -558,7 +558,7 @@ int Engine::setupDevice()
       while (c1 < ce && c1 - c < kPriceTileCols && ((hColStart[c1 + 1] + 3) & ~3) - ea <= kPriceTile)
         c1++;
       if (c1 == c)
-        ok = false; // a single column does not fit a tile: fall back to the warp-per-column kernel
+        ok = false; // a single column does not fit a tile: the LDG-direct kernel is used
       c = c1;
     }
     tiles.push_back(ce);
@@ -611,6 +611,8 @@ int Engine::setupDevice()
   d.nucCol = dalloc<int>(m);
   dS1RowStart = dalloc<int>(m + 1);
   d.s1RowStart = dS1RowStart;
+  dS1cStart = dalloc<int>(m + 1);
+  d.s1cStart = dS1cStart;
   // Clp's default frequency balances its sparse FT update against a sparse refactorization; here
   // an eta costs one extra 8m-byte panel column per solve while a refactorization costs O(k^3)
   // flops, so the default cycle is longer (the accuracy gate still forces early refactorizations)
@@ -842,22 +844,33 @@ int Engine::refactor()
       s1Start[i + 1] += s1Start[i];
     std::vector<int> s1Col(s1Start[m]);
     std::vector<double> s1Val(s1Start[m]);
+    // the same entries by nucleus column (this loop visits them in that order)
+    std::vector<int> s1cStart(k + 1, 0), s1cRow(s1Start[m]);
+    std::vector<double> s1cVal(s1Start[m]);
     {
       std::vector<int> fill(s1Start.begin(), s1Start.end() - 1);
-      for (int j = 0; j < k; j++)
+      int atc = 0;
+      for (int j = 0; j < k; j++) {
         for (int e = hColStart[nucCol[j]]; e < hColStart[nucCol[j] + 1]; e++) {
           int i = hRow[e];
           if (posToNuc[i] < 0) {
             int at = fill[i]++;
             s1Col[at] = j;
             s1Val[at] = wVal[e];
+            s1cRow[atc] = i;
+            s1cVal[atc] = wVal[e];
+            atc++;
           }
         }
+        s1cStart[j + 1] = atc;
+      }
     }
     if ((size_t)s1Start[m] > s1Cap) {
       s1Cap = (size_t)s1Start[m] * 3 / 2 + 1024;
       dS1Col = dalloc<int>(s1Cap);
       dS1Val = dalloc<double>(s1Cap);
+      dS1cRow = dalloc<int>(s1Cap);
+      dS1cVal = dalloc<double>(s1Cap);
     }
     d.s1Col = dS1Col;
     d.s1Val = dS1Val;
@@ -878,6 +891,8 @@ int Engine::refactor()
       hfd.NinvT = d.NinvT;
       hfd.s1Col = dS1Col;
       hfd.s1Val = dS1Val;
+      hfd.s1cRow = dS1cRow;
+      hfd.s1cVal = dS1cVal;
       CUDA_OK(cudaMemcpyAsync(d.fd, &hfd, sizeof(FactorDesc), cudaMemcpyHostToDevice, stream));
       CUDA_OK(cudaStreamSynchronize(stream)); // hfd is a stack object
     }
@@ -887,9 +902,12 @@ int Engine::refactor()
       CUDA_OK(cudaMemcpyAsync(d.nucCol, nucCol.data(), sizeof(int) * k, cudaMemcpyHostToDevice, stream));
     }
     CUDA_OK(cudaMemcpyAsync(dS1RowStart, s1Start.data(), sizeof(int) * (m + 1), cudaMemcpyHostToDevice, stream));
+    CUDA_OK(cudaMemcpyAsync(dS1cStart, s1cStart.data(), sizeof(int) * (k + 1), cudaMemcpyHostToDevice, stream));
     if (s1Start[m] > 0) {
       CUDA_OK(cudaMemcpyAsync(dS1Col, s1Col.data(), sizeof(int) * s1Start[m], cudaMemcpyHostToDevice, stream));
       CUDA_OK(cudaMemcpyAsync(dS1Val, s1Val.data(), sizeof(double) * s1Start[m], cudaMemcpyHostToDevice, stream));
+      CUDA_OK(cudaMemcpyAsync(dS1cRow, s1cRow.data(), sizeof(int) * s1Start[m], cudaMemcpyHostToDevice, stream));
+      CUDA_OK(cudaMemcpyAsync(dS1cVal, s1cVal.data(), sizeof(double) * s1Start[m], cudaMemcpyHostToDevice, stream));
     }
     int info = 0;
     if (k > 0) {

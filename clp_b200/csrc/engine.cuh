@@ -89,6 +89,8 @@ struct FactorDesc {
   const double *NinvT; // [k x ldk] row-major of the transpose (BTRAN  y = Ninv^T b)
   const int *s1Col;    // CSR of S1 = A[C rows, nucleus columns]: nucleus index
   const double *s1Val;
+  const int *s1cRow;   // the same S1 by nucleus column (CSC): position (= row) of each entry
+  const double *s1cVal;
 };
 
 // All device pointers of one model.  Plain struct passed by value to kernels.
@@ -121,6 +123,7 @@ struct DeviceModel {
   const int *s1RowStart; // CSR of S1 = A[C rows, nucleus columns], rows indexed by position
   const int *s1Col;      // nucleus index
   const double *s1Val;
+  const int *s1cStart;   // [k+1] S1 by nucleus column; entries in FactorDesc::s1cRow / s1cVal
   // product-form etas
   int tmax;           // capacity (row pitch of W, pitch of Ginv)
   double *W;          // [m x tmax] row-major, column i = W_i

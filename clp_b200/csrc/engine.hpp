@@ -41,7 +41,7 @@ public:
   int batch = 16;                 // iterations enqueued per host synchronisation
   bool timing = false;
   bool useGraph = true;
-  bool usePriceTma = true;        // TMA-staged price kernel (false: warp-per-column kernel)
+  bool usePriceTma = false;       // TMA-staged price kernel (default: LDG-direct kernel, 26% faster)
   bool useRowPass = true;         // cooperative row-pass kernel (false / column-sharded: separate kernels)
   int warmupIterations = 0;       // device-timed window starts once this many iterations ran
   double timedMilliseconds = 0.0; // CUDA-event time of the window (iterations + refactorizations)
@@ -123,6 +123,8 @@ private:
   int *dIpiv = nullptr, *dPerm = nullptr, *dInfo = nullptr;
   int *dS1RowStart = nullptr, *dS1Col = nullptr;
   double *dS1Val = nullptr;
+  int *dS1cStart = nullptr, *dS1cRow = nullptr;
+  double *dS1cVal = nullptr;
   size_t s1Cap = 0;
   size_t nucCap = 0; // capacity (elements) of Ninv / NinvT
   IterState *hState = nullptr; // pinned

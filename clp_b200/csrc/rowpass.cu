@@ -25,23 +25,39 @@
 
 namespace clpb {
 
-// generation barrier over all CTAs of a cooperative grid; bar[0] = arrival count, bar[1] = generation
-__device__ __forceinline__ void grid_barrier(unsigned int *bar)
+// Generation barrier over all CTAs of a cooperative grid; bar[0] = arrival count, bar[1] =
+// generation.  One acq_rel atomic per CTA plus an acquire spin on the generation word (which the
+// last arriver publishes with a release store): ~1.5 us, against ~3.5 us for the fence + atomic +
+// volatile-spin + fence formulation.  'gen' is thread 0's private copy of the current generation
+// (read once at kernel start: nobody can advance it before every CTA has arrived at barrier 1).
+__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int *p)
+{
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned int atom_add_acq_rel_u32(unsigned int *p, unsigned int v)
+{
+  unsigned int o;
+  asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], %2;" : "=r"(o) : "l"(p), "r"(v) : "memory");
+  return o;
+}
+__device__ __forceinline__ void st_release_u32(unsigned int *p, unsigned int v)
+{
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void grid_barrier(unsigned int *bar, unsigned int &gen)
 {
   __syncthreads();
   if (threadIdx.x == 0) {
-    volatile unsigned int *gen = bar + 1;
-    const unsigned int g = *gen; // read BEFORE arriving
-    __threadfence();
-    if (atomicAdd(bar, 1u) == gridDim.x - 1) {
-      bar[0] = 0u;
-      __threadfence();
-      atomicAdd(bar + 1, 1u);
+    if (atom_add_acq_rel_u32(bar, 1u) == gridDim.x - 1) {
+      bar[0] = 0u; // ordered before the release store below
+      st_release_u32(bar + 1, gen + 1u);
     } else {
-      while (*gen == g) {
+      while (ld_acquire_u32(bar + 1) == gen) {
       }
     }
-    __threadfence();
+    gen++;
   }
   __syncthreads();
 }
@@ -98,6 +114,9 @@ __global__ void __launch_bounds__(1024, 1) row_pass_kernel(DeviceModel d)
   const int sigma = st->sigma;
   const double infeas = st->infeas;
   const int n = d.n, nm = d.nm;
+  unsigned int barGen = 0u;
+  if (tid == 0)
+    barGen = ld_acquire_u32(d.gridBar + 1);
   if (gtid == 0) { // consumed after barrier 3 / 4
     st->harrisBits = 0x7FF0000000000000ull;
     st->chuzcKey = 0ull;
@@ -152,7 +171,7 @@ __global__ void __launch_bounds__(1024, 1) row_pass_kernel(DeviceModel d)
     atomicAdd(d.segTotal + tid, sSegTot[tid]);
     atomicMax(d.segLast + tid, sSegLast[tid]);
   }
-  grid_barrier(d.gridBar);
+  grid_barrier(d.gridBar, barGen);
 
   // ---------------------------------------------------------------- P1 crossing bucket (every CTA)
   constexpr int NSEG = kHistBuckets / 1024; // 32: one lane per segment
@@ -248,7 +267,7 @@ __global__ void __launch_bounds__(1024, 1) row_pass_kernel(DeviceModel d)
     atomicAdd(d.hist2Weight, sHot);
     atomicMin(d.hist2Min, sHotMin);
   }
-  grid_barrier(d.gridBar);
+  grid_barrier(d.gridBar, barGen);
 
   // ---------------------------------------------------------------- P3 theta* (every CTA)
   {
@@ -339,7 +358,7 @@ __global__ void __launch_bounds__(1024, 1) row_pass_kernel(DeviceModel d)
     if (tid == 0 && best != 0x7FF0000000000000ull)
       atomicMin(&st->harrisBits, best);
   }
-  grid_barrier(d.gridBar);
+  grid_barrier(d.gridBar, barGen);
 
   // ---------------------------------------------------------------- P5 largest |alpha| in [theta*, harris]
   const unsigned long long harrisBits = __ldcg(&st->harrisBits);
@@ -361,7 +380,7 @@ __global__ void __launch_bounds__(1024, 1) row_pass_kernel(DeviceModel d)
     if (tid == 0 && best != 0ull)
       atomicMax(&st->chuzcKey, best);
   }
-  grid_barrier(d.gridBar);
+  grid_barrier(d.gridBar, barGen);
 
   // ---------------------------------------------------------------- P6 winner, dual update, flips
   const unsigned long long key = __ldcg(&st->chuzcKey);
@@ -422,7 +441,7 @@ __global__ void __launch_bounds__(1024, 1) row_pass_kernel(DeviceModel d)
     if (tid == 0 && maxRange != 0ull)
       atomicMax(&st->flipMaxBits, maxRange);
   }
-  grid_barrier(d.gridBar);
+  grid_barrier(d.gridBar, barGen);
 
   // ---------------------------------------------------------------- P8 scatter flips + entering column
   // every contribution |a_ij * delta_j| <= amax * maxRange < 2^Ex, at most nf < 2^bitsN of them per
@@ -459,7 +478,7 @@ __global__ void __launch_bounds__(1024, 1) row_pass_kernel(DeviceModel d)
     for (int e = d.colStart[seqIn] + tid; e < e1; e += 1024)
       d.aqBuf[d.rowIdx[e]] = d.val[e];
   }
-  grid_barrier(d.gridBar);
+  grid_barrier(d.gridBar, barGen);
 
   // ---------------------------------------------------------------- P9 rhs3 and its nucleus gather
   {

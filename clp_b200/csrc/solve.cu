@@ -39,12 +39,14 @@ __global__ void gather_nucleus_kernel(DeviceModel d, const double *__restrict__ 
   }
 }
 
-// y[c][i] = sum_j M[i][j] * x[c][j]   (M row-major k x ldk).  One CTA streams a group of four
-// consecutive rows: each thread issues the four 16-byte loads (one per row) back to back and
-// reuses every x value for the four rows, so the L1 traffic for x is NRHS/4 of the matrix
-// traffic and 16 KB of matrix (4 KB contiguous per row) are in flight per CTA step.
-// if outIndex != nullptr the result is scattered: out[c*ostride + outIndex[i]]
-template <int NRHS>
+// y[c][i] = sum_j M[i][j] * x[c][j]   (M row-major k x ldk).  One CTA streams R consecutive rows with
+// DEPTH 16-byte loads per row in flight per thread, i.e. R*DEPTH*4 KB contiguous per row and step:
+// few, long DRAM streams (measured on B200, tests/microbench/iter_kernels.cu, k = 4682 / 5787:
+// one right-hand side R=1 DEPTH=8 33 / 45 us against 37 / 56 us for R=4 DEPTH=1; three right-hand
+// sides R=2 DEPTH=2 38 / 53 us against 43 / 60 us -- x goes through L1, so more rows per CTA pay
+// once there are three of them).  outIndex != nullptr: the result is scattered,
+// out[c*ostride + outIndex[i]].
+template <int NRHS, int R, int DEPTH>
 __global__ void __launch_bounds__(256)
     gemv_rows_kernel(const FactorDesc *__restrict__ fd, int transposed,
                      const double *__restrict__ x, double *__restrict__ out, int ostride,
@@ -52,7 +54,6 @@ __global__ void __launch_bounds__(256)
 {
   if (checkState && !iter_active(st))
     return;
-  constexpr int R = 4;
   __shared__ double part[8][R * NRHS];
   const int k = fd->k, ldk = fd->ldk;
   const double *__restrict__ M = transposed ? fd->NinvT : fd->Ninv;
@@ -71,19 +72,26 @@ __global__ void __launch_bounds__(256)
 #pragma unroll
       for (int c = 0; c < NRHS; c++)
         acc[r][c] = 0.0;
-#pragma unroll 2
-    for (int j = threadIdx.x; j < half; j += 256) {
-      double2 a[R];
+    for (int j = threadIdx.x; j < half; j += 256 * DEPTH) {
+      double2 a[DEPTH][R];
 #pragma unroll
-      for (int r = 0; r < R; r++)
-        a[r] = __ldcs(row[r] + j);
+      for (int u = 0; u < DEPTH; u++) {
+        const bool p = j + 256 * u < half;
 #pragma unroll
-      for (int c = 0; c < NRHS; c++) {
-        const double2 xv = __ldg(reinterpret_cast<const double2 *>(x + (size_t)c * ldk) + j);
+        for (int r = 0; r < R; r++)
+          a[u][r] = p ? __ldcs(row[r] + j + 256 * u) : make_double2(0.0, 0.0);
+      }
 #pragma unroll
-        for (int r = 0; r < R; r++) {
-          acc[r][c] = fma(a[r].x, xv.x, acc[r][c]);
-          acc[r][c] = fma(a[r].y, xv.y, acc[r][c]);
+      for (int u = 0; u < DEPTH; u++) {
+        const int jj = min(j + 256 * u, half - 1);
+#pragma unroll
+        for (int c = 0; c < NRHS; c++) {
+          const double2 xv = __ldg(reinterpret_cast<const double2 *>(x + (size_t)c * ldk) + jj);
+#pragma unroll
+          for (int r = 0; r < R; r++) {
+            acc[r][c] = fma(a[u][r].x, xv.x, acc[r][c]);
+            acc[r][c] = fma(a[u][r].y, xv.y, acc[r][c]);
+          }
         }
       }
     }
@@ -298,7 +306,10 @@ static void ftran_impl(const DeviceModel &d, double *b, bool applyEtas, bool che
   int blocks = maxk < 148 * 8 ? maxk : 148 * 8;
   if (g_kernelTimers && checkState)
     cudaEventRecord(g_kernelTimers->ftranGemv[0], s);
-  gemv_rows_kernel<NRHS><<<blocks, 256, 0, s>>>(d.fd, 0, xg, d.ywork, -1, nullptr, d.st, checkState);
+  if (NRHS == 1)
+    gemv_rows_kernel<NRHS, 1, 8><<<blocks, 256, 0, s>>>(d.fd, 0, xg, d.ywork, -1, nullptr, d.st, checkState);
+  else
+    gemv_rows_kernel<NRHS, 2, 2><<<blocks, 256, 0, s>>>(d.fd, 0, xg, d.ywork, -1, nullptr, d.st, checkState);
   if (g_kernelTimers && checkState)
     cudaEventRecord(g_kernelTimers->ftranGemv[1], s);
   ftran_spread_kernel<NRHS><<<(m * 8 + 255) / 256, 256, 0, s>>>(d, b, m, d.ywork, checkState, applyEtas);
@@ -461,17 +472,15 @@ __global__ void __launch_bounds__(256) btran_us_kernel(DeviceModel d, double *__
   const int lane = threadIdx.x & 31;
   const int k = d.fd->k, ldk = d.fd->ldk;
   const int warpsPerBlock = blockDim.x >> 5;
+  const int *__restrict__ s1cRow = d.fd->s1cRow;
+  const double *__restrict__ s1cVal = d.fd->s1cVal;
   for (int j = blockIdx.x * warpsPerBlock + (threadIdx.x >> 5); j < k; j += gridDim.x * warpsPerBlock) {
-    const int col = d.nucCol[j];
     double acc = 0.0;
-    const int e1 = d.colStart[col + 1];
-    for (int e = d.colStart[col] + lane; e < e1; e += 32) {
-      const int i = d.rowIdx[e];
-      if (d.posToNuc[i] < 0) {
-        const double u = btran_u_of(d, i, r, t);
-        if (u != 0.0)
-          acc = fma(d.val[e], u, acc);
-      }
+    const int e1 = d.s1cStart[j + 1];
+    for (int e = d.s1cStart[j] + lane; e < e1; e += 32) { // entries of column j in rows of C only
+      const double u = btran_u_of(d, s1cRow[e], r, t);
+      if (u != 0.0)
+        acc = fma(s1cVal[e], u, acc);
     }
     acc = warp_sum(acc);
     if (lane == 0)
@@ -498,8 +507,8 @@ static void btran_gemv(const DeviceModel &d, double *rhoOut, bool checkState, cu
   int blocks = d.m < 148 * 8 ? d.m : 148 * 8;
   if (g_kernelTimers && checkState)
     cudaEventRecord(g_kernelTimers->btranGemv[0], s);
-  gemv_rows_kernel<1><<<blocks, 256, 0, s>>>(d.fd, 1, d.swork, rhoOut, d.m, d.nucRow, d.st,
-                                             checkState);
+  gemv_rows_kernel<1, 1, 8><<<blocks, 256, 0, s>>>(d.fd, 1, d.swork, rhoOut, d.m, d.nucRow, d.st,
+                                                   checkState);
   if (g_kernelTimers && checkState)
     cudaEventRecord(g_kernelTimers->btranGemv[1], s);
 }

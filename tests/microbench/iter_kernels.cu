@@ -353,6 +353,264 @@ __global__ void __launch_bounds__(1024, 1)
   }
 }
 
+
+// v3: big tiles, deep ring, but only 256 threads and LPC lanes per column (32/LPC columns per warp at
+// once): ~7x fewer instructions per column than one-warp-per-column, so the CTA is load bound.
+template <int E, int S, typename IdxT, int LPC, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1)
+    price_v3(const IdxT *__restrict__ rowIdx, const double *__restrict__ val, const int *__restrict__ colStart,
+             const double *__restrict__ rhoG, int m, double *__restrict__ alphaRow, const int4 *__restrict__ tileDesc,
+             int ntiles, int descCap)
+{
+  extern __shared__ __align__(128) unsigned char smemRaw[];
+  unsigned long long *full = reinterpret_cast<unsigned long long *>(smemRaw);
+  int4 *sdesc = reinterpret_cast<int4 *>(smemRaw + 128);
+  int *scol = reinterpret_cast<int *>(smemRaw + 128 + (size_t)descCap * 16); // [S][MAXC+8]
+  double *sval = reinterpret_cast<double *>(scol + S * (MAXC + 8));           // [S][E]
+  IdxT *sidx = reinterpret_cast<IdxT *>(sval + (size_t)S * E);                // [S][E]
+  double *srho = reinterpret_cast<double *>(sidx + (size_t)S * E);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int G = gridDim.x;
+  const int myTiles = (int)blockIdx.x < ntiles ? (ntiles - 1 - blockIdx.x) / G + 1 : 0;
+  for (int i = tid; i < myTiles; i += THREADS)
+    sdesc[i] = tileDesc[blockIdx.x + (size_t)i * G];
+  if (tid == 0) {
+    for (int q = 0; q < S; q++)
+      mbar_init(&full[q], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+  auto issue = [&](int i, int stage) {
+    const int4 ds = sdesc[i];
+    const unsigned cnt = (unsigned)ds.w;
+    const unsigned colBytes = (unsigned)(((ds.y + 1 + 3) & ~3) * 4);
+    mbar_expect_tx(&full[stage], cnt * (8u + (unsigned)sizeof(IdxT)) + colBytes);
+    bulk_g2s(sval + (size_t)stage * E, val + ds.z, cnt * 8u, &full[stage]);
+    bulk_g2s(sidx + (size_t)stage * E, rowIdx + ds.z, cnt * (unsigned)sizeof(IdxT), &full[stage]);
+    bulk_g2s(scol + stage * (MAXC + 8), colStart + ds.x, colBytes, &full[stage]);
+  };
+  if (tid == 0)
+    for (int q = 0; q < S && q < myTiles; q++)
+      issue(q, q);
+  for (int i = tid; i < m; i += THREADS)
+    srho[i] = rhoG[i];
+  __syncthreads();
+  constexpr int CPW = 32 / LPC;               // columns per warp at once
+  constexpr int CPP = CPW * (THREADS / 32);   // columns per pass of the CTA
+  const int grp = lane / LPC, sub = lane % LPC;
+  for (int it = 0; it < myTiles; it++) {
+    const int stage = it % S;
+    const int4 ds = sdesc[it];
+    mbar_wait(&full[stage], (unsigned)((it / S) & 1));
+    const double *v = sval + (size_t)stage * E;
+    const IdxT *ix = sidx + (size_t)stage * E;
+    const int *cs = scol + stage * (MAXC + 8);
+    for (int c0 = 0; c0 < ds.y; c0 += CPP) {
+      const int c = c0 + warp * CPW + grp;
+      int b0 = 0, b1 = 0;
+      if (c < ds.y) {
+        b0 = cs[c] - ds.z;
+        b1 = cs[c + 1] - ds.z;
+      }
+      double acc0 = 0.0, acc1 = 0.0;
+      for (int e = b0 + sub; e < b1; e += 2 * LPC) {
+        const bool p1 = e + LPC < b1;
+        const int r0 = ix[e];
+        const int r1 = p1 ? (int)ix[e + LPC] : 0;
+        const double v0 = v[e];
+        const double v1 = p1 ? v[e + LPC] : 0.0;
+        acc0 = fma(v0, srho[r0], acc0);
+        acc1 = fma(v1, srho[r1], acc1);
+      }
+      double acc = acc0 + acc1;
+#pragma unroll
+      for (int o = LPC / 2; o > 0; o >>= 1)
+        acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if (sub == 0 && c < ds.y)
+        alphaRow[ds.x + c] = acc;
+    }
+    __syncthreads();
+    if (tid == 0 && it + S < myTiles) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      issue(it + S, stage);
+    }
+  }
+}
+
+
+// LDG-direct price: no shared-memory staging of the matrix (only rho lives in shared memory), one
+// warp per column, the NEXT column's entries are prefetched into registers while the current one
+// is reduced.  Columns longer than 128 entries take an extra (unpipelined) loop.
+template <int THREADS, int CTAS>
+__global__ void __launch_bounds__(THREADS, CTAS)
+    price_ldg(const int *__restrict__ rowIdx, const double *__restrict__ val, const int *__restrict__ colStart,
+              const double *__restrict__ rhoG, int m, double *__restrict__ alphaRow, int n)
+{
+  extern __shared__ __align__(16) unsigned char rawr[];
+  double *srho = reinterpret_cast<double *>(rawr);
+  for (int i = threadIdx.x; i < m; i += THREADS)
+    srho[i] = rhoG[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int gw = blockIdx.x * (THREADS >> 5) + (threadIdx.x >> 5);
+  const int GW = gridDim.x * (THREADS >> 5);
+  int j = gw;
+  int nb0 = 0, nb1 = 0;
+  int ni[4];
+  double nv[4];
+  auto fetchBounds = [&](int jj) {
+    if (jj < n) {
+      nb0 = __ldg(colStart + jj);
+      nb1 = __ldg(colStart + jj + 1);
+    } else {
+      nb0 = nb1 = 0;
+    }
+  };
+  auto fetchEntries = [&](int b0, int b1) {
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int e = b0 + lane + 32 * u;
+      const bool p = e < b1;
+      ni[u] = p ? __ldcs(rowIdx + e) : 0;
+      nv[u] = p ? __ldcs(val + e) : 0.0;
+    }
+  };
+  fetchBounds(j);
+  int b0 = nb0, b1 = nb1;
+  fetchEntries(b0, b1);
+  fetchBounds(j + GW);
+  for (; j < n; j += GW) {
+    int ci[4];
+    double cv[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      ci[u] = ni[u];
+      cv[u] = nv[u];
+    }
+    const int cb0 = b0, cb1 = b1;
+    b0 = nb0;
+    b1 = nb1;
+    fetchEntries(b0, b1);      // next column's entries in flight
+    fetchBounds(j + 2 * GW);   // bounds two columns ahead
+    double acc0 = cv[0] * srho[ci[0]], acc1 = cv[1] * srho[ci[1]];
+    acc0 = fma(cv[2], srho[ci[2]], acc0);
+    acc1 = fma(cv[3], srho[ci[3]], acc1);
+    for (int e = cb0 + 128 + lane; e < cb1; e += 32) // long columns
+      acc0 = fma(__ldg(val + e), srho[__ldg(rowIdx + e)], acc0);
+    const double acc = warp_sum(acc0 + acc1);
+    if (lane == 0)
+      alphaRow[j] = acc;
+  }
+}
+
+// CTA per row, DEPTH 16-byte loads in flight per thread, x through L1 (NRHS right-hand sides)
+template <int NRHS, int DEPTH>
+__global__ void __launch_bounds__(256)
+    gemv_row(const double *__restrict__ M, int k, int ldk, const double *__restrict__ x, double *__restrict__ out)
+{
+  __shared__ double part[8][NRHS];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int half = ldk >> 1;
+  for (int i = blockIdx.x; i < k; i += gridDim.x) {
+    const double2 *row = reinterpret_cast<const double2 *>(M + (size_t)i * ldk);
+    double acc[NRHS];
+#pragma unroll
+    for (int c = 0; c < NRHS; c++)
+      acc[c] = 0.0;
+    for (int j = threadIdx.x; j < half; j += 256 * DEPTH) {
+      double2 a[DEPTH];
+#pragma unroll
+      for (int u = 0; u < DEPTH; u++)
+        a[u] = (j + 256 * u < half) ? __ldcs(row + j + 256 * u) : make_double2(0.0, 0.0);
+#pragma unroll
+      for (int u = 0; u < DEPTH; u++) {
+        const int jj = min(j + 256 * u, half - 1);
+#pragma unroll
+        for (int c = 0; c < NRHS; c++) {
+          const double2 xv = __ldg(reinterpret_cast<const double2 *>(x + (size_t)c * ldk) + jj);
+          acc[c] = fma(a[u].x, xv.x, acc[c]);
+          acc[c] = fma(a[u].y, xv.y, acc[c]);
+        }
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < NRHS; c++) {
+      const double v = warp_sum(acc[c]);
+      if (lane == 0)
+        part[warp][c] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < NRHS) {
+      double sum = 0.0;
+#pragma unroll
+      for (int w = 0; w < 8; w++)
+        sum += part[w][threadIdx.x];
+      out[(size_t)threadIdx.x * ldk + i] = sum;
+    }
+    __syncthreads();
+  }
+}
+// two rows per CTA
+template <int NRHS, int DEPTH>
+__global__ void __launch_bounds__(256)
+    gemv_row2(const double *__restrict__ M, int k, int ldk, const double *__restrict__ x, double *__restrict__ out)
+{
+  __shared__ double part[8][2 * NRHS];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int half = ldk >> 1;
+  const int ngroups = (k + 1) / 2;
+  for (int g = blockIdx.x; g < ngroups; g += gridDim.x) {
+    const int i0 = g * 2;
+    const double2 *row0 = reinterpret_cast<const double2 *>(M + (size_t)i0 * ldk);
+    const double2 *row1 = reinterpret_cast<const double2 *>(M + (size_t)min(i0 + 1, k - 1) * ldk);
+    double acc[2][NRHS];
+#pragma unroll
+    for (int c = 0; c < NRHS; c++)
+      acc[0][c] = acc[1][c] = 0.0;
+    for (int j = threadIdx.x; j < half; j += 256 * DEPTH) {
+      double2 a[DEPTH], b[DEPTH];
+#pragma unroll
+      for (int u = 0; u < DEPTH; u++) {
+        const bool p = j + 256 * u < half;
+        a[u] = p ? __ldcs(row0 + j + 256 * u) : make_double2(0.0, 0.0);
+        b[u] = p ? __ldcs(row1 + j + 256 * u) : make_double2(0.0, 0.0);
+      }
+#pragma unroll
+      for (int u = 0; u < DEPTH; u++) {
+        const int jj = min(j + 256 * u, half - 1);
+#pragma unroll
+        for (int c = 0; c < NRHS; c++) {
+          const double2 xv = __ldg(reinterpret_cast<const double2 *>(x + (size_t)c * ldk) + jj);
+          acc[0][c] = fma(a[u].x, xv.x, acc[0][c]);
+          acc[0][c] = fma(a[u].y, xv.y, acc[0][c]);
+          acc[1][c] = fma(b[u].x, xv.x, acc[1][c]);
+          acc[1][c] = fma(b[u].y, xv.y, acc[1][c]);
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 2; r++)
+#pragma unroll
+      for (int c = 0; c < NRHS; c++) {
+        const double v = warp_sum(acc[r][c]);
+        if (lane == 0)
+          part[warp][r * NRHS + c] = v;
+      }
+    __syncthreads();
+    if (threadIdx.x < 2 * NRHS) {
+      double sum = 0.0;
+#pragma unroll
+      for (int w = 0; w < 8; w++)
+        sum += part[w][threadIdx.x];
+      const int r = threadIdx.x / NRHS, c = threadIdx.x % NRHS;
+      if (i0 + r < k)
+        out[(size_t)c * ldk + i0 + r] = sum;
+    }
+    __syncthreads();
+  }
+}
+
 // naive reference: warp per column
 __global__ void price_ref(const int *__restrict__ rowIdx, const double *__restrict__ val, const int *__restrict__ colStart,
                           const double *__restrict__ rho, int n, double *__restrict__ alpha)
@@ -596,6 +854,25 @@ int main(int argc, char **argv)
         snprintf(nm, 96, "cur<3> grid %d", grid);
         report(nm, t3, 3);
       }
+      if (which & 16) {
+        for (int grid : {592, 1184, 2368}) {
+          char nm[96];
+#define RUN_ROW(KERN, LABEL, NR)                                                                   \
+  do {                                                                                             \
+    CK(cudaMemset(out, 0, sizeof(double) * 3 * ldk));                                              \
+    float t = timeit([&] { KERN<<<grid, 256>>>(Mw(), k, ldk, x3, out); });                         \
+    snprintf(nm, 96, LABEL " grid %d", grid);                                                      \
+    report(nm, t, NR);                                                                             \
+  } while (0)
+          RUN_ROW((gemv_row<1, 4>), "row<1,D4>", 1);
+          RUN_ROW((gemv_row<1, 8>), "row<1,D8>", 1);
+          RUN_ROW((gemv_row<3, 4>), "row<3,D4>", 3);
+          RUN_ROW((gemv_row<3, 8>), "row<3,D8>", 3);
+          RUN_ROW((gemv_row2<1, 4>), "row2<1,D4>", 1);
+          RUN_ROW((gemv_row2<3, 2>), "row2<3,D2>", 3);
+          RUN_ROW((gemv_row2<3, 4>), "row2<3,D4>", 3);
+        }
+      }
       auto runItems = [&](auto kern, const char *name, int nrhs, int threads, int Q) {
         const int half = ldk / 2;
         int seg2 = ((half + Q - 1) / Q + 31) / 32 * 32;
@@ -763,6 +1040,75 @@ int main(int argc, char **argv)
     report(nm, t, 8.0 + sizeof(IDXT));                                                                            \
     cudaFree(dDesc);                                                                                              \
   } while (0)
+#define RUN_V3(EE, SS, IDXT, LPCV, THR, MAXCOLS, IDXPTR)                                                          \
+  do {                                                                                                            \
+    const int E = EE, S = SS;                                                                                     \
+    std::vector<int> desc;                                                                                        \
+    int c = 0, ntl = 0;                                                                                           \
+    bool ok = true;                                                                                               \
+    while (c < n) {                                                                                               \
+      const int ea = cs[c] & ~7;                                                                                  \
+      int c1 = c;                                                                                                 \
+      while (c1 < n && c1 - c < MAXCOLS) {                                                                        \
+        int c2 = std::min(n, c1 + 4);                                                                             \
+        if (((cs[c2] + 7) & ~7) - ea > E)                                                                         \
+          break;                                                                                                  \
+        c1 = c2;                                                                                                  \
+      }                                                                                                           \
+      if (c1 == c) { ok = false; break; }                                                                         \
+      desc.push_back(c); desc.push_back(c1 - c); desc.push_back(ea); desc.push_back(((cs[c1] + 7) & ~7) - ea);    \
+      c = c1;                                                                                                     \
+      ntl++;                                                                                                      \
+    }                                                                                                             \
+    const int descCap = ((ntl + 147) / 148 + 7) / 8 * 8;                                                          \
+    const size_t smem = 128 + (size_t)descCap * 16 + (size_t)S * (MAXC + 8) * 4 + (size_t)S * E * (8 + sizeof(IDXT)) + sizeof(double) * m; \
+    char nm[160];                                                                                                 \
+    snprintf(nm, 160, "price_v3 E=%d S=%d idx%zu lpc=%d thr=%d maxc=%d (%d tiles, smem %zu)", E, S, sizeof(IDXT) * 8, LPCV, THR, MAXCOLS, ntl, smem); \
+    if (!ok || smem > 227 * 1024) { printf("%s: skipped\n", nm); break; }                                          \
+    int4 *dDesc;                                                                                                  \
+    CK(cudaMalloc(&dDesc, sizeof(int) * desc.size()));                                                            \
+    CK(cudaMemcpy(dDesc, desc.data(), sizeof(int) * desc.size(), cudaMemcpyHostToDevice));                        \
+    CK(cudaFuncSetAttribute(price_v3<EE, SS, IDXT, LPCV, THR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
+    CK(cudaMemset(dAlpha, 0, sizeof(double) * n));                                                                \
+    float t = timeit([&] {                                                                                        \
+      win = (win + 1) % NW;                                                                                       \
+      price_v3<EE, SS, IDXT, LPCV, THR><<<148, THR, smem>>>(IDXPTR + win * stride, dVal + win * stride, dCs, dRho, m, dAlpha, dDesc, ntl, descCap); \
+    });                                                                                                           \
+    report(nm, t, 8.0 + sizeof(IDXT));                                                                            \
+    cudaFree(dDesc);                                                                                              \
+  } while (0)
+    if (which & 32) {
+#define RUN_LDG(THR, CT)                                                                           \
+  do {                                                                                             \
+    CK(cudaFuncSetAttribute(price_ldg<THR, CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(double) * m)); \
+    CK(cudaMemset(dAlpha, 0, sizeof(double) * n));                                                 \
+    float t = timeit([&] {                                                                         \
+      win = (win + 1) % NW;                                                                        \
+      price_ldg<THR, CT><<<148 * CT, THR, sizeof(double) * m>>>(dIdx + win * stride, dVal + win * stride, dCs, dRho, m, dAlpha, n); \
+    });                                                                                            \
+    char nm[96];                                                                                   \
+    snprintf(nm, 96, "price_ldg thr=%d ctas/SM=%d", THR, CT);                                      \
+    report(nm, t, 12.0);                                                                           \
+  } while (0)
+      RUN_LDG(768, 2);
+      RUN_LDG(1024, 2);
+      RUN_LDG(512, 2);
+      RUN_LDG(1024, 1);
+      RUN_LDG(640, 2);
+    }
+    if (which & 8) {
+    RUN_V3(2816, 4, int, 8, 256, 32, dIdx);
+    RUN_V3(2816, 4, int, 16, 256, 32, dIdx);
+    RUN_V3(2816, 4, int, 8, 512, 64, dIdx);
+    RUN_V3(2816, 4, int, 16, 512, 32, dIdx);
+    RUN_V3(2816, 4, int, 4, 256, 64, dIdx);
+    RUN_V3(3584, 3, int, 8, 256, 32, dIdx);
+    RUN_V3(2048, 5, int, 8, 256, 32, dIdx);
+    RUN_V3(1792, 6, int, 8, 256, 16, dIdx);
+    RUN_V3(3328, 4, unsigned short, 8, 256, 32, dIdx16);
+    RUN_V3(3328, 4, unsigned short, 16, 256, 32, dIdx16);
+    RUN_V3(2816, 4, int, 8, 1024, 64, dIdx);
+    }
     RUN_BIG(2816, 4, int, true, dIdx);
     RUN_BIG(2048, 5, int, true, dIdx);
     RUN_BIG(1536, 7, int, true, dIdx);
