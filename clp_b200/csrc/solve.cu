@@ -241,45 +241,79 @@ __global__ void __launch_bounds__(256) pfi_mu_kernel(DeviceModel d, bool checkSt
   }
 }
 
-// x_c[p] -= sum_{i<t} W[p][i] * mu_c[i]   (one warp per position, eight loads of the panel row in
-// flight per lane, 64 warps per SM).  pivotTail: the last CTA then evaluates the accuracy gate and
-// the primal step (pivot_scalars_body) on the finished columns.
+// x_c[p] -= sum_{i<t} W[p][i] * mu_c[i] : a GEMV over the first t columns of the m x tmax panel,
+// same shape as gemv_rows_kernel (one CTA streams R = 2 rows, DEPTH = 2 sixteen-byte loads per row in
+// flight per thread; mu goes through L1).  pivotTail: the last CTA then evaluates the accuracy gate
+// and the primal step (pivot_scalars_body) on the finished columns.
 template <int NRHS>
 __global__ void __launch_bounds__(256) pfi_apply_kernel(DeviceModel d, double *__restrict__ x, int xstride,
                                                         bool checkState, bool pivotTail)
 {
+  constexpr int R = 2, DEPTH = 2;
+  __shared__ double part[8][R * NRHS];
   if (checkState && !iter_active(d.st))
     return;
   const int t = d.st->numEtas;
   if (t > 0) {
-    const int lane = threadIdx.x & 31;
-    const int warpsPerBlock = blockDim.x >> 5;
-    for (int p = blockIdx.x * warpsPerBlock + (threadIdx.x >> 5); p < d.m;
-         p += gridDim.x * warpsPerBlock) {
-      const double *wrow = d.W + (size_t)p * d.tmax;
-      double acc[NRHS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int half = (t + 1) >> 1; // double2 per row; an odd t reads one stale entry, masked below
+    const int ngroups = (d.m + R - 1) / R;
+    for (int g = blockIdx.x; g < ngroups; g += gridDim.x) {
+      const int p0 = g * R;
+      const double2 *row[R];
 #pragma unroll
-      for (int c = 0; c < NRHS; c++)
-        acc[c] = 0.0;
-      for (int i = lane; i < t; i += 256) {
-        double w[8];
+      for (int r = 0; r < R; r++)
+        row[r] = reinterpret_cast<const double2 *>(d.W + (size_t)min(p0 + r, d.m - 1) * d.tmax);
+      double acc[R][NRHS];
 #pragma unroll
-        for (int u = 0; u < 8; u++)
-          w[u] = (i + 32 * u < t) ? __ldcs(wrow + i + 32 * u) : 0.0;
+      for (int r = 0; r < R; r++)
 #pragma unroll
-        for (int u = 0; u < 8; u++) {
-          const int ii = min(i + 32 * u, t - 1);
+        for (int c = 0; c < NRHS; c++)
+          acc[r][c] = 0.0;
+      for (int j = threadIdx.x; j < half; j += 256 * DEPTH) {
+        double2 a[DEPTH][R];
 #pragma unroll
-          for (int c = 0; c < NRHS; c++)
-            acc[c] = fma(w[u], __ldg(d.mu + (size_t)c * d.tmax + ii), acc[c]);
+        for (int u = 0; u < DEPTH; u++) {
+          const bool p = j + 256 * u < half;
+#pragma unroll
+          for (int r = 0; r < R; r++)
+            a[u][r] = p ? __ldcs(row[r] + j + 256 * u) : make_double2(0.0, 0.0);
+        }
+#pragma unroll
+        for (int u = 0; u < DEPTH; u++) {
+          const int jj = min(j + 256 * u, half - 1);
+          const bool second = 2 * jj + 1 < t;
+#pragma unroll
+          for (int c = 0; c < NRHS; c++) {
+            const double m0 = __ldg(d.mu + (size_t)c * d.tmax + 2 * jj);
+            const double m1 = second ? __ldg(d.mu + (size_t)c * d.tmax + 2 * jj + 1) : 0.0;
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+              acc[r][c] = fma(a[u][r].x, m0, acc[r][c]);
+              acc[r][c] = fma(second ? a[u][r].y : 0.0, m1, acc[r][c]);
+            }
+          }
         }
       }
 #pragma unroll
-      for (int c = 0; c < NRHS; c++)
-        acc[c] = warp_sum(acc[c]);
-      if (lane == 0)
-        for (int c = 0; c < NRHS; c++)
-          x[(size_t)c * xstride + p] -= acc[c];
+      for (int r = 0; r < R; r++)
+#pragma unroll
+        for (int c = 0; c < NRHS; c++) {
+          const double v = warp_sum(acc[r][c]);
+          if (lane == 0)
+            part[warp][r * NRHS + c] = v;
+        }
+      __syncthreads();
+      if (threadIdx.x < R * NRHS) {
+        double sum = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; w++)
+          sum += part[w][threadIdx.x];
+        const int r = threadIdx.x / NRHS, c = threadIdx.x % NRHS;
+        if (p0 + r < d.m)
+          x[(size_t)c * xstride + p0 + r] -= sum;
+      }
+      __syncthreads();
     }
   }
   if (!pivotTail)
@@ -315,7 +349,7 @@ static void ftran_impl(const DeviceModel &d, double *b, bool applyEtas, bool che
   ftran_spread_kernel<NRHS><<<(m * 8 + 255) / 256, 256, 0, s>>>(d, b, m, d.ywork, checkState, applyEtas);
   if (applyEtas) {
     pfi_mu_kernel<NRHS><<<d.tmax, 256, 0, s>>>(d, checkState);
-    int pblocks = (m + 7) / 8;
+    int pblocks = (m + 1) / 2;
     if (pblocks > 148 * 8)
       pblocks = 148 * 8;
     pfi_apply_kernel<NRHS><<<pblocks, 256, 0, s>>>(d, b, m, checkState, pivotTail);
