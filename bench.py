@@ -154,7 +154,17 @@ def run_reference(args, lp, status, start, cycle):
     }
 
 
+def _claim_stdout():
+    """Rank 0 must print exactly ONE JSON line: park the real stdout and point fd 1 at stderr, so that
+    library banners (NCCL prints its version to stdout) cannot precede or follow the line."""
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    return os.fdopen(real, "w")
+
+
 def main():
+    out = _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=8)
@@ -178,9 +188,10 @@ def main():
         if rank != 0:
             return 0
         lp, status, start = build_workload(args.workload)
-        print(json.dumps(run_reference(args, lp, status, start, cycle)), flush=True)
+        print(json.dumps(run_reference(args, lp, status, start, cycle)), file=out, flush=True)
         return 0
 
+    os.environ.setdefault("NCCL_DEBUG", "WARN")  # NCCL's version banner would go to stdout
     import torch
 
     import clp_b200
@@ -312,7 +323,7 @@ def main():
                                             "oracle/ restatement of Clp's dual path (coin-or/Clp itself cannot be "
                                             "built: CoinUtils absent)"}
     if rank == 0:
-        print(json.dumps(result), flush=True)
+        print(json.dumps(result), file=out, flush=True)
     if dist is not None:
         dist.destroy_process_group()
     return 0

@@ -144,6 +144,8 @@ int Clpb_setParameter(Clpb_Simplex *model, const char *key, double value)
     e.useGraph = value != 0.0;
   else if (k == "useRowPass")
     e.useRowPass = value != 0.0;
+  else if (k == "pfiApplyVariant")
+    clpb::g_pfiApplyVariant = (int)value;
   else if (k == "objectiveOffset")
     e.objectiveOffset = value;
   else if (k == "scaling")

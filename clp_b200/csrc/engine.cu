@@ -1019,22 +1019,21 @@ void Engine::enqueueIteration(bool timed, int slot)
     cudaEventRecord(ev[2], stream);
   bool rowPassed = false;
   if (worldSize > 1) {
+    // column-sharded pricing: this rank's block of raw dot products, then ONE exchange per pricing
+    // pass -- an in-place all-gather of the row shards (padded to 'per' entries; the padding lands
+    // on the slack part of the row, which the row kernels recompute from rho).  Everything after
+    // the gather runs replicated on identical data.
     int per = (n + worldSize - 1) / worldSize;
     int c0 = std::min(n, rank * per), c1 = std::min(n, c0 + per);
     launch_price(d, c0, c1, false, stream);
-    launch_price_slacks(d, c0, c1, false, stream); // status mask / tolerance on the own shard
-    // one exchange per pricing pass: all-gather of the row shards (padded to 'per' entries;
-    // the padding lands on the slack part, which is rewritten afterwards)
     allGatherFn(ncclComm, d.alphaRow, sizeof(double) * per, stream);
-    launch_price_slacks(d, 0, 0, false, stream);
-    launch_histogram(d, stream);
-  } else if (useRowPass) {
-    launch_price(d, 0, n, false, stream);
-    rowPassed = true;
   } else {
-    launch_price(d, 0, n, true, stream);
-    launch_price_slacks(d, 0, n, true, stream);
+    launch_price(d, 0, n, false, stream);
   }
+  if (useRowPass)
+    rowPassed = true;
+  else
+    launch_price_slacks(d, 0, n, true, stream); // status mask, slack part, level-1 histogram
   if (timed)
     cudaEventRecord(ev[3], stream);
   if (rowPassed) {
@@ -1061,7 +1060,7 @@ void Engine::enqueueIteration(bool timed, int slot)
   if (timed)
     cudaEventRecord(ev[7], stream);
   g_kernelTimers = nullptr;
-  kernelLaunches += rowPassed ? 3 + 1 + 1 + 4 + 1 : 3 + 2 + 4 + 3 + 5 + 1 + (worldSize > 1 ? 3 : 0);
+  kernelLaunches += rowPassed ? 3 + 1 + 1 + 4 + 1 : 3 + 2 + 4 + 3 + 5 + 1;
 }
 
 // start of a batch: stand-alone CHUZR (2 kernels)
@@ -1104,7 +1103,7 @@ void Engine::buildIterationGraph()
       cudaGraphDestroy(graph);
     if (!ok) {
       cudaGetLastError(); // clear the sticky capture error
-      if (useRowPass && worldSize == 1) {
+      if (useRowPass) {
         fprintf(stderr, "clp_b200: cooperative row pass not capturable, using the separate kernels\n");
         useRowPass = false;
       } else {

@@ -168,6 +168,7 @@ struct KernelTimers {
   cudaEvent_t price[2], ftranGemv[2], btranGemv[2];
 };
 extern KernelTimers *g_kernelTimers; // nullptr outside timing mode (engine.cu)
+extern int g_pfiApplyVariant;         // solve.cu
 
 // ---- launch wrappers (implemented in the .cu files) ---------------------------------------
 // solve.cu

@@ -19,6 +19,8 @@ namespace clpb {
 
 static inline int roundUp8(int v) { return (v + 7) / 8 * 8; }
 
+int g_pfiApplyVariant = 0; // 0: warp per panel row, 1: GEMV-shaped (two rows per CTA); "pfiApplyVariant"
+
 // ---------------------------------------------------------------------------------------
 // gather b_N : xg[c][j] = b_c[nucRow[j]]
 __global__ void gather_nucleus_kernel(DeviceModel d, const double *__restrict__ b, int bstride,
@@ -324,6 +326,55 @@ __global__ void __launch_bounds__(256) pfi_apply_kernel(DeviceModel d, double *_
     pivot_scalars_body(d);
 }
 
+// x_c[p] -= sum_{i<t} W[p][i] * mu_c[i]   (one warp per position, eight loads of the panel row in
+// flight per lane, 64 warps per SM).  pivotTail: the last CTA then evaluates the accuracy gate and
+// the primal step (pivot_scalars_body) on the finished columns.
+template <int NRHS>
+__global__ void __launch_bounds__(256) pfi_apply_warp_kernel(DeviceModel d, double *__restrict__ x, int xstride,
+                                                        bool checkState, bool pivotTail)
+{
+  if (checkState && !iter_active(d.st))
+    return;
+  const int t = d.st->numEtas;
+  if (t > 0) {
+    const int lane = threadIdx.x & 31;
+    const int warpsPerBlock = blockDim.x >> 5;
+    for (int p = blockIdx.x * warpsPerBlock + (threadIdx.x >> 5); p < d.m;
+         p += gridDim.x * warpsPerBlock) {
+      const double *wrow = d.W + (size_t)p * d.tmax;
+      double acc[NRHS];
+#pragma unroll
+      for (int c = 0; c < NRHS; c++)
+        acc[c] = 0.0;
+      for (int i = lane; i < t; i += 256) {
+        double w[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++)
+          w[u] = (i + 32 * u < t) ? __ldcs(wrow + i + 32 * u) : 0.0;
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+          const int ii = min(i + 32 * u, t - 1);
+#pragma unroll
+          for (int c = 0; c < NRHS; c++)
+            acc[c] = fma(w[u], __ldg(d.mu + (size_t)c * d.tmax + ii), acc[c]);
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < NRHS; c++)
+        acc[c] = warp_sum(acc[c]);
+      if (lane == 0)
+        for (int c = 0; c < NRHS; c++)
+          x[(size_t)c * xstride + p] -= acc[c];
+    }
+  }
+  if (!pivotTail)
+    return;
+  if (!last_block_done(d.tailCounter + TAIL_PFI_APPLY))
+    return;
+  if (threadIdx.x == 0)
+    pivot_scalars_body(d);
+}
+
 template <int NRHS>
 static void ftran_impl(const DeviceModel &d, double *b, bool applyEtas, bool checkState,
                        cudaStream_t s, bool pivotTail = false, bool pregathered = false)
@@ -349,10 +400,17 @@ static void ftran_impl(const DeviceModel &d, double *b, bool applyEtas, bool che
   ftran_spread_kernel<NRHS><<<(m * 8 + 255) / 256, 256, 0, s>>>(d, b, m, d.ywork, checkState, applyEtas);
   if (applyEtas) {
     pfi_mu_kernel<NRHS><<<d.tmax, 256, 0, s>>>(d, checkState);
-    int pblocks = (m + 1) / 2;
-    if (pblocks > 148 * 8)
-      pblocks = 148 * 8;
-    pfi_apply_kernel<NRHS><<<pblocks, 256, 0, s>>>(d, b, m, checkState, pivotTail);
+    if (g_pfiApplyVariant == 1) {
+      int pblocks = (m + 1) / 2;
+      if (pblocks > 148 * 8)
+        pblocks = 148 * 8;
+      pfi_apply_kernel<NRHS><<<pblocks, 256, 0, s>>>(d, b, m, checkState, pivotTail);
+    } else {
+      int pblocks = (m + 7) / 8;
+      if (pblocks > 148 * 8)
+        pblocks = 148 * 8;
+      pfi_apply_warp_kernel<NRHS><<<pblocks, 256, 0, s>>>(d, b, m, checkState, pivotTail);
+    }
   }
 }
 

@@ -322,6 +322,22 @@ def test_perturbed_solve_reaches_the_true_optimum(name):
         assert int((s.statusArray() == 1).sum()) == lp.m
 
 
+@pytest.mark.parametrize("name", ["TSP-MTZ-40", "SetCover-100x500", "transport-20x500"])
+def test_kernel_variants_take_the_same_pivots(name):
+    """The cooperative row-pass kernel against the separate row kernels (the capture fallback), and
+    the LDG-direct price kernel against the TMA-staged one: all reductions are order independent,
+    so the solves must be identical (iterations and objective bit for bit)."""
+    lp = load_golden(name)
+    res = []
+    for params in ({}, {"useRowPass": 0}, {"usePriceTma": 1}, {"useRowPass": 0, "useGraph": 0}):
+        s = engine(lp, **params)
+        assert s.dual() == 0, params
+        res.append((s.numberIterations(), s.objectiveValue()))
+    assert res[0] == res[1] == res[3], res
+    # the two price kernels sum a column in different orders: same optimum, maybe other pivots
+    assert abs(res[2][1] - res[0][1]) <= 1e-9 * (1 + abs(res[0][1]))
+
+
 def test_batch_size_does_not_change_result():
     lp = load_golden("TSP-MTZ-20")
     objs = []
