@@ -641,6 +641,11 @@ int Engine::setupDevice()
   CUDA_OK(cudaMemset(d.gridBar, 0, sizeof(unsigned int) * 2));
   d.aqBuf = dalloc<double>(m);
   CUDA_OK(cudaMemset(d.aqBuf, 0, sizeof(double) * m));
+  d.candA = dalloc<double>(nm);
+  d.candD = dalloc<double>(nm);
+  d.candJ = dalloc<int>(nm);
+  d.candCount = dalloc<int>(1);
+  CUDA_OK(cudaMemset(d.candCount, 0, sizeof(int)));
   d.amax = 1.0;
   for (long long e = 0; e < nnz; e++)
     d.amax = std::max(d.amax, std::fabs(wVal[e]));
@@ -767,6 +772,7 @@ void Engine::resetStateForRun()
   CUDA_OK(cudaMemset(d.tailCounter, 0, sizeof(unsigned int) * 16));
   CUDA_OK(cudaMemset(d.gridBar, 0, sizeof(unsigned int) * 2));
   CUDA_OK(cudaMemset(d.aqBuf, 0, sizeof(double) * m));
+  CUDA_OK(cudaMemset(d.candCount, 0, sizeof(int)));
   d.primalTolerance = primalTolerance;
   d.dualTolerance = dualTolerance;
   d.acceptablePivot = acceptablePivot;

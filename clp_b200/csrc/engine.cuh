@@ -145,6 +145,8 @@ struct DeviceModel {
   unsigned int *tailCounter; // [16] last-block-done tickets (one per kernel that has a tail)
   unsigned int *gridBar;     // [2] arrival count / generation of the row-pass grid barrier
   double *aqBuf;      // [m] entering column scattered by the row pass (zero when idle)
+  double *candA, *candD; // [n+m] short list of ratio-test candidates near the crossing bucket
+  int *candJ, *candCount;
   double *mu;         // [3 x tmax]
   double *nu;         // [tmax]
   // ratio test

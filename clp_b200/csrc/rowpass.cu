@@ -13,8 +13,9 @@
 // kernel boundaries; the small scans are done redundantly by every CTA, which saves a barrier.
 //   P0 finalize row + level-1 ratio histogram + per-segment totals      | barrier
 //   P1 crossing bucket (every CTA)  P2 level-2 histogram of that bucket | barrier
-//   P3 theta* (every CTA)           P4 Harris bound (atomicMin)         | barrier
-//   P5 largest |alpha| in [theta*, harris] (atomicMax)                  | barrier
+//   P3 theta* (every CTA)  P4/P5 Harris bound + largest |alpha| in [theta*, harris] from the short
+//      list of the crossing bucket's candidates (every CTA; two more barriers only if the bound
+//      leaves the listed window)
 //   P6 decode winner, dual update + bound flips (unordered list)        | barrier
 //   P8 flip columns -> fixed-point accumulator; entering column -> aqBuf| barrier
 //   P9 three FTRAN right-hand sides rhs3 and their nucleus gather xg
@@ -94,6 +95,7 @@ __device__ __forceinline__ unsigned long long block_max_u64(unsigned long long v
 }
 
 enum : unsigned { F_CAND = 1u, F_BOXED = 2u, F_VALID = 4u };
+constexpr int kWindowBuckets = 1; // level-1 buckets beyond the crossing one kept in the short list
 
 template <int E>
 __global__ void __launch_bounds__(1024, 1) row_pass_kernel(DeviceModel d)
@@ -261,6 +263,17 @@ __global__ void __launch_bounds__(1024, 1) row_pass_kernel(DeviceModel d)
     hist_add_aggregated(d.hist2Weight, sb,
                         in ? slope_weight(aabs[e], (flags[e] & F_BOXED) != 0u, range[e], infeas) : 0ull, in, &sHot);
     hist_min_aggregated(d.hist2Min, sb, bits, in, &sHotMin);
+    // candidates of the crossing bucket and the next one: the short list every CTA scans for the
+    // Harris bound and the pivot (see P4/P5) -- unordered, min/max do not care
+    if (flags[e] & F_CAND) {
+      const int bk = (int)(bits >> 48) & (kHistBuckets - 1);
+      if (bk >= bucket1 && bk <= bucket1 + kWindowBuckets) {
+        const int at = atomicAdd(d.candCount, 1);
+        d.candA[at] = aabs[e];
+        d.candD[at] = dtil[e];
+        d.candJ[at] = gtid + e * gthreads;
+      }
+    }
   }
   __syncthreads();
   if (tid == 0 && sHot != 0ull) {
@@ -347,46 +360,77 @@ __global__ void __launch_bounds__(1024, 1) row_pass_kernel(DeviceModel d)
     }
   }
 
-  // ---------------------------------------------------------------- P4 Harris bound
+  // ---------------------------------------------------------------- P4/P5 Harris bound and pivot
+  // Fast path (no barrier): every CTA scans the short list of the candidates whose ratio lies in
+  // the crossing level-1 bucket or the next kWindowBuckets.  If the Harris bound found there is
+  // below the upper edge U of that window it is the global one -- a candidate outside the list has
+  // ratio >= U (or < theta*), so its own bound (d~+tol)/|alpha| >= U cannot be the minimum -- and
+  // every candidate of [theta*, harris] is in the list, so the largest |alpha| is found there too.
+  // Otherwise (uniform decision) the two global reductions with their grid barriers run.
+  unsigned long long harrisBits, key;
   {
+    const int cnt = __ldcg(d.candCount);
     unsigned long long best = 0x7FF0000000000000ull;
-#pragma unroll
-    for (int e = 0; e < E; e++)
-      if ((flags[e] & F_CAND) && aabs[e] >= d.acceptablePivot && dtil[e] / aabs[e] >= thetaStar)
-        best = min(best, (unsigned long long)__double_as_longlong((dtil[e] + d.dualTolerance) / aabs[e]));
-    best = block_min_u64(best, sU64);
-    if (tid == 0 && best != 0x7FF0000000000000ull)
-      atomicMin(&st->harrisBits, best);
-  }
-  grid_barrier(d.gridBar, barGen);
-
-  // ---------------------------------------------------------------- P5 largest |alpha| in [theta*, harris]
-  const unsigned long long harrisBits = __ldcg(&st->harrisBits);
-  const double harris = __longlong_as_double((long long)harrisBits);
-  {
-    unsigned long long best = 0ull;
-#pragma unroll
-    for (int e = 0; e < E; e++) {
-      if (!(flags[e] & F_CAND) || aabs[e] < d.acceptablePivot)
-        continue;
-      const double ratio = dtil[e] / aabs[e];
-      if (ratio < thetaStar || ratio > harris)
-        continue;
-      const int j = gtid + e * gthreads;
-      best = max(best, ((unsigned long long)__double_as_longlong(aabs[e]) & ~0xFFFFFull) |
-                           (unsigned long long)(0xFFFFF - j));
+    for (int i = tid; i < cnt; i += 1024) {
+      const double a = __ldcg(d.candA + i), dt = __ldcg(d.candD + i);
+      if (a >= d.acceptablePivot && dt / a >= thetaStar)
+        best = min(best, (unsigned long long)__double_as_longlong((dt + d.dualTolerance) / a));
     }
-    best = block_max_u64(best, sU64);
-    if (tid == 0 && best != 0ull)
-      atomicMax(&st->chuzcKey, best);
+    best = block_min_u64(best, sU64);
+    const unsigned long long windowEnd = (unsigned long long)(bucket1 + kWindowBuckets + 1) << 48;
+    if (best < windowEnd && best != 0x7FF0000000000000ull) {
+      harrisBits = best;
+      const double harrisL = __longlong_as_double((long long)best);
+      unsigned long long bk = 0ull;
+      for (int i = tid; i < cnt; i += 1024) {
+        const double a = __ldcg(d.candA + i), dt = __ldcg(d.candD + i);
+        const double ratio = dt / a;
+        if (a >= d.acceptablePivot && ratio >= thetaStar && ratio <= harrisL)
+          bk = max(bk, ((unsigned long long)__double_as_longlong(a) & ~0xFFFFFull) |
+                           (unsigned long long)(0xFFFFF - __ldcg(d.candJ + i)));
+      }
+      key = block_max_u64(bk, sU64);
+    } else {
+      // ---- global Harris bound
+      unsigned long long gb = 0x7FF0000000000000ull;
+#pragma unroll
+      for (int e = 0; e < E; e++)
+        if ((flags[e] & F_CAND) && aabs[e] >= d.acceptablePivot && dtil[e] / aabs[e] >= thetaStar)
+          gb = min(gb, (unsigned long long)__double_as_longlong((dtil[e] + d.dualTolerance) / aabs[e]));
+      gb = block_min_u64(gb, sU64);
+      if (tid == 0 && gb != 0x7FF0000000000000ull)
+        atomicMin(&st->harrisBits, gb);
+      grid_barrier(d.gridBar, barGen);
+      harrisBits = __ldcg(&st->harrisBits);
+      const double harrisG = __longlong_as_double((long long)harrisBits);
+      // ---- global largest |alpha| in [theta*, harris]
+      unsigned long long bk = 0ull;
+#pragma unroll
+      for (int e = 0; e < E; e++) {
+        if (!(flags[e] & F_CAND) || aabs[e] < d.acceptablePivot)
+          continue;
+        const double ratio = dtil[e] / aabs[e];
+        if (ratio < thetaStar || ratio > harrisG)
+          continue;
+        const int j = gtid + e * gthreads;
+        bk = max(bk, ((unsigned long long)__double_as_longlong(aabs[e]) & ~0xFFFFFull) |
+                         (unsigned long long)(0xFFFFF - j));
+      }
+      bk = block_max_u64(bk, sU64);
+      if (tid == 0 && bk != 0ull)
+        atomicMax(&st->chuzcKey, bk);
+      grid_barrier(d.gridBar, barGen);
+      key = __ldcg(&st->chuzcKey);
+    }
   }
-  grid_barrier(d.gridBar, barGen);
+  const double harris = __longlong_as_double((long long)harrisBits);
 
   // ---------------------------------------------------------------- P6 winner, dual update, flips
-  const unsigned long long key = __ldcg(&st->chuzcKey);
   if (key == 0ull) {
-    if (gtid == 0)
+    if (gtid == 0) {
       st->stop = STOP_NO_COLUMN;
+      *d.candCount = 0;
+    }
     return; // uniform
   }
   const int seqIn = 0xFFFFF - (int)(key & 0xFFFFFull);
@@ -483,8 +527,10 @@ __global__ void __launch_bounds__(1024, 1) row_pass_kernel(DeviceModel d)
   // ---------------------------------------------------------------- P9 rhs3 and its nucleus gather
   {
     const double inv = invScale;
-    if (gtid == 0)
+    if (gtid == 0) {
       st->flipMaxBits = 0ull; // every CTA read it before the last barrier
+      *d.candCount = 0;       // the list was last read before barrier 6
+    }
     const int ldk = d.fd->ldk, k = d.fd->k;
     const int maxk8 = (d.m + 7) / 8 * 8;
     double *xg = d.ywork + (size_t)3 * maxk8;
