@@ -96,6 +96,7 @@ __device__ __forceinline__ unsigned long long block_max_u64(unsigned long long v
 
 enum : unsigned { F_CAND = 1u, F_BOXED = 2u, F_VALID = 4u };
 constexpr int kWindowBuckets = 1; // level-1 buckets beyond the crossing one kept in the short list
+constexpr int kListCap = 4096;    // longer lists (degenerate LPs: thousands of ratio-0 ties) take the global path
 
 template <int E>
 __global__ void __launch_bounds__(1024, 1) row_pass_kernel(DeviceModel d)
@@ -269,9 +270,11 @@ __global__ void __launch_bounds__(1024, 1) row_pass_kernel(DeviceModel d)
       const int bk = (int)(bits >> 48) & (kHistBuckets - 1);
       if (bk >= bucket1 && bk <= bucket1 + kWindowBuckets) {
         const int at = atomicAdd(d.candCount, 1);
-        d.candA[at] = aabs[e];
-        d.candD[at] = dtil[e];
-        d.candJ[at] = gtid + e * gthreads;
+        if (at < kListCap) {
+          d.candA[at] = aabs[e];
+          d.candD[at] = dtil[e];
+          d.candJ[at] = gtid + e * gthreads;
+        }
       }
     }
   }
@@ -369,7 +372,8 @@ __global__ void __launch_bounds__(1024, 1) row_pass_kernel(DeviceModel d)
   // Otherwise (uniform decision) the two global reductions with their grid barriers run.
   unsigned long long harrisBits, key;
   {
-    const int cnt = __ldcg(d.candCount);
+    const int cntAll = __ldcg(d.candCount);
+    const int cnt = cntAll <= kListCap ? cntAll : 0;
     unsigned long long best = 0x7FF0000000000000ull;
     for (int i = tid; i < cnt; i += 1024) {
       const double a = __ldcg(d.candA + i), dt = __ldcg(d.candD + i);
@@ -378,7 +382,7 @@ __global__ void __launch_bounds__(1024, 1) row_pass_kernel(DeviceModel d)
     }
     best = block_min_u64(best, sU64);
     const unsigned long long windowEnd = (unsigned long long)(bucket1 + kWindowBuckets + 1) << 48;
-    if (best < windowEnd && best != 0x7FF0000000000000ull) {
+    if (cntAll <= kListCap && best < windowEnd && best != 0x7FF0000000000000ull) {
       harrisBits = best;
       const double harrisL = __longlong_as_double((long long)best);
       unsigned long long bk = 0ull;
