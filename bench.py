@@ -283,8 +283,17 @@ def main():
         dom = max(kern, key=lambda q: kern[q][1])
         b, t_ms = kern[dom]
         ach = b / (t_ms * 1e-3) / 1e9 if t_ms > 0 else 0.0
+        # DRAM bytes per launch of that kernel from the committed ncu --set full capture (same
+        # workload, same nucleus size); null when the nucleus differs from the captured one
+        traffic, traffic_src = None, None
+        tp = os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")
+        if os.path.exists(tp):
+            rec = json.load(open(tp)).get(dom)
+            if rec and int(rec.get("nucleus_size", -1)) == int(k):
+                traffic, traffic_src = rec["traffic"], rec["source"]
         result["roofline"] = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
-                              "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                              "frac": ach / peak, "traffic": traffic, "traffic_source": traffic_src,
+                              "peak_source": peak_src,
                               "bytes_per_launch": b, "ms_per_launch": t_ms, "nucleus_size": k,
                               "all": {q: {"bytes": v[0], "ms": v[1], "GBps": (v[0] / (v[1] * 1e-3) / 1e9 if v[1] > 0 else 0.0)}
                                       for q, v in kern.items()},

@@ -1370,6 +1370,17 @@ int Engine::dual()
           problemStatus = 4;
         break;
       }
+      // the reference only believes "no entering column" on fresh factors once the acceptable
+      // pivot has been relaxed to 1e-8 (ClpSimplexDual.cpp:1882-1884, :2072-2074): retry the same
+      // row with the smaller tolerance before declaring the problem primal infeasible
+      if (d.acceptablePivot > 1.0e-8) {
+        d.acceptablePivot = 1.0e-8;
+        if (iterGraph) { // kernel arguments are captured by value
+          cudaGraphExecDestroy(iterGraph);
+          iterGraph = nullptr;
+        }
+        break;
+      }
       problemStatus = 1;
       break;
     }
