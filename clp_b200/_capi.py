@@ -35,6 +35,7 @@ SIGNATURES = {
     "Clpb_setParameter": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_double]),
     "Clpb_scaling": (None, [ctypes.c_void_p, ctypes.c_int]),
     "Clpb_scaleFactors": (ctypes.c_int, [ctypes.c_void_p, c_double_p, c_double_p]),
+    "Clpb_perturbedCosts": (ctypes.c_int, [ctypes.c_void_p, c_double_p]),
     "Clpb_copyinStatus": (None, [ctypes.c_void_p, c_ubyte_p]),
     "Clpb_dual": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "Clpb_status": (ctypes.c_int, [ctypes.c_void_p]),

@@ -167,6 +167,13 @@ int Clpb_scaleFactors(Clpb_Simplex *model, double *rowScale, double *columnScale
     columnScale[j] = rc == 0 ? e.columnScale[j] : 1.0;
   return rc;
 }
+int Clpb_perturbedCosts(Clpb_Simplex *model, double *cost)
+{
+  // host only: what ClpSimplexDual::perturb would make of the objective for the current status
+  clpb::Engine &e = model->e;
+  const int rc = e.previewPerturbation(cost);
+  return rc;
+}
 void Clpb_copyinStatus(Clpb_Simplex *model, const unsigned char *statusArray)
 {
   model->e.setStatus(statusArray);

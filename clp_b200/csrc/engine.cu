@@ -510,6 +510,26 @@ int Engine::perturbCosts(std::vector<double> &cost) const
   return 0;
 }
 
+// Host-only preview used by the CPU test-suite: builds the working problem (scaling included),
+// normalises the status array the way resetStateForRun does, and applies perturbCosts.
+int Engine::previewPerturbation(double *costOut)
+{
+  prepareWorkingProblem();
+  int nBasic = 0;
+  for (int j = 0; j < nm; j++)
+    if (hStatus[j] == basic)
+      nBasic++;
+  if (nBasic != m) {
+    hStatus.assign(nm, atLowerBound);
+    for (int i = 0; i < m; i++)
+      hStatus[n + i] = basic;
+  }
+  std::vector<double> pc(wCost.begin(), wCost.begin() + n);
+  const int rc = perturbCosts(pc);
+  std::copy(pc.begin(), pc.end(), costOut);
+  return rc;
+}
+
 int Engine::setupDevice()
 {
   if (deviceReady)

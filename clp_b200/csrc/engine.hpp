@@ -57,6 +57,7 @@ public:
   // benchmark configuration states "perturbation off").  ClpSimplexDual::perturb, :6533.
   int perturbation = 102;
   int perturbCosts(std::vector<double> &cost) const; // 0 = perturbed (cost[n] modified in place)
+  int previewPerturbation(double *costOut);          // host only (no device): scaled working costs after perturb
   double largestPerturbation = 0.0;
   // column sharding of the pricing pass (multi-GPU): this rank prices [colBegin,colEnd)
   int rank = 0, worldSize = 1;

@@ -121,6 +121,12 @@ class ClpSimplex:
         """ClpSimplex::setPerturbation: 50 perturb costs, 100 automatic, 102 off (default here)."""
         self._set("perturbation", value)
 
+    def perturbedCosts(self):
+        """(rc, cost[n]) -- host-only preview of ClpSimplexDual::perturb for the current settings."""
+        c = np.zeros(self.numberColumns())
+        rc = self._L.Clpb_perturbedCosts(self._h, _dp(c))
+        return rc, c
+
     def scaling(self, mode):
         """ClpModel::scaling(mode): 0 off, 1 equilibrium, 2 geometric, 3 automatic, 4 dynamic."""
         self._L.Clpb_scaling(self._h, int(mode))

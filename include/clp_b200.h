@@ -57,6 +57,10 @@ int Clpb_setParameter(Clpb_Simplex *model, const char *key, double value);
    in the caller's units. */
 void Clpb_scaling(Clpb_Simplex *model, int mode);
 int Clpb_scaleFactors(Clpb_Simplex *model, double *rowScale, double *columnScale);
+/* Host-only preview of ClpSimplexDual::perturb (src/ClpSimplexDual.cpp:6533) for the current
+   "perturbation" setting and status: cost[n] = the (scaled) working objective after perturbation.
+   Returns 0 if costs were perturbed, 1 if the rule decided not to (copy of the objective). */
+int Clpb_perturbedCosts(Clpb_Simplex *model, double *cost);
 /* Clp_copyinStatus :280 : status[n+m], columns first */
 void Clpb_copyinStatus(Clpb_Simplex *model, const unsigned char *statusArray);
 /* Clp_dual :346 (ClpSimplex::dual src/ClpSimplex.cpp:5631).  Returns Clp_status :212:

@@ -124,6 +124,35 @@ def test_scale_factors_match_restatement(mode):
     assert scaled >= 6
 
 
+def test_perturbation_rule_properties():
+    """Engine::perturbCosts (ClpSimplexDual::perturb :6533, default setting 50) on the host: only
+    non-fixed nonbasic columns move, towards the dual feasible side of their bound (up at lower
+    bound), by at most max(1e3*dualTolerance, maximumFraction*average cost); deterministic; and the automatic
+    setting (100) leaves LPs with many distinct cost values alone (:6575)."""
+    import clp_b200
+
+    for name in ("transport-20x500", "NQueens-20", "UFL-20x60", "staircase-480"):
+        lp = load_golden(name)
+        s = clp_b200.ClpSimplex(); s.loadLP(lp); s.setPerturbation(50)
+        rc, pc = s.perturbedCosts()
+        rc2, pc2 = s.perturbedCosts()
+        assert rc == rc2 == 0 and np.array_equal(pc, pc2), name
+        delta = pc - lp.objective
+        moved = delta != 0.0
+        assert moved.any(), name
+        fixed = lp.col_upper <= lp.col_lower
+        assert not (moved & fixed).any(), name
+        assert (delta[moved] > 0).all(), name  # all-slack start: every column sits at its lower bound
+        nz = np.abs(lp.objective[lp.objective != 0])
+        avg = nz.mean() if nz.size else 1.0
+        # largestAllowed = max(1e3*dualTolerance, maximumFraction*averageCost) with maximumFraction <= 1e-3 (:6709, :6803)
+        assert np.abs(delta).max() <= max(1e-4, 1e-3 * avg) * 1.0001, name
+    lp = G.random_sparse_lp(200, 2000, 0.03, 5)  # 2000 distinct costs: automatic mode does nothing
+    s = clp_b200.ClpSimplex(); s.loadLP(lp); s.setPerturbation(100)
+    rc, pc = s.perturbedCosts()
+    assert rc == 1 and np.array_equal(pc, lp.objective)
+
+
 def test_cabi_exports_every_declared_symbol():
     from clp_b200 import _capi
 
