@@ -213,7 +213,7 @@ void Clpb_statusArray(Clpb_Simplex *model, unsigned char *st)
 }
 double Clpb_secondsInLoop(Clpb_Simplex *model) { return model->e.secondsInLoop; }
 long long Clpb_kernelLaunches(Clpb_Simplex *model) { return model->e.kernelLaunches; }
-void Clpb_phaseTimes(Clpb_Simplex *model, double *o /* 12 */)
+void Clpb_phaseTimes(Clpb_Simplex *model, double *o /* 14 */)
 {
   const clpb::PhaseTimes &p = model->e.phase;
   o[0] = p.chuzr;
@@ -228,6 +228,8 @@ void Clpb_phaseTimes(Clpb_Simplex *model, double *o /* 12 */)
   o[9] = p.priceKernel;
   o[10] = p.ftranGemv;
   o[11] = p.btranGemv;
+  o[12] = p.ftranGemvBytes;
+  o[13] = p.btranGemvBytes;
 }
 int Clpb_nucleusSize(Clpb_Simplex *model) { return model->e.lastNucleusSize; }
 void Clpb_timedWindow(Clpb_Simplex *model, double *milliseconds, int *iterations)

@@ -1299,6 +1299,8 @@ int Engine::dual()
         phase.priceKernel += k0;
         phase.ftranGemv += k1;
         phase.btranGemv += k2;
+        phase.ftranGemvBytes += 8.0 * d.k * d.ldk + 48.0 * d.k;
+        phase.btranGemvBytes += 8.0 * d.k * d.ldk + 16.0 * d.k;
         phase.samples++;
       }
     }

@@ -17,6 +17,7 @@ struct PhaseTimes { // accumulated device milliseconds per phase (when timing is
   double chuzr = 0, btran = 0, price = 0, chuzc = 0, dualUpdate = 0, ftran = 0, update = 0,
          refactor = 0;
   double priceKernel = 0, ftranGemv = 0, btranGemv = 0; // single kernels inside the phases
+  double ftranGemvBytes = 0, btranGemvBytes = 0;        // algorithmic bytes of those launches (the nucleus size changes at a refactorization)
   long samples = 0;
 };
 

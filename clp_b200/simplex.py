@@ -167,10 +167,10 @@ class ClpSimplex:
         return ms.value, it.value
 
     def phaseTimes(self):
-        o = np.zeros(12)
+        o = np.zeros(14)
         self._L.Clpb_phaseTimes(self._h, _dp(o))
         keys = ["chuzr", "btran", "price", "chuzc", "dualUpdate", "ftran", "update", "refactor", "samples",
-                "priceKernel", "ftranGemv", "btranGemv"]
+                "priceKernel", "ftranGemv", "btranGemv", "ftranGemvBytes", "btranGemvBytes"]
         return dict(zip(keys, o.tolist()))
 
     def _vec(self, fn, size, dtype=np.float64):

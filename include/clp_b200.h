@@ -81,10 +81,11 @@ void Clpb_dualRowSolution(Clpb_Simplex *model, double *rowPrice /* m */);
 void Clpb_statusArray(Clpb_Simplex *model, unsigned char *status /* n+m */);
 /* measurement: seconds in the iteration loop, kernels launched, per-phase device ms
    (order: chuzr, btran, price, chuzc, dualUpdate, ftran, update, refactor, samples, then the
-   single kernels priceKernel, ftranGemv, btranGemv; 12 doubles) */
+   single kernels priceKernel, ftranGemv, btranGemv, then the algorithmic bytes summed over the
+   timed FTRAN / BTRAN GEMV launches; 14 doubles) */
 double Clpb_secondsInLoop(Clpb_Simplex *model);
 long long Clpb_kernelLaunches(Clpb_Simplex *model);
-void Clpb_phaseTimes(Clpb_Simplex *model, double *out12);
+void Clpb_phaseTimes(Clpb_Simplex *model, double *out14);
 int Clpb_nucleusSize(Clpb_Simplex *model);
 /* CUDA-event time (on the engine's stream) and iteration count of the window that starts after
    "warmupIterations" iterations and ends when Clpb_dual returns (refactorizations included) */
