@@ -338,6 +338,20 @@ def test_kernel_variants_take_the_same_pivots(name):
     assert abs(res[2][1] - res[0][1]) <= 1e-9 * (1 + abs(res[0][1]))
 
 
+def test_long_row_uses_multi_entry_row_pass():
+    """n+m above 148*1024: every thread of the cooperative row kernel owns two entries of the
+    tableau row (row_pass_kernel<2>); same optimum as the planted solution and as the separate
+    kernels."""
+    lp = G.random_sparse_lp(500, 170000, 0.02, 31)
+    s = engine(lp)
+    assert s.dual() == 0
+    assert abs(s.objectiveValue() - lp.known_objective) <= 1e-8 * (1 + abs(lp.known_objective))
+    assert kkt(lp, s) == 0
+    s2 = engine(lp, useRowPass=0)
+    assert s2.dual() == 0
+    assert (s2.numberIterations(), s2.objectiveValue()) == (s.numberIterations(), s.objectiveValue())
+
+
 def test_batch_size_does_not_change_result():
     lp = load_golden("TSP-MTZ-20")
     objs = []
