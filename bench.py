@@ -302,7 +302,8 @@ def main():
                 capture = {"nucleus_size": kc, "algorithmic_bytes": cap, "traffic": rec["traffic"],
                            "traffic_over_algorithmic": rec["traffic"] / cap, "source": rec["source"]}
         result["roofline"] = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
-                              "frac": ach / peak, "traffic": traffic, "traffic_source": traffic_src,
+                              "frac": ach / peak, "frac_of_nominal_8TBps": ach / 8000.0, "traffic": traffic,
+                              "traffic_source": traffic_src,
                               "traffic_capture": capture,
                               "peak_source": peak_src,
                               "bytes_per_launch": b, "ms_per_launch": t_ms, "nucleus_size": k,
