@@ -37,6 +37,8 @@ SIGNATURES = {
     "Clpb_scaleFactors": (ctypes.c_int, [ctypes.c_void_p, c_double_p, c_double_p]),
     "Clpb_perturbedCosts": (ctypes.c_int, [ctypes.c_void_p, c_double_p]),
     "Clpb_copyinStatus": (None, [ctypes.c_void_p, c_ubyte_p]),
+    "Clpb_writeBasis": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int, ctypes.c_int]),
+    "Clpb_readBasis": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p]),
     "Clpb_dual": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "Clpb_status": (ctypes.c_int, [ctypes.c_void_p]),
     "Clpb_objectiveValue": (ctypes.c_double, [ctypes.c_void_p]),

@@ -210,7 +210,14 @@ void Clpb_statusArray(Clpb_Simplex *model, unsigned char *st)
 {
   if (!model->e.status.empty())
     std::copy(model->e.status.begin(), model->e.status.end(), st);
+  else // before a solve: the status handed in (copyinStatus / readBasis) or the all-slack default
+    std::copy(model->e.currentStatus().begin(), model->e.currentStatus().end(), st);
 }
+int Clpb_writeBasis(Clpb_Simplex *model, const char *filename, int, int)
+{
+  return model->e.writeBasis(filename);
+}
+int Clpb_readBasis(Clpb_Simplex *model, const char *filename) { return model->e.readBasis(filename); }
 double Clpb_secondsInLoop(Clpb_Simplex *model) { return model->e.secondsInLoop; }
 long long Clpb_kernelLaunches(Clpb_Simplex *model) { return model->e.kernelLaunches; }
 void Clpb_phaseTimes(Clpb_Simplex *model, double *o /* 14 */)

@@ -530,6 +530,93 @@ int Engine::previewPerturbation(double *costOut)
   return rc;
 }
 
+// MPS basis file, restating ClpSimplexOther::writeBasis (src/ClpSimplexOther.cpp:1018-1133, the
+// branch without names and without values): every basic column is paired with the next nonbasic
+// row -- "XU Cj Ri" if that row sits at its upper bound, "XL Cj Ri" otherwise; "UL Cj" marks a
+// nonbasic column at its upper bound; everything not mentioned is a column at lower bound / a
+// basic row.
+int Engine::writeBasis(const char *fileName) const
+{
+  FILE *fp = fopen(fileName, "w");
+  if (!fp)
+    return -1;
+  fprintf(fp, "NAME          %s       \n", problemName.empty() ? "BLANK" : problemName.c_str());
+  int iRow = 0;
+  for (int j = 0; j < n; j++) {
+    if (hStatus[j] == basic) {
+      for (; iRow < m; iRow++)
+        if (hStatus[n + iRow] != basic)
+          break;
+      if (iRow != m) {
+        fprintf(fp, " %s C%7.7d     R%7.7d\n", hStatus[n + iRow] == atUpperBound ? "XU" : "XL", j, iRow);
+        iRow++;
+      } else {
+        fprintf(fp, " BS C%7.7d\n", j); // too many basics
+      }
+    } else if (hStatus[j] == atUpperBound) {
+      fprintf(fp, " UL C%7.7d\n", j);
+    }
+  }
+  fprintf(fp, "ENDATA\n");
+  fclose(fp);
+  return 0;
+}
+
+// The reader side lives in CoinMpsIO::readBasis (CoinUtils, not in the reference tree; call site
+// src/ClpSimplexOther.cpp:1155).  Standard MPS basis semantics: start from "all columns at lower
+// bound, all rows basic"; XU/XL make the column basic and the row nonbasic at upper/lower; UL/LL
+// put a column at its upper/lower bound; BS makes a column basic.  Returns 0, -1 (cannot open) or
+// the number of records that could not be interpreted.
+int Engine::readBasis(const char *fileName)
+{
+  FILE *fp = fopen(fileName, "r");
+  if (!fp)
+    return -1;
+  std::vector<unsigned char> st(nm, atLowerBound);
+  for (int i = 0; i < m; i++)
+    st[n + i] = basic;
+  auto index = [](const char *name, char kind, int limit) {
+    if (name[0] != kind)
+      return -1;
+    char *end = nullptr;
+    long v = strtol(name + 1, &end, 10);
+    if (end == name + 1 || v < 0 || v >= limit)
+      return -1;
+    return (int)v;
+  };
+  char line[512];
+  int bad = 0;
+  while (fgets(line, sizeof(line), fp)) {
+    char key[16] = "", a[64] = "", b[64] = "";
+    const int got = sscanf(line, "%15s %63s %63s", key, a, b);
+    if (got < 1 || !strcmp(key, "NAME"))
+      continue;
+    if (!strcmp(key, "ENDATA"))
+      break;
+    const int j = got >= 2 ? index(a, 'C', n) : -1;
+    if (!strcmp(key, "XU") || !strcmp(key, "XL")) {
+      const int i = got >= 3 ? index(b, 'R', m) : -1;
+      if (j < 0 || i < 0) {
+        bad++;
+        continue;
+      }
+      st[j] = basic;
+      st[n + i] = key[1] == 'U' ? atUpperBound : atLowerBound;
+    } else if (!strcmp(key, "UL") || !strcmp(key, "LL") || !strcmp(key, "BS")) {
+      if (j < 0) {
+        bad++;
+        continue;
+      }
+      st[j] = key[0] == 'U' ? atUpperBound : key[0] == 'L' ? atLowerBound : basic;
+    } else {
+      bad++;
+    }
+  }
+  fclose(fp);
+  setStatus(st.data());
+  return bad;
+}
+
 int Engine::setupDevice()
 {
   if (deviceReady)

@@ -82,6 +82,11 @@ public:
   std::vector<unsigned char> status; // n+m
   std::vector<int> pivotVariable;   // m
   void setStatus(const unsigned char *st);
+  // ClpSimplex::writeBasis / readBasis (src/ClpSimplex.cpp:6569,6577 -> ClpSimplexOther.cpp:1018,1136):
+  // MPS basis file in the reference's no-names form (C%7.7d / R%7.7d), host only
+  int writeBasis(const char *fileName) const;
+  int readBasis(const char *fileName);
+  const std::vector<unsigned char> &currentStatus() const { return hStatus; }
 
   // ---- plug-in level entry points (parity tests; host buffers) ----
   int factorize(const int *basicSequence, int *pivotVariableOut);

@@ -141,6 +141,13 @@ class ClpSimplex:
         st = np.ascontiguousarray(status, dtype=np.uint8)
         self._L.Clpb_copyinStatus(self._h, _up(st))
 
+    # ---- ClpSimplex::writeBasis / readBasis ----
+    def writeBasis(self, fileName, writeValues=False, formatType=0):
+        return self._L.Clpb_writeBasis(self._h, str(fileName).encode(), int(writeValues), int(formatType))
+
+    def readBasis(self, fileName):
+        return self._L.Clpb_readBasis(self._h, str(fileName).encode())
+
     # ---- ClpSimplex::dual ----
     def dual(self, ifValuesPass=0):
         rc = self._L.Clpb_dual(self._h, int(ifValuesPass))

@@ -63,6 +63,13 @@ int Clpb_scaleFactors(Clpb_Simplex *model, double *rowScale, double *columnScale
 int Clpb_perturbedCosts(Clpb_Simplex *model, double *cost);
 /* Clp_copyinStatus :280 : status[n+m], columns first */
 void Clpb_copyinStatus(Clpb_Simplex *model, const unsigned char *statusArray);
+/* ClpSimplex::writeBasis / readBasis (src/ClpSimplex.cpp:6569 / :6577 -> ClpSimplexOther.cpp:1018 /
+   :1136): MPS basis file (XU/XL/UL/LL/BS records) in the reference's no-names form C%7.7d / R%7.7d;
+   writeValues / formatType are accepted for signature compatibility, values are not written.
+   readBasis returns 0, -1 (cannot open) or the number of records it could not interpret; the basis
+   becomes the starting basis of the next Clpb_dual (like Clpb_copyinStatus).  Host only. */
+int Clpb_writeBasis(Clpb_Simplex *model, const char *filename, int writeValues, int formatType);
+int Clpb_readBasis(Clpb_Simplex *model, const char *filename);
 /* Clp_dual :346 (ClpSimplex::dual src/ClpSimplex.cpp:5631).  Returns Clp_status :212:
    0 optimal, 1 primal infeasible, 2 dual infeasible, 3 stopped on iterations/time,
    4 stopped due to errors. */

@@ -153,6 +153,38 @@ def test_perturbation_rule_properties():
     assert rc == 1 and np.array_equal(pc, lp.objective)
 
 
+def test_basis_file_round_trip(tmp_path):
+    """ClpSimplex::writeBasis / readBasis (ClpSimplexOther.cpp:1018): the optimal basis of the CPU
+    oracle written in the reference's no-names format and read back into a fresh model."""
+    import clp_b200
+    from oracle.oracle import OracleSimplex
+
+    lp = load_golden("UFL-10x30")
+    o = OracleSimplex(lp)
+    assert o.dual() == 0
+    st = np.asarray(o.status(), dtype=np.uint8)
+    st[(st != 1) & (st != 2)] = 3  # the file distinguishes basic / at upper / everything else
+    s = clp_b200.ClpSimplex(); s.loadLP(lp); s.copyinStatus(st)
+    f = tmp_path / "opt.bas"
+    assert s.writeBasis(f) == 0
+    text = f.read_text().splitlines()
+    assert text[0].startswith("NAME") and text[-1] == "ENDATA"
+    nb_cols = int((st[: lp.n] == 1).sum())
+    assert sum(l.startswith((" XU", " XL")) for l in text) == nb_cols
+    assert all(len(l.split()) == 3 and l.split()[1][0] == "C" and l.split()[2][0] == "R" for l in text if l.startswith(" X"))
+    t = clp_b200.ClpSimplex(); t.loadLP(lp)
+    assert t.readBasis(f) == 0
+    back = t.statusArray()
+    assert np.array_equal(back == 1, st == 1)                      # same basic set
+    assert np.array_equal(back[: lp.n] == 2, st[: lp.n] == 2)     # same columns at upper bound
+    nonbasic_rows = st[lp.n:] != 1
+    assert np.array_equal(back[lp.n:][nonbasic_rows] == 2, st[lp.n:][nonbasic_rows] == 2)
+    assert t.readBasis(tmp_path / "missing.bas") == -1
+    g = tmp_path / "bad.bas"
+    g.write_text("NAME x\n XU C0000001 R9999999\n ZZ C0000001\nENDATA\n")
+    assert t.readBasis(g) == 2
+
+
 def test_cabi_exports_every_declared_symbol():
     from clp_b200 import _capi
 
