@@ -86,6 +86,12 @@ int Clpb_readMps(Clpb_Simplex *model, const char *filename, int, int)
 {
   return guarded([&] { return model->e.readMps(filename); });
 }
+int Clpb_writeMps(Clpb_Simplex *model, const char *filename, int, int, double)
+{
+  clpb::Engine &e = model->e;
+  return clpb::writeMpsFile(filename, e.m, e.n, e.hColStart, e.hRow, e.hVal, e.hLower, e.hUpper, e.hCost,
+                            e.objectiveOffset, e.problemName);
+}
 int Clpb_numberRows(Clpb_Simplex *model) { return model->e.numberRows(); }
 int Clpb_numberColumns(Clpb_Simplex *model) { return model->e.numberColumns(); }
 long long Clpb_getNumElements(Clpb_Simplex *model)

@@ -169,4 +169,9 @@ int readMpsFile(const char *fileName, int &m, int &n, std::vector<int> &colStart
                 std::vector<double> &rowLower, std::vector<double> &rowUpper, double &objOffset,
                 std::string &name);
 
+int writeMpsFile(const char *fileName, int m, int n, const std::vector<int> &colStart,
+                 const std::vector<int> &row, const std::vector<double> &val,
+                 const std::vector<double> &lower, const std::vector<double> &upper,
+                 const std::vector<double> &cost, double objOffset, const std::string &name);
+
 } // namespace clpb

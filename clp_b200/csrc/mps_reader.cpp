@@ -300,4 +300,83 @@ int readMpsFile(const char *fileName, int &m, int &n, std::vector<int> &colStart
   return 0;
 }
 
+// ClpModel::writeMps (/root/reference/src/ClpModel.cpp:3986 -> CoinMpsIO::writeMps, CoinUtils) for
+// the model as loaded: default names R%7.7d / C%7.7d (what Clp uses when a model has none), one
+// entry per line, 17 significant digits (formatType 1, "extra accuracy").  Row types: E (equal
+// bounds), L / G (one finite bound), L + RANGES (both finite), N (free row: the reader, like
+// CoinMpsIO, drops such rows).  Column bounds: default [0, inf) is not written; FR, MI(+UP), FX,
+// LO, UP otherwise.  objOffset goes to the RHS of the objective row, negated.
+int writeMpsFile(const char *fileName, int m, int n, const std::vector<int> &colStart,
+                 const std::vector<int> &row, const std::vector<double> &val,
+                 const std::vector<double> &lower, const std::vector<double> &upper,
+                 const std::vector<double> &cost, double objOffset, const std::string &name)
+{
+  FILE *fp = fopen(fileName, "w");
+  if (!fp)
+    return -1;
+  fprintf(fp, "NAME          %s\nROWS\n N  OBJROW\n", name.empty() ? "BLANK" : name.c_str());
+  std::vector<char> type(m);
+  for (int i = 0; i < m; i++) {
+    const double lo = lower[n + i], up = upper[n + i];
+    const bool flo = lo > -kInf, fup = up < kInf;
+    type[i] = (flo && fup) ? (lo == up ? 'E' : 'L') : fup ? 'L' : flo ? 'G' : 'N';
+    fprintf(fp, " %c  R%7.7d\n", type[i], i);
+  }
+  fprintf(fp, "COLUMNS\n");
+  for (int j = 0; j < n; j++) {
+    if (cost[j] != 0.0 || colStart[j + 1] == colStart[j])
+      fprintf(fp, "    C%7.7d  OBJROW    %.17g\n", j, cost[j]);
+    for (int e = colStart[j]; e < colStart[j + 1]; e++)
+      fprintf(fp, "    C%7.7d  R%7.7d  %.17g\n", j, row[e], val[e]);
+  }
+  fprintf(fp, "RHS\n");
+  if (objOffset != 0.0)
+    fprintf(fp, "    RHS       OBJROW    %.17g\n", -objOffset);
+  for (int i = 0; i < m; i++) {
+    const double rhs = type[i] == 'G' ? lower[n + i] : type[i] == 'N' ? 0.0 : upper[n + i];
+    if (rhs != 0.0)
+      fprintf(fp, "    RHS       R%7.7d  %.17g\n", i, rhs);
+  }
+  bool anyRange = false;
+  for (int i = 0; i < m; i++)
+    if (type[i] == 'L' && lower[n + i] > -kInf) {
+      if (!anyRange)
+        fprintf(fp, "RANGES\n");
+      anyRange = true;
+      fprintf(fp, "    RANGE     R%7.7d  %.17g\n", i, upper[n + i] - lower[n + i]);
+    }
+  bool anyBound = false;
+  auto head = [&]() {
+    if (!anyBound)
+      fprintf(fp, "BOUNDS\n");
+    anyBound = true;
+  };
+  for (int j = 0; j < n; j++) {
+    const double lo = lower[j], up = upper[j];
+    const bool flo = lo > -kInf, fup = up < kInf;
+    if (!flo && !fup) {
+      head();
+      fprintf(fp, " FR BOUND     C%7.7d\n", j);
+    } else if (flo && fup && lo == up) {
+      head();
+      fprintf(fp, " FX BOUND     C%7.7d  %.17g\n", j, lo);
+    } else {
+      if (!flo) {
+        head();
+        fprintf(fp, " MI BOUND     C%7.7d\n", j);
+      } else if (lo != 0.0) {
+        head();
+        fprintf(fp, " LO BOUND     C%7.7d  %.17g\n", j, lo);
+      }
+      if (fup) {
+        head();
+        fprintf(fp, " UP BOUND     C%7.7d  %.17g\n", j, up);
+      }
+    }
+  }
+  fprintf(fp, "ENDATA\n");
+  fclose(fp);
+  return 0;
+}
+
 } // namespace clpb

@@ -83,6 +83,9 @@ class ClpSimplex:
     def readMps(self, fileName, keepNames=False, ignoreErrors=False):
         return self._L.Clpb_readMps(self._h, str(fileName).encode(), int(keepNames), int(ignoreErrors))
 
+    def writeMps(self, fileName, formatType=1, numberAcross=1, objSense=0.0):
+        return self._L.Clpb_writeMps(self._h, str(fileName).encode(), int(formatType), int(numberAcross), float(objSense))
+
     def numberRows(self):
         return self._L.Clpb_numberRows(self._h)
 

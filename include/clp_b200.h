@@ -33,6 +33,11 @@ int Clpb_loadProblem(Clpb_Simplex *model, int numcols, int numrows, const int *s
                      const double *rowub);
 /* Clp_readMps :116 (ClpModel::readMps src/ClpModel.cpp:2884) */
 int Clpb_readMps(Clpb_Simplex *model, const char *filename, int keepNames, int ignoreErrors);
+/* Clp_writeMps :120 (ClpModel::writeMps src/ClpModel.cpp:3986): the model as loaded, default names
+   R%7.7d / C%7.7d, 17 significant digits; formatType / numberAcross / objSense are accepted for
+   signature compatibility.  0 ok, -1 cannot open.  Host only. */
+int Clpb_writeMps(Clpb_Simplex *model, const char *filename, int formatType, int numberAcross,
+                  double objSense);
 /* Clp_numberRows :174, Clp_numberColumns :176, Clp_getNumElements :246 */
 int Clpb_numberRows(Clpb_Simplex *model);
 int Clpb_numberColumns(Clpb_Simplex *model);
