@@ -611,6 +611,78 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+
+// ---- eta panel apply: x_c[p] -= sum_{i<t} W[p][i] * mu_c[i], W row-major m x tmax (round-2 candidates)
+template <int NRHS, int DEPTH>
+__global__ void __launch_bounds__(256) panel_warp8(const double *__restrict__ W, int m, int tmax, int t,
+                                                   const double *__restrict__ mu, double *__restrict__ x)
+{
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  for (int p = blockIdx.x * wpb + (threadIdx.x >> 5); p < m; p += gridDim.x * wpb) {
+    const double *wrow = W + (size_t)p * tmax;
+    double acc[NRHS];
+#pragma unroll
+    for (int c = 0; c < NRHS; c++) acc[c] = 0.0;
+    for (int i = lane; i < t; i += 32 * DEPTH) {
+      double w[DEPTH];
+#pragma unroll
+      for (int u = 0; u < DEPTH; u++) w[u] = (i + 32 * u < t) ? __ldcs(wrow + i + 32 * u) : 0.0;
+#pragma unroll
+      for (int u = 0; u < DEPTH; u++) {
+        const int ii = min(i + 32 * u, t - 1);
+#pragma unroll
+        for (int c = 0; c < NRHS; c++) acc[c] = fma(w[u], __ldg(mu + (size_t)c * tmax + ii), acc[c]);
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < NRHS; c++) acc[c] = warp_sum(acc[c]);
+    if (lane == 0)
+      for (int c = 0; c < NRHS; c++) x[(size_t)c * m + p] -= acc[c];
+  }
+}
+// same with 16-byte loads and mu staged in shared memory
+template <int NRHS, int DEPTH>
+__global__ void __launch_bounds__(256) panel_warp16_smem(const double *__restrict__ W, int m, int tmax, int t,
+                                                         const double *__restrict__ mu, double *__restrict__ x)
+{
+  extern __shared__ __align__(16) unsigned char rawmu[];
+  double *smu = reinterpret_cast<double *>(rawmu); // [NRHS][tpad]
+  const int tpad = (t + 1) & ~1;
+  for (int i = threadIdx.x; i < tpad; i += blockDim.x)
+#pragma unroll
+    for (int c = 0; c < NRHS; c++) smu[c * tpad + i] = i < t ? mu[(size_t)c * tmax + i] : 0.0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  const int half = tpad >> 1;
+  for (int p = blockIdx.x * wpb + (threadIdx.x >> 5); p < m; p += gridDim.x * wpb) {
+    const double2 *wrow = reinterpret_cast<const double2 *>(W + (size_t)p * tmax);
+    double acc[NRHS];
+#pragma unroll
+    for (int c = 0; c < NRHS; c++) acc[c] = 0.0;
+    for (int i = lane; i < half; i += 32 * DEPTH) {
+      double2 w[DEPTH];
+#pragma unroll
+      for (int u = 0; u < DEPTH; u++) w[u] = (i + 32 * u < half) ? __ldcs(wrow + i + 32 * u) : make_double2(0.0, 0.0);
+#pragma unroll
+      for (int u = 0; u < DEPTH; u++) {
+        const int ii = min(i + 32 * u, half - 1);
+#pragma unroll
+        for (int c = 0; c < NRHS; c++) {
+          const double2 mv = reinterpret_cast<const double2 *>(smu + c * tpad)[ii];
+          acc[c] = fma(w[u].x, mv.x, acc[c]);
+          acc[c] = fma((2 * ii + 1 < t) ? w[u].y : 0.0, mv.y, acc[c]);
+        }
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < NRHS; c++) acc[c] = warp_sum(acc[c]);
+    if (lane == 0)
+      for (int c = 0; c < NRHS; c++) x[(size_t)c * m + p] -= acc[c];
+  }
+}
+
 // naive reference: warp per column
 __global__ void price_ref(const int *__restrict__ rowIdx, const double *__restrict__ val, const int *__restrict__ colStart,
                           const double *__restrict__ rho, int n, double *__restrict__ alpha)
@@ -1120,6 +1192,57 @@ int main(int argc, char **argv)
     RUN_BIG(4096, 4, int, false, dIdx);
     RUN_BIG(3072, 6, int, false, dIdx);
     RUN_BIG(3072, 7, unsigned short, false, dIdx16);
+  }
+
+  // ------------------------------------------------------------------ eta panel apply (round-2 candidates)
+  if (which & 64) {
+    const int m = 10000, tmax = 2048, NW = 4;
+    double *W, *mu, *x;
+    CK(cudaMalloc(&W, sizeof(double) * (size_t)NW * m * tmax));
+    CK(cudaMalloc(&mu, sizeof(double) * 3 * tmax));
+    CK(cudaMalloc(&x, sizeof(double) * 3 * m));
+    std::vector<double> hW((size_t)m * tmax), hmu(3 * tmax);
+    for (auto &v : hW) v = U(rng);
+    for (auto &v : hmu) v = U(rng);
+    for (int w = 0; w < NW; w++)
+      CK(cudaMemcpy(W + (size_t)w * m * tmax, hW.data(), sizeof(double) * hW.size(), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(mu, hmu.data(), sizeof(double) * hmu.size(), cudaMemcpyHostToDevice));
+    int win = 0;
+    auto Ww = [&]() { win = (win + 1) % NW; return W + (size_t)win * m * tmax; };
+    for (int t : {500, 1000, 2000}) {
+      const double bytes = 8.0 * m * t;
+      std::vector<double> ref(3 * m), got(3 * m);
+      auto check = [&](const char *name, float ms) {
+        CK(cudaMemset(x, 0, sizeof(double) * 3 * m));
+        return ms;
+      };
+      (void)check;
+      auto run = [&](const char *name, auto launch) {
+        CK(cudaMemset(x, 0, sizeof(double) * 3 * m));
+        launch();
+        CK(cudaMemcpy(got.data(), x, sizeof(double) * 3 * m, cudaMemcpyDeviceToHost));
+        double d = 0, sc = 0;
+        for (int p = 0; p < 3 * m; p += 997) {
+          const int c = p / m, pp = p % m;
+          double r = 0;
+          for (int i = 0; i < t; i++) r -= hW[(size_t)pp * tmax + i] * hmu[(size_t)c * tmax + i];
+          d = std::max(d, std::fabs(r - got[p]));
+          sc = std::max(sc, std::fabs(r));
+        }
+        float ms = timeit(launch);
+        printf("t=%4d %-40s %7.1f us  %7.1f GB/s  relerr %.1e\n", t, name, ms * 1000, bytes / ms / 1e6, d / (sc > 0 ? sc : 1));
+      };
+      run("panel_warp8<3,8> grid 1184", [&] { panel_warp8<3, 8><<<1184, 256>>>(Ww(), m, tmax, t, mu, x); });
+      run("panel_warp8<3,4> grid 1184", [&] { panel_warp8<3, 4><<<1184, 256>>>(Ww(), m, tmax, t, mu, x); });
+      run("panel_warp8<3,8> grid 1250", [&] { panel_warp8<3, 8><<<1250, 256>>>(Ww(), m, tmax, t, mu, x); });
+      const size_t sm = sizeof(double) * 3 * ((t + 1) & ~1);
+      CK(cudaFuncSetAttribute(panel_warp16_smem<3, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+      CK(cudaFuncSetAttribute(panel_warp16_smem<3, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+      run("panel_warp16_smem<3,4> grid 592", [&] { panel_warp16_smem<3, 4><<<592, 256, sm>>>(Ww(), m, tmax, t, mu, x); });
+      run("panel_warp16_smem<3,4> grid 1184", [&] { panel_warp16_smem<3, 4><<<1184, 256, sm>>>(Ww(), m, tmax, t, mu, x); });
+      run("panel_warp16_smem<3,8> grid 592", [&] { panel_warp16_smem<3, 8><<<592, 256, sm>>>(Ww(), m, tmax, t, mu, x); });
+    }
+    cudaFree(W); cudaFree(mu); cudaFree(x);
   }
   // ------------------------------------------------------------------ DGEMM
   if (which & 4) {
