@@ -291,6 +291,102 @@ def test_write_mps_round_trip(tmp_path, name):
         assert np.array_equal(np.clip(a, -1e30, 1e30), np.clip(b, -1e30, 1e30))
 
 
+MPS_EDGE = """* comment line
+NAME          EDGE   a second token is ignored
+OBJSENSE
+    MAX
+ROWS
+ N  COST
+ N  FREEROW
+ E  EQ1
+ E  EQ2
+ L  LE1
+ G  GE1
+ L  LE2
+COLUMNS
+    X1        COST      1.5        EQ1       1.0
+    X1        LE1       2.0        FREEROW   9.0
+    MARKER    'MARKER'  'INTORG'
+    X2        COST      -2.0       EQ2       1.0
+    X2        GE1       1.0
+    MARKER    'MARKER'  'INTEND'
+    X3        EQ1       1.0        LE2       4.0
+    X3        EQ1       0.5
+    X4        GE1       1.0
+    X5        LE1       1.0
+    X6        LE2       1.0
+    X7        COST      0.25
+RHS
+    RHS       COST      -7.0       EQ1       3.0
+    RHS       EQ2       4.0        LE1       10.0
+    RHS       GE1       1.0        LE2       8.0
+RANGES
+    RNG       EQ1       2.0        EQ2       -1.5
+    RNG       LE1       4.0        GE1       3.0
+BOUNDS
+ UP BND       X1        4.0
+ UP BND       X2        -1.0
+ LO BND       X3        -2.0
+ UP BND       X3        -0.5
+ MI BND       X4
+ BV BND       X5
+ FX BND       X6        2.5
+ FR BND       X7
+ENDATA
+"""
+
+
+def test_mps_reader_conventions(tmp_path):
+    """The fixed conventions of the MPS format the reference inherits from CoinMpsIO (CoinUtils;
+    ClpModel::readMps src/ClpModel.cpp:2884): first N row is the objective, further N rows are
+    dropped, RHS on the objective row is minus the constant, OBJSENSE MAX negates the objective,
+    RANGES on E rows extend up (R>0) or down (R<0), on L rows down, on G rows up, an UP bound < 0
+    without a lower bound makes the lower bound -infinity, MI / BV / FX / FR, repeated entries of a
+    column add up, MARKER lines are skipped."""
+    import clp_b200
+
+    f = tmp_path / "edge.mps"
+    f.write_text(MPS_EDGE)
+    s = clp_b200.ClpSimplex()
+    assert s.readMps(f) == 0
+    lp = s.getProblem()
+    assert (lp.m, lp.n) == (5, 7)                       # FREEROW dropped
+    inf = 1e30
+    np.testing.assert_array_equal(lp.objective, -np.array([1.5, -2.0, 0, 0, 0, 0, 0.25]))   # MAX -> negated
+    rl, ru = np.clip(lp.row_lower, -inf, inf), np.clip(lp.row_upper, -inf, inf)
+    np.testing.assert_array_equal(rl, [3.0, 2.5, 6.0, 1.0, -inf])   # EQ1 [3,5], EQ2 [2.5,4], LE1 [6,10], GE1 [1,4], LE2 <= 8
+    np.testing.assert_array_equal(ru, [5.0, 4.0, 10.0, 4.0, 8.0])
+    cl, cu = np.clip(lp.col_lower, -inf, inf), np.clip(lp.col_upper, -inf, inf)
+    np.testing.assert_array_equal(cl, [0.0, -inf, -2.0, -inf, 0.0, 2.5, -inf])
+    np.testing.assert_array_equal(cu, [4.0, -1.0, -0.5, inf, 1.0, 2.5, inf])
+    A = lp.to_scipy().toarray()
+    assert A[0, 2] == 1.5 and A[0, 0] == 1.0 and A[2, 0] == 2.0 and A[4, 2] == 4.0   # 1.0 + 0.5 merged
+    assert lp.nnz == 9
+    # the constant: objective row RHS -7 means +7 on the objective, negated again by MAX
+    st_all = clp_b200.ClpSimplex(); st_all.readMps(f)
+    out = tmp_path / "edge_out.mps"
+    assert st_all.writeMps(out) == 0
+    assert "OBJROW" in out.read_text()
+    t = clp_b200.ClpSimplex(); assert t.readMps(out) == 0
+    lp2 = t.getProblem()
+    assert abs(lp.to_scipy() - lp2.to_scipy()).max() == 0
+    for a, b in ((lp.col_lower, lp2.col_lower), (lp.col_upper, lp2.col_upper), (lp.row_lower, lp2.row_lower),
+                 (lp.row_upper, lp2.row_upper), (lp.objective, lp2.objective)):
+        assert np.array_equal(np.clip(a, -inf, inf), np.clip(b, -inf, inf))
+
+
+def test_mps_reader_rejects_unknown_names(tmp_path):
+    import clp_b200
+
+    f = tmp_path / "bad.mps"
+    f.write_text("NAME B\nROWS\n N C\n L R1\nCOLUMNS\n    X1 NOPE 1.0\nENDATA\n")
+    assert clp_b200.ClpSimplex().readMps(f) == -2
+    g = tmp_path / "bad2.mps"
+    g.write_text("NAME B\nROWS\n N C\n L R1\nCOLUMNS\n    X1 R1 1.0\nBOUNDS\n UP B X9 1.0\nENDATA\n")
+    assert clp_b200.ClpSimplex().readMps(g) == -3
+    assert clp_b200.ClpSimplex().readMps(tmp_path / "missing.mps") == -1
+
+
 @pytest.mark.skipif(not os.path.isdir("/root/reference/examples"), reason="reference tree absent")
 def test_mps_reader_on_reference_files():
     import clp_b200
