@@ -27,6 +27,9 @@ SIGNATURES = {
                                         c_double_p, c_double_p, c_double_p, c_double_p, c_double_p,
                                         c_double_p]),
     "Clpb_readMps": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int, ctypes.c_int]),
+    "Clpb_presolvedModel": (ctypes.c_void_p, [ctypes.c_void_p, c_int_p]),
+    "Clpb_postsolve": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
+    "Clpb_setSolution": (None, [ctypes.c_void_p, c_double_p, c_double_p, c_ubyte_p, ctypes.c_int]),
     "Clpb_writeMps": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int, ctypes.c_int, ctypes.c_double]),
     "Clpb_numberRows": (ctypes.c_int, [ctypes.c_void_p]),
     "Clpb_numberColumns": (ctypes.c_int, [ctypes.c_void_p]),

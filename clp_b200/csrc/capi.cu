@@ -8,6 +8,7 @@
 
 struct Clpb_Simplex {
   clpb::Engine e;
+  clpb::Presolve pre; // filled by Clpb_presolvedModel on the ORIGINAL model
 };
 
 namespace {
@@ -85,6 +86,55 @@ int Clpb_loadProblem(Clpb_Simplex *model, int numcols, int numrows, const int *s
 int Clpb_readMps(Clpb_Simplex *model, const char *filename, int, int)
 {
   return guarded([&] { return model->e.readMps(filename); });
+}
+Clpb_Simplex *Clpb_presolvedModel(Clpb_Simplex *model, int *status)
+{
+  Clpb_Simplex *red = new Clpb_Simplex();
+  const int rc = model->pre.presolve(model->e, red->e);
+  if (status)
+    *status = rc;
+  if (rc != 0) {
+    delete red;
+    return nullptr;
+  }
+  // parameters travel with the model
+  red->e.primalTolerance = model->e.primalTolerance;
+  red->e.dualTolerance = model->e.dualTolerance;
+  red->e.dualBound = model->e.dualBound;
+  red->e.maximumIterations = model->e.maximumIterations;
+  red->e.maximumSeconds = model->e.maximumSeconds;
+  red->e.scalingFlag = model->e.scalingFlag;
+  red->e.perturbation = model->e.perturbation;
+  red->e.logLevel = model->e.logLevel;
+  return red;
+}
+int Clpb_postsolve(Clpb_Simplex *model, Clpb_Simplex *reduced)
+{
+  clpb::Engine &o = model->e, &r = reduced->e;
+  if ((int)r.solution.size() != r.nm || (int)r.rowPrice.size() != r.m || (int)r.status.size() != r.nm)
+    return -1; // the reduced model holds no solution
+  std::vector<double> xr(r.solution.begin(), r.solution.begin() + r.n);
+  model->pre.postsolve(xr, r.rowPrice, r.status, o, o.solution, o.reducedCost, o.rowPrice, o.status);
+  o.setStatus(o.status.data());
+  double obj = o.objectiveOffset;
+  for (int j = 0; j < o.n; j++)
+    obj += o.hCost[j] * o.solution[j];
+  o.objectiveValue = obj;
+  o.problemStatus = r.problemStatus;
+  o.numberIterations = r.numberIterations;
+  return 0;
+}
+void Clpb_setSolution(Clpb_Simplex *model, const double *x, const double *rowPrice, const unsigned char *status,
+                      int problemStatus)
+{
+  // hand a solution in from outside (the parity tests solve the presolved model with the CPU oracle)
+  clpb::Engine &e = model->e;
+  e.solution.assign(e.nm, 0.0);
+  std::copy(x, x + e.n, e.solution.begin());
+  e.rowPrice.assign(rowPrice, rowPrice + e.m);
+  e.status.assign(status, status + e.nm);
+  e.reducedCost.assign(e.nm, 0.0);
+  e.problemStatus = problemStatus;
 }
 int Clpb_writeMps(Clpb_Simplex *model, const char *filename, int, int, double)
 {

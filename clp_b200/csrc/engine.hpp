@@ -21,6 +21,8 @@ struct PhaseTimes { // accumulated device milliseconds per phase (when timing is
   long samples = 0;
 };
 
+struct Presolve;
+
 class Engine {
 public:
   Engine();
@@ -160,6 +162,31 @@ private:
   void buildRowCopy(const std::vector<double> &val, std::vector<int> &rowStart,
                     std::vector<int> &colIdx, std::vector<double> &rval) const;
   void prepareWorkingProblem();
+};
+
+// presolve.cpp -- elementary presolve actions and their postsolve (host only)
+struct Presolve {
+  struct Action {
+    char kind;      // 'F' fixed column, 'S' singleton row, 'C' empty column, 'R' empty row
+    int col, row;
+    double value;   // F/C: the value of the column; S: the coefficient a_ij
+    double oldLo, oldUp;         // S: column bounds before the row was folded in
+    double impliedLo, impliedUp; // S: bounds the row implies
+  };
+  int m = 0, n = 0;
+  std::vector<Action> actions;
+  std::vector<char> colAlive, rowAlive;
+  std::vector<int> colMap, rowMap; // original -> reduced index or -1
+  std::vector<double> lower, upper, cost; // working bounds (n+m) and costs (n)
+  std::vector<int> colStart, rowIdx;
+  std::vector<double> val;
+  double offset = 0.0;
+  // 0 ok (dst loaded with the reduced problem), 1 primal infeasible, 2 dual infeasible (unbounded)
+  int presolve(const Engine &src, Engine &dst);
+  void postsolve(const std::vector<double> &xr, const std::vector<double> &pir,
+                 const std::vector<unsigned char> &statusR, const Engine &orig,
+                 std::vector<double> &solution, std::vector<double> &reducedCost,
+                 std::vector<double> &rowPrice, std::vector<unsigned char> &status) const;
 };
 
 // mps_reader.cpp

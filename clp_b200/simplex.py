@@ -83,6 +83,37 @@ class ClpSimplex:
     def readMps(self, fileName, keepNames=False, ignoreErrors=False):
         return self._L.Clpb_readMps(self._h, str(fileName).encode(), int(keepNames), int(ignoreErrors))
 
+    # ---- ClpPresolve::presolvedModel / postsolve (elementary actions) ----
+    def presolvedModel(self):
+        """Returns (status, reduced ClpSimplex or None); status 0 ok, 1 infeasible, 2 unbounded."""
+        st = ctypes.c_int(0)
+        h = self._L.Clpb_presolvedModel(self._h, ctypes.byref(st))
+        if not h:
+            return st.value, None
+        red = ClpSimplex.__new__(ClpSimplex)
+        red._L, red._h, red._keep = self._L, h, None
+        return 0, red
+
+    def postsolve(self, reduced):
+        return self._L.Clpb_postsolve(self._h, reduced._h)
+
+    def setSolution(self, x, rowPrice, status, problemStatus=0):
+        x = np.ascontiguousarray(x, dtype=np.float64); pi = np.ascontiguousarray(rowPrice, dtype=np.float64)
+        st = np.ascontiguousarray(status, dtype=np.uint8)
+        self._L.Clpb_setSolution(self._h, _dp(x), _dp(pi), _up(st), int(problemStatus))
+
+    def initialSolve(self, presolve=True):
+        """ClpSimplex::initialSolve with the dual algorithm: presolve -> dual -> postsolve."""
+        if not presolve:
+            return self.dual()
+        st, red = self.presolvedModel()
+        if red is None:
+            return st
+        rc = red.dual()
+        if rc == 0:
+            self.postsolve(red)
+        return rc
+
     def writeMps(self, fileName, formatType=1, numberAcross=1, objSense=0.0):
         return self._L.Clpb_writeMps(self._h, str(fileName).encode(), int(formatType), int(numberAcross), float(objSense))
 

@@ -33,6 +33,18 @@ int Clpb_loadProblem(Clpb_Simplex *model, int numcols, int numrows, const int *s
                      const double *rowub);
 /* Clp_readMps :116 (ClpModel::readMps src/ClpModel.cpp:2884) */
 int Clpb_readMps(Clpb_Simplex *model, const char *filename, int keepNames, int ignoreErrors);
+/* ClpPresolve::presolvedModel / postsolve (src/ClpPresolve.hpp:40,61) restricted to the elementary
+   actions (fixed columns, singleton rows, empty columns, empty rows; src/ClpPresolve.cpp:966,1141,
+   1448,1449).  Clpb_presolvedModel returns a NEW model (delete it with Clpb_deleteModel) holding the
+   reduced problem, or NULL with *status = 1 (primal infeasible) / 2 (dual infeasible); the original
+   model keeps the postsolve information.  After solving the reduced model, Clpb_postsolve writes
+   the solution of the original problem (primal, dual, status, objective) into the original model.
+   Clpb_setSolution hands a solution of a model in from outside (x[n], rowPrice[m], status[n+m]).
+   Host only. */
+Clpb_Simplex *Clpb_presolvedModel(Clpb_Simplex *model, int *status);
+int Clpb_postsolve(Clpb_Simplex *model, Clpb_Simplex *presolved);
+void Clpb_setSolution(Clpb_Simplex *model, const double *x, const double *rowPrice,
+                      const unsigned char *status, int problemStatus);
 /* Clp_writeMps :120 (ClpModel::writeMps src/ClpModel.cpp:3986): the model as loaded, default names
    R%7.7d / C%7.7d, 17 significant digits; formatType / numberAcross / objSense are accepted for
    signature compatibility.  0 ok, -1 cannot open.  Host only. */

@@ -1,0 +1,140 @@
+"""Presolve / postsolve (clp_b200/csrc/presolve.cpp) checked on the CPU: the reduced model is solved
+by the CPU oracle, the solution is handed to Clpb_postsolve, and the result is audited on the
+ORIGINAL problem (KKT incl. row duals, same optimum as the oracle on the original problem)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, load_golden
+
+import clp_b200
+from clp_b200 import generators as G
+from oracle import oracle as O
+
+INF = 1e29
+
+
+def decorate(lp, seed):
+    """Add what the elementary actions remove: fixed columns, singleton rows (some binding, some
+    not, one equality), an empty column, an empty row."""
+    import scipy.sparse as sp
+
+    rng = np.random.default_rng(seed)
+    A = lp.to_scipy().tocsc()
+    m, n = lp.m, lp.n
+    o = O.OracleSimplex(lp)
+    assert o.dual() == 0
+    x0 = o.column_solution()
+    col_lower, col_upper, obj = lp.col_lower.copy(), lp.col_upper.copy(), lp.objective.copy()
+    # fix a few columns at their optimal value
+    for j in rng.choice(n, size=min(5, n), replace=False):
+        col_lower[j] = col_upper[j] = x0[j]
+    # singleton rows through the optimum x0 of the undecorated LP (so the LP stays feasible); the
+    # cost of the column is pushed against the row, so that the row is active with a nonzero dual
+    rows, rl, ru = [], [], []
+    fixed = col_lower == col_upper
+    picks = [j for j in rng.permutation(n) if not fixed[j]][:8]
+    for t, j in enumerate(picks):
+        a = float(rng.choice([-2.0, 0.5, 3.0]))
+        rows.append(sp.csr_matrix(([a], ([0], [j])), shape=(1, n)))
+        v = a * x0[j]
+        kind = t % 4
+        if kind == 0:      # x_j <= x0_j through the row, and the cost wants x_j larger
+            obj[j] -= 1.0
+            (rl.append(-1e30), ru.append(v)) if a > 0 else (rl.append(v), ru.append(1e30))
+        elif kind == 1:    # x_j >= x0_j through the row, and the cost wants x_j smaller
+            obj[j] += 1.0
+            (rl.append(v), ru.append(1e30)) if a > 0 else (rl.append(-1e30), ru.append(v))
+        elif kind == 2:    # slack row
+            rl.append(v - 10.0); ru.append(v + 10.0)
+        else:              # equality row: fixes the column
+            rl.append(v); ru.append(v)
+    rows.append(sp.csr_matrix((1, n)))   # empty row
+    rl.append(-1.0); ru.append(2.0)
+    A2 = sp.vstack([A] + rows).tocsc()
+    # an empty column with positive cost and one with zero cost
+    A2 = sp.hstack([A2, sp.csc_matrix((A2.shape[0], 2))]).tocsc()
+    col_lower = np.concatenate([col_lower, [1.5, -3.0]])
+    col_upper = np.concatenate([col_upper, [4.0, 1e30]])
+    obj = np.concatenate([obj, [2.0, 0.0]])
+    # keep the singleton rows compatible with the column bounds (the LP must stay feasible)
+    lp2 = G.LP(lp.name + "+presolvable", A2.shape[0], A2.shape[1], A2.indptr.astype(np.int32),
+               A2.indices.astype(np.int32), A2.data.astype(np.float64), col_lower, col_upper, obj,
+               np.concatenate([lp.row_lower, rl]), np.concatenate([lp.row_upper, ru]))
+    return lp2
+
+
+def full_audit(lp, s, tol=1e-6):
+    x, act, dj, pi, st = (s.primalColumnSolution(), s.primalRowSolution(), s.dualColumnSolution(),
+                          s.dualRowSolution(), s.statusArray())
+    assert O.kkt_violations(lp, x, act, dj) == 0
+    A = lp.to_scipy()
+    np.testing.assert_allclose(dj, lp.objective - A.T @ pi, atol=tol * (1 + np.abs(lp.objective).max()))
+    # row duals: >= 0 needs the row at its lower bound, <= 0 at its upper bound
+    at_lo = np.abs(act - lp.row_lower) <= 1e-5 * (1 + np.abs(act))
+    at_up = np.abs(act - lp.row_upper) <= 1e-5 * (1 + np.abs(act))
+    assert not np.any((pi > tol) & ~at_lo)
+    assert not np.any((pi < -tol) & ~at_up)
+    assert int((st == 1).sum()) == lp.m                     # square basis
+    assert np.all(np.abs(dj[st[: lp.n] == 1]) <= tol)       # basic columns have zero reduced cost
+    assert np.all(np.abs(pi[st[lp.n:] == 1]) <= tol)        # basic rows have zero price
+
+
+@pytest.mark.parametrize("name,seed", [("UFL-10x30", 1), ("TSP-MTZ-20", 2), ("modified_afiro", 3), ("SetCover-30x100", 4),
+                                       ("staircase-480", 5), ("transport-10x200", 6)])
+def test_presolve_postsolve_against_oracle(name, seed):
+    lp = decorate(load_golden(name), seed)
+    ref = O.OracleSimplex(lp)
+    st_ref = ref.dual()
+    s = clp_b200.ClpSimplex(); s.loadLP(lp)
+    st, red = s.presolvedModel()
+    assert st_ref == 0 and st == 0
+    rlp = red.getProblem()
+    assert rlp.n <= lp.n - 5 and rlp.m <= lp.m - 3           # something was removed
+    o = O.OracleSimplex(rlp)
+    assert o.dual() == 0
+    red.setSolution(o.column_solution(), o.row_price(), o.status(), 0)
+    assert s.postsolve(red) == 0
+    assert abs(s.objectiveValue() - ref.objective_value) <= 1e-8 * (1 + abs(ref.objective_value))
+    full_audit(lp, s)
+
+
+def test_presolve_detects_trivial_infeasibility_and_unboundedness():
+    import scipy.sparse as sp
+
+    # singleton rows 2x >= 3 and 2x <= 1
+    A = sp.csc_matrix(np.array([[2.0, 0.0], [2.0, 0.0], [0.0, 1.0]]))
+    lp = G.LP("inf", 3, 2, A.indptr.astype(np.int32), A.indices.astype(np.int32), A.data, np.zeros(2), np.full(2, 1e30),
+              np.ones(2), np.array([3.0, -1e30, 0.0]), np.array([1e30, 1.0, 5.0]))
+    s = clp_b200.ClpSimplex(); s.loadLP(lp)
+    assert s.presolvedModel() == (1, None)
+    # empty column with negative cost and no upper bound
+    A = sp.csc_matrix(np.array([[1.0, 0.0]]))
+    lp = G.LP("unb", 1, 2, A.indptr.astype(np.int32), A.indices.astype(np.int32), A.data, np.zeros(2), np.full(2, 1e30),
+              np.array([1.0, -1.0]), np.array([0.0]), np.array([4.0]))
+    s = clp_b200.ClpSimplex(); s.loadLP(lp)
+    assert s.presolvedModel() == (2, None)
+
+
+def test_presolve_leaves_irreducible_models_alone():
+    lp = load_golden("NQueens-8")
+    s = clp_b200.ClpSimplex(); s.loadLP(lp)
+    st, red = s.presolvedModel()
+    assert st == 0
+    r = red.getProblem()
+    assert (r.m, r.n, r.nnz) == (lp.m, lp.n, lp.nnz)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,seed", [("UFL-10x30", 1), ("SetCover-30x100", 4), ("staircase-480", 5)])
+def test_initial_solve_with_presolve_on_the_device(name, seed):
+    """ClpSimplex::initialSolve: presolve -> dual simplex on the GPU -> postsolve."""
+    lp = decorate(load_golden(name), seed)
+    ref = O.OracleSimplex(lp)
+    assert ref.dual() == 0
+    s = clp_b200.ClpSimplex(); s.loadLP(lp)
+    assert s.initialSolve(presolve=True) == 0
+    assert abs(s.objectiveValue() - ref.objective_value) <= 1e-8 * (1 + abs(ref.objective_value))
+    full_audit(lp, s)
