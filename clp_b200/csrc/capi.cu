@@ -127,7 +127,7 @@ int Clpb_postsolve(Clpb_Simplex *model, Clpb_Simplex *reduced)
 void Clpb_setSolution(Clpb_Simplex *model, const double *x, const double *rowPrice, const unsigned char *status,
                       int problemStatus)
 {
-  // hand a solution in from outside (the parity tests solve the presolved model with the CPU oracle)
+  // hand a solution in from outside (the parity tests solve the presolved model with an independent CPU solver)
   clpb::Engine &e = model->e;
   e.solution.assign(e.nm, 0.0);
   std::copy(x, x + e.n, e.solution.begin());
