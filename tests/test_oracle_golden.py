@@ -431,6 +431,24 @@ t = torch.tensor([lo, hi])
 out = [torch.zeros(2, dtype=torch.long) for _ in range(2)]
 dist.all_gather(out, t)
 assert out[0][0] == 0 and out[0][1] == out[1][0] and out[1][1] == n
+# the exchange of Engine::enqueueIteration: every rank prices its block, then ONE in-place
+# all-gather of shards padded to per = ceil(n/world) entries; the padding of the last shard lands
+# on the slack part of the row (entries n..n+m), which the row kernel recomputes from rho
+rng = np.random.default_rng(7)
+m = 40
+A = rng.standard_normal((m, n)) * (rng.uniform(size=(m, n)) < 0.1)
+rho = rng.standard_normal(m)
+per = (n + 2 - 1) // 2
+row = np.full(n + m, np.nan)
+row[lo:hi] = rho @ A[:, lo:hi]                      # this rank's raw dot products
+send = torch.from_numpy(row[rank * per: rank * per + per].copy())
+parts = [torch.zeros(per, dtype=torch.float64) for _ in range(2)]
+dist.all_gather(parts, send)
+for r in range(2):
+    row[r * per: r * per + per] = parts[r].numpy()
+row[n:] = -rho                                       # slack part rewritten after the gather
+assert np.array_equal(row[:n], np.concatenate([rho @ A[:, :per], rho @ A[:, per:]]))
+assert 2 * per <= n + m
 dist.destroy_process_group()
 print("ok", rank)
 """ % ROOT
