@@ -94,6 +94,9 @@ Clpb_Simplex *Clpb_presolvedModel(Clpb_Simplex *model, int *status)
   if (status)
     *status = rc;
   if (rc != 0) {
+    // presolve itself proved the problem infeasible / unbounded: the ORIGINAL model says so
+    model->e.problemStatus = rc;
+    model->e.numberIterations = 0;
     delete red;
     return nullptr;
   }
@@ -106,11 +109,29 @@ Clpb_Simplex *Clpb_presolvedModel(Clpb_Simplex *model, int *status)
   red->e.scalingFlag = model->e.scalingFlag;
   red->e.perturbation = model->e.perturbation;
   red->e.logLevel = model->e.logLevel;
+  red->e.acceptablePivot = model->e.acceptablePivot;
+  red->e.zeroTolerance = model->e.zeroTolerance;
+  red->e.factorizationFrequency = model->e.factorizationFrequency;
+  red->e.batch = model->e.batch;
+  red->e.useGraph = model->e.useGraph;
+  red->e.useRowPass = model->e.useRowPass;
+  red->e.usePriceTma = model->e.usePriceTma;
+  red->e.factorMode = model->e.factorMode;
+  red->e.rank = model->e.rank;
+  red->e.worldSize = model->e.worldSize;
+  red->e.ncclComm = model->e.ncclComm;
+  red->e.allGatherFn = model->e.allGatherFn;
   return red;
 }
 int Clpb_postsolve(Clpb_Simplex *model, Clpb_Simplex *reduced)
 {
   clpb::Engine &o = model->e, &r = reduced->e;
+  if (r.problemStatus != 0) {
+    // not optimal: nothing to postsolve, but the original model reports the outcome
+    o.problemStatus = r.problemStatus;
+    o.numberIterations = r.numberIterations;
+    return 0;
+  }
   if ((int)r.solution.size() != r.nm || (int)r.rowPrice.size() != r.m || (int)r.status.size() != r.nm)
     return -1; // the reduced model holds no solution
   std::vector<double> xr(r.solution.begin(), r.solution.begin() + r.n);

@@ -619,8 +619,16 @@ int Engine::readBasis(const char *fileName)
 
 int Engine::setupDevice()
 {
-  if (deviceReady)
+  // what the device copy was built for: a later scaling() / factorizationFrequency / timing change
+  // rebuilds it instead of being silently ignored
+  const long long signature = (long long)scalingFlag * 1000003ll + (long long)factorizationFrequency * 101ll +
+                              (timing ? 7 : 0) + (long long)worldSize * 13ll + (long long)rank * 17ll +
+                              (usePriceTma ? 3 : 0) + (long long)factorMode * 29ll;
+  if (deviceReady && signature == readySignature)
     return 0;
+  if (deviceReady)
+    freeAll();
+  readySignature = signature;
   int devCount = 0;
   if (cudaGetDeviceCount(&devCount) != cudaSuccess || devCount == 0) {
     fprintf(stderr, "clp_b200: no CUDA device -- this engine has no CPU fallback\n");
@@ -793,8 +801,9 @@ int Engine::setupDevice()
   d.NinvT = nullptr;
   d.primalTolerance = primalTolerance;
   d.dualTolerance = dualTolerance;
-  d.acceptablePivot = acceptablePivot;
   d.zeroTolerance = zeroTolerance;
+  d.flagged = dalloc<unsigned char>(m);
+  CUDA_OK(cudaMemset(d.flagged, 0, m));
 
   CUDA_OK(cudaMemcpy(d.costTrue, wCost.data(), sizeof(double) * nm, cudaMemcpyHostToDevice));
   CUDA_OK(cudaMemcpy(d.cost, wCost.data(), sizeof(double) * nm, cudaMemcpyHostToDevice));
@@ -821,6 +830,13 @@ int Engine::setupDevice()
   }
   deviceReady = true;
   return 0;
+}
+
+void Engine::setAcceptablePivot(double value)
+{
+  currentAcceptablePivot = value;
+  CUDA_OK(cudaMemcpyAsync(&d.st->acceptablePivot, &currentAcceptablePivot, sizeof(double), cudaMemcpyHostToDevice, stream));
+  CUDA_OK(cudaStreamSynchronize(stream));
 }
 
 void Engine::resetStateForRun()
@@ -882,9 +898,14 @@ void Engine::resetStateForRun()
   CUDA_OK(cudaMemset(d.candCount, 0, sizeof(int)));
   d.primalTolerance = primalTolerance;
   d.dualTolerance = dualTolerance;
-  d.acceptablePivot = acceptablePivot;
   d.zeroTolerance = zeroTolerance;
+  CUDA_OK(cudaMemset(d.flagged, 0, m));
+  setAcceptablePivot(acceptablePivot);
   currentDualBound = dualBound;
+  if (iterGraph) { // DeviceModel (tolerances included) is captured by value: a new run re-captures
+    cudaGraphExecDestroy(iterGraph);
+    iterGraph = nullptr;
+  }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -1042,6 +1063,9 @@ int Engine::refactor()
       CUDA_OK(cudaMemsetAsync(d.etaLastOfPos, 0xFF, sizeof(int) * m, stream));
       // numEtas = 0 (keep the rest of the state)
       CUDA_OK(cudaMemsetAsync(&d.st->numEtas, 0, sizeof(int), stream));
+      // flagged rows get another chance on fresh factors (ClpSimplexDual.cpp:5024ff unflag)
+      CUDA_OK(cudaMemsetAsync(d.flagged, 0, m, stream));
+      CUDA_OK(cudaMemsetAsync(&d.st->numFlagged, 0, sizeof(int), stream));
       CUDA_OK(cudaStreamSynchronize(stream));
       hPivot = newPivot;
       numberRefactorizations++;
@@ -1269,6 +1293,59 @@ void Engine::downloadSolution()
   }
 }
 
+// An LP without rows or without columns (what presolve can leave behind): every column goes to the
+// bound its cost prefers; no device work.  0 optimal, 1 primal infeasible, 2 dual infeasible.
+int Engine::trivialSolve()
+{
+  solution.assign(nm, 0.0);
+  reducedCost.assign(nm, 0.0);
+  rowPrice.assign(m, 0.0);
+  status.assign(nm, atLowerBound);
+  pivotVariable.resize(m);
+  problemStatus = 0;
+  objectiveValue = objectiveOffset;
+  sumPrimalInfeasibilities = 0.0;
+  for (int j = 0; j < n; j++) {
+    const double c = hCost[j], lo = hLower[j], up = hUpper[j];
+    double x;
+    unsigned char st;
+    if (lo > up + primalTolerance)
+      problemStatus = 1;
+    if (c > dualTolerance || (c >= -dualTolerance && lo > -kInf)) {
+      x = lo;
+      st = atLowerBound;
+      if (lo <= -kInf) {
+        problemStatus = problemStatus == 1 ? 1 : 2;
+        x = up < kInf ? up : 0.0;
+      }
+    } else if (c < -dualTolerance || up < kInf) {
+      x = up;
+      st = atUpperBound;
+      if (up >= kInf) {
+        problemStatus = problemStatus == 1 ? 1 : 2;
+        x = lo > -kInf ? lo : 0.0;
+      }
+    } else {
+      x = 0.0;
+      st = isFree;
+    }
+    if (lo == up)
+      st = isFixed;
+    solution[j] = x;
+    status[j] = st;
+    reducedCost[j] = c;
+    objectiveValue += c * x;
+  }
+  for (int i = 0; i < m; i++) { // n == 0: every row activity is 0
+    status[n + i] = basic;
+    pivotVariable[i] = n + i;
+    if (hLower[n + i] > primalTolerance || hUpper[n + i] < -primalTolerance)
+      problemStatus = 1;
+  }
+  hStatus = status;
+  return problemStatus;
+}
+
 int Engine::startup()
 {
   setupDevice();
@@ -1300,6 +1377,8 @@ int Engine::dual()
   numberRefactorizations = 0;
   kernelLaunches = 0;
   phase = PhaseTimes();
+  if (m == 0 || n == 0)
+    return trivialSolve();
   if (startup() != 0) {
     problemStatus = 4;
     return problemStatus;
@@ -1405,6 +1484,8 @@ int Engine::dual()
               numberIterations, hState->numEtas, d.k, hState->stop, hState->infeas,
               hState->thetaDual);
     const int stop = hState->stop;
+    if (done > 0 && currentAcceptablePivot < acceptablePivot && hState->numEtas >= 5)
+      setAcceptablePivot(acceptablePivot); // acceptablePivot_ = fabs(...) once pivots() >= 5 (:2070-2074)
     if (stop == STOP_NONE) {
       consecutiveTrouble = 0;
       continue;
@@ -1458,10 +1539,32 @@ int Engine::dual()
         problemStatus = 2;
         break;
       }
+      if (hState->numFlagged > 0) {
+        // Every row that is still primal infeasible is flagged: its infeasibility is below the
+        // reference's 1e-4 test value and no entering column with an acceptable pivot exists on
+        // fresh, refined factors.  The reference leaves the dual here with status 10 and lets the
+        // primal simplex remove sum-of-infeasibilities < 1e-3 (ClpSimplexDual.cpp:1988-2010,
+        // ClpSimplex.cpp:5808-5851).  There is no primal algorithm on this path: the basis is
+        // reported optimal when the flagged infeasibilities stay below that 1e-3 threshold
+        // (sumPrimalInfeasibilities says how much), primal infeasible otherwise.
+        launch_objective(d, dObj, stream);
+        double obj2[2];
+        CUDA_OK(cudaMemcpyAsync(obj2, dObj, sizeof(double) * 2, cudaMemcpyDeviceToHost, stream));
+        CUDA_OK(cudaStreamSynchronize(stream));
+        if (logLevel > 0)
+          fprintf(stderr, "clp_b200: %d flagged rows left, sum of primal infeasibilities %.3g\n",
+                  hState->numFlagged, obj2[1]);
+        problemStatus = obj2[1] < 1.0e-3 ? 0 : 1;
+        break;
+      }
       problemStatus = 0;
       break;
     }
     case STOP_NO_COLUMN: {
+      if (logLevel > 0)
+        fprintf(stderr, "clp_b200: no entering column: it %d row %d seqOut %d infeas %.6g etas %d acceptable %.1e flagged %d\n",
+                numberIterations, hState->pivotRow, hState->seqOut, hState->infeas, hState->numEtas,
+                currentAcceptablePivot, hState->numFlagged);
       if (!fresh) {
         if (refresh() != 0)
           problemStatus = 4;
@@ -1481,13 +1584,25 @@ int Engine::dual()
       }
       // the reference only believes "no entering column" on fresh factors once the acceptable
       // pivot has been relaxed to 1e-8 (ClpSimplexDual.cpp:1882-1884, :2072-2074): retry the same
-      // row with the smaller tolerance before declaring the problem primal infeasible
-      if (d.acceptablePivot > 1.0e-8) {
-        d.acceptablePivot = 1.0e-8;
-        if (iterGraph) { // kernel arguments are captured by value
-          cudaGraphExecDestroy(iterGraph);
-          iterGraph = nullptr;
-        }
+      // row with the smaller tolerance before anything else
+      if (currentAcceptablePivot > 1.0e-8) {
+        setAcceptablePivot(1.0e-8);
+        break;
+      }
+      // a small infeasibility whose row has no usable pivot: flag the row and carry on with the
+      // others (setFlagged, ClpSimplexDual.cpp:2058-2066; test value 1e-4 / 1e-6 of :1984-1988)
+      if (hState->infeas < 1.0e-4 && hState->numFlagged < m) {
+        const unsigned char one = 1;
+        const int nf = hState->numFlagged + 1;
+        CUDA_OK(cudaMemcpyAsync(d.flagged + hState->pivotRow, &one, 1, cudaMemcpyHostToDevice, stream));
+        CUDA_OK(cudaMemcpyAsync(&d.st->numFlagged, &nf, sizeof(int), cudaMemcpyHostToDevice, stream));
+        CUDA_OK(cudaStreamSynchronize(stream));
+        break;
+      }
+      // a real infeasibility: the reference calls the problem infeasible only when the best
+      // possible pivot of the row is below 1e-11 (:1978); relax step by step down to that
+      if (currentAcceptablePivot > 1.0e-11) {
+        setAcceptablePivot(std::max(1.0e-11, currentAcceptablePivot * 0.1));
         break;
       }
       problemStatus = 1;
@@ -1598,6 +1713,7 @@ int Engine::dualColumnTest(const double *alphaRow, const double *dj, const unsig
   IterState st;
   memset(&st, 0, sizeof(st));
   st.sigma = sigma;
+  st.acceptablePivot = acceptablePivot;
   st.infeas = infeas;
   CUDA_OK(cudaMemcpy(d.st, &st, sizeof(st), cudaMemcpyHostToDevice));
   CUDA_OK(cudaMemsetAsync(d.histWeight, 0, sizeof(unsigned long long) * kHistBuckets, stream));

@@ -72,6 +72,11 @@ struct IterState {
   // bound-flip right-hand side in fixed point (order independent => bit-identical on every rank)
   unsigned long long flipMaxBits; // max range (u-l) over this iteration's flips (double bits)
   double flipScale, flipInvScale; // contribution * flipScale is accumulated as int64
+  // acceptable pivot of the ratio test (ClpSimplexDual::acceptablePivot_): lives here and not in
+  // DeviceModel because the driver relaxes it (ClpSimplexDual.cpp:2072-2074) while the captured
+  // iteration graph holds DeviceModel by value
+  double acceptablePivot;
+  int numFlagged;        // rows currently excluded from CHUZR (ClpSimplex::setFlagged, ClpSimplexDual.cpp:2058-2066)
 };
 
 struct IterRecord { // what the host reads back per iteration
@@ -162,7 +167,8 @@ struct DeviceModel {
   IterRecord *rec;    // ring of records (device)
   int recCap;
   // tolerances
-  double primalTolerance, dualTolerance, acceptablePivot, zeroTolerance;
+  double primalTolerance, dualTolerance, zeroTolerance;
+  unsigned char *flagged; // [m] by position: 1 = row is flagged (skipped by CHUZR until the next refactorization)
 };
 
 // Optional per-kernel CUDA-event brackets (timing mode only): price kernel, FTRAN GEMV, BTRAN GEMV.

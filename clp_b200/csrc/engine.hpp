@@ -45,6 +45,9 @@ public:
   bool timing = false;
   bool useGraph = true;
   bool usePriceTma = false;       // TMA-staged price kernel (default: LDG-direct kernel, 26% faster)
+  // 0 = choose per basis (block-banded nucleus when it pays), 1 = always the dense nucleus inverse,
+  // 2 = always block-banded (tests)
+  int factorMode = 0;
   bool useRowPass = true;         // cooperative row-pass kernel (false / column-sharded: separate kernels)
   int warmupIterations = 0;       // device-timed window starts once this many iterations ran
   double timedMilliseconds = 0.0; // CUDA-event time of the window (iterations + refactorizations)
@@ -122,6 +125,8 @@ private:
   DeviceModel d{};
   cudaStream_t stream = nullptr;
   bool deviceReady = false;
+  long long readySignature = -1;
+  int trivialSolve(); // m == 0 or n == 0 (a presolved model can be empty): host only
   bool haveUserStatus = false;
   // device allocations (owned)
   std::vector<void *> allocs;
@@ -144,6 +149,8 @@ private:
   std::vector<int> hPivot;
   int tmax = 0;
   double currentDualBound = 0.0;
+  double currentAcceptablePivot = 1.0e-7;
+  void setAcceptablePivot(double value); // device-resident (IterState): no graph re-capture
   cudaGraphExec_t iterGraph = nullptr; // one captured iteration (replayed 'batch' times per sync)
   int kernelsPerIteration = 0;
   void buildIterationGraph();

@@ -635,7 +635,7 @@ __global__ void chuzc_harris_kernel(DeviceModel d)
     bool boxed;
     if (!candidate(d, j, alpha, sigma, a, dtil, boxed, range))
       continue;
-    if (a < d.acceptablePivot || dtil / a < thetaStar)
+    if (a < d.st->acceptablePivot || dtil / a < thetaStar)
       continue;
     unsigned long long h = (unsigned long long)__double_as_longlong((dtil + tol) / a);
     best = min(best, h);
@@ -665,7 +665,7 @@ __global__ void chuzc_select_kernel(DeviceModel d)
     if (!candidate(d, j, alpha, sigma, a, dtil, boxed, range))
       continue;
     const double ratio = dtil / a;
-    if (a < d.acceptablePivot || ratio < thetaStar || ratio > harris)
+    if (a < d.st->acceptablePivot || ratio < thetaStar || ratio > harris)
       continue;
     unsigned long long key = ((unsigned long long)__double_as_longlong(a) & ~0xFFFFFull) |
                              (unsigned long long)(0xFFFFF - j);

@@ -377,7 +377,7 @@ __global__ void __launch_bounds__(1024, 1) row_pass_kernel(DeviceModel d)
     unsigned long long best = 0x7FF0000000000000ull;
     for (int i = tid; i < cnt; i += 1024) {
       const double a = __ldcg(d.candA + i), dt = __ldcg(d.candD + i);
-      if (a >= d.acceptablePivot && dt / a >= thetaStar)
+      if (a >= st->acceptablePivot && dt / a >= thetaStar)
         best = min(best, (unsigned long long)__double_as_longlong((dt + d.dualTolerance) / a));
     }
     best = block_min_u64(best, sU64);
@@ -389,7 +389,7 @@ __global__ void __launch_bounds__(1024, 1) row_pass_kernel(DeviceModel d)
       for (int i = tid; i < cnt; i += 1024) {
         const double a = __ldcg(d.candA + i), dt = __ldcg(d.candD + i);
         const double ratio = dt / a;
-        if (a >= d.acceptablePivot && ratio >= thetaStar && ratio <= harrisL)
+        if (a >= st->acceptablePivot && ratio >= thetaStar && ratio <= harrisL)
           bk = max(bk, ((unsigned long long)__double_as_longlong(a) & ~0xFFFFFull) |
                            (unsigned long long)(0xFFFFF - __ldcg(d.candJ + i)));
       }
@@ -399,7 +399,7 @@ __global__ void __launch_bounds__(1024, 1) row_pass_kernel(DeviceModel d)
       unsigned long long gb = 0x7FF0000000000000ull;
 #pragma unroll
       for (int e = 0; e < E; e++)
-        if ((flags[e] & F_CAND) && aabs[e] >= d.acceptablePivot && dtil[e] / aabs[e] >= thetaStar)
+        if ((flags[e] & F_CAND) && aabs[e] >= st->acceptablePivot && dtil[e] / aabs[e] >= thetaStar)
           gb = min(gb, (unsigned long long)__double_as_longlong((dtil[e] + d.dualTolerance) / aabs[e]));
       gb = block_min_u64(gb, sU64);
       if (tid == 0 && gb != 0x7FF0000000000000ull)
@@ -411,7 +411,7 @@ __global__ void __launch_bounds__(1024, 1) row_pass_kernel(DeviceModel d)
       unsigned long long bk = 0ull;
 #pragma unroll
       for (int e = 0; e < E; e++) {
-        if (!(flags[e] & F_CAND) || aabs[e] < d.acceptablePivot)
+        if (!(flags[e] & F_CAND) || aabs[e] < st->acceptablePivot)
           continue;
         const double ratio = dtil[e] / aabs[e];
         if (ratio < thetaStar || ratio > harrisG)

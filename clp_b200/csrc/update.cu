@@ -40,7 +40,8 @@ __global__ void chuzr_kernel(DeviceModel d)
   }
   for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < d.m; p += gridDim.x * blockDim.x) {
     const int seq = d.pivotVariable[p];
-    best = max(best, chuzr_key(d.sol[seq], d.lower[seq], d.upper[seq], d.weights[p], tol, p));
+    if (!d.flagged[p])
+      best = max(best, chuzr_key(d.sol[seq], d.lower[seq], d.upper[seq], d.weights[p], tol, p));
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1)
@@ -410,12 +411,14 @@ __global__ void __launch_bounds__(256) iteration_update_kernel(DeviceModel d, in
           w = w < kDevexTryNorm ? kDevexTryNorm : w;
           d.weights[p] = w;
         }
-        best = chuzr_key(x, d.lower[seq], d.upper[seq], w, d.primalTolerance, p);
+        if (!d.flagged[p])
+          best = chuzr_key(x, d.lower[seq], d.upper[seq], w, d.primalTolerance, p);
       } else {
         double w = st->rhoNorm2 / (alphaR * alphaR);
         w = w < kDevexTryNorm ? kDevexTryNorm : w;
         d.weights[p] = w;
         const int q = st->seqIn; // becomes basic at this position (housekeeping in the tail)
+        d.flagged[p] = 0; // a new variable at this position
         best = chuzr_key(d.sol[q] + st->thetaPrimal, d.lowerTrue[q], d.upperTrue[q], w, d.primalTolerance, p);
       }
     }
@@ -524,6 +527,20 @@ __global__ void scatter_basic_kernel(DeviceModel d, const double *__restrict__ x
   int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p < d.m)
     d.sol[d.pivotVariable[p]] = x[p];
+}
+// rhs[i] += value of the row variable (basic or not): residual y - A x
+__global__ void primal_residual_rows_kernel(DeviceModel d, double *__restrict__ rhs)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < d.m)
+    rhs[i] += d.sol[d.n + i];
+}
+// sol[pivotVariable[p]] += dx[p]
+__global__ void add_basic_kernel(DeviceModel d, const double *__restrict__ dx)
+{
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < d.m)
+    d.sol[d.pivotVariable[p]] += dx[p];
 }
 // cB[p] = cost[pivotVariable[p]]
 __global__ void gather_basic_cost_kernel(DeviceModel d, double *__restrict__ cb)
@@ -699,6 +716,12 @@ void launch_compute_primals(const DeviceModel &d, double *xn, double *rhs, cudaS
   primal_rhs_slack_kernel<<<(d.m + 255) / 256, 256, 0, s>>>(d, rhs);
   launch_ftran_buffer(d, rhs, 1, false, s);
   scatter_basic_kernel<<<(d.m + 255) / 256, 256, 0, s>>>(d, rhs);
+  // one step of iterative refinement (ClpSimplex::computePrimals, src/ClpSimplex.cpp:1057-1110):
+  // r = y - A x over ALL variables, x_B += B0^-1 r
+  launch_times_rows(d, d.sol, rhs, -1.0, s);
+  primal_residual_rows_kernel<<<(d.m + 255) / 256, 256, 0, s>>>(d, rhs);
+  launch_ftran_buffer(d, rhs, 1, false, s);
+  add_basic_kernel<<<(d.m + 255) / 256, 256, 0, s>>>(d, rhs);
 }
 void launch_compute_duals(const DeviceModel &d, double *pi, double *z, cudaStream_t s)
 {

@@ -110,8 +110,7 @@ class ClpSimplex:
         if red is None:
             return st
         rc = red.dual()
-        if rc == 0:
-            self.postsolve(red)
+        self.postsolve(red)  # also hands a non-optimal status back to this model
         return rc
 
     def writeMps(self, fileName, formatType=1, numberAcross=1, objSense=0.0):
