@@ -1,34 +1,40 @@
 #!/usr/bin/env python
-"""bench.py -- dual-simplex iterations/sec of the B200 engine on BASELINE.json's workload.
+"""bench.py -- dual-simplex iterations/sec (and wall-to-optimal) of the B200 engine on BASELINE.json's workloads.
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload c2|c3|small]
 
-A *step* is one factorization cycle of the hot path: `cycle` dual simplex iterations plus the
-refactorization + recompute (computePrimals/computeDuals) that ends the cycle.  `cycle` is the
-engine's default refactorization interval max(ClpSimplex::defaultFactorizationFrequency, m/5)
-= 2000 for m = 10 000 (an eta costs one 8m-byte panel column per solve here, a refactorization
-O(k^3) flops, so the optimum interval is longer than the reference's 275).  W warm-up steps run
-untimed, then exactly K steps are timed with CUDA events on the engine's stream (max over ranks).
+Workloads
+  N = 1 (default c2): BASELINE.json configs[1] -- synthetic random LP m=10k n=100k 1% nnz, fp64, dual
+      steepest edge, no presolve / scaling / perturbation.  A *step* is one factorization cycle of the
+      hot path: `cycle` = 2000 dual simplex iterations plus the refactorization + recompute that ends
+      the cycle.  The timed window starts from a mid-solve basis (tests/golden/c2_status_it12000.npz:
+      the basis the CPU oracle reaches after 12 000 iterations) so that the nucleus of the basis has a
+      representative size.  After the window the SAME LP is solved from the all-slack basis to
+      optimality: `wall_to_optimal_s`, final status and the planted optimum check.
+  N > 1 (default c3): BASELINE.json configs[2] -- m=50k n=500k 1% nnz (2.5e8 nonzeros), the size
+      north_star assigns to several GPUs.  One process per GPU; the matrix is column-sharded for the
+      pricing pass and the factors (rows of the nucleus inverse, rows of the eta panel) are row-sharded;
+      every rank holds the same m-vectors after ONE in-place NCCL all-gather per solve / pricing pass.
+      A step is 512 iterations (a quarter of the 2048-iteration factorization cycle, so the window
+      holds one refactorization per four steps).  `python bench.py --gpus 1 --workload c3` measures the
+      same workload on one GPU (profiles/ holds that line; quoted in `strong_scaling_reference`).
+  Inputs are larger than L2 (CSC copy of A >= 120 MB + factors), no L2 flush is needed.
 
-Workload (N = 1): BASELINE.json configs[1] -- synthetic random LP m=10k n=100k 1% nnz, fp64,
-dual steepest edge, no presolve / scaling / perturbation.  The timed window starts from a
-mid-solve basis (tests/golden/c2_status_it12000.npz: the basis the CPU oracle reaches after
-12 000 iterations) so that the nucleus of the basis has a representative size; inputs are
-larger than L2 (CSC copy of A = 120 MB + factors), no L2 flush is needed.
+W warm-up steps run untimed, then exactly K steps are timed with CUDA events on the engine's stream
+(max over ranks).
 
-For N > 1 the same LP is solved with column-sharded pricing (one process per GPU, one NCCL
-all-gather of the tableau-row shards per pricing pass): strong scaling.
-
---impl reference times the reference's CPU implementation of the path.  coin-or/Clp cannot be
-built here (its CoinUtils dependency is absent), so the arm runs the CPU restatement in oracle/
-("kind": "port") on all host cores; a step is a bounded sample of 25 iterations of the same
-window.
+--impl reference times the reference's CPU implementation of the path.  coin-or/Clp cannot be built
+here (its CoinUtils dependency is absent), so the arm runs the CPU restatement in oracle/
+("kind": "port") on all host cores on the same workload, window and configuration; each step is a
+bounded sample (25 iterations) of the factorization cycle, refactorizing at the reference's own
+default frequency.
 """
 from __future__ import annotations
 
 import argparse
 import json
 import os
+import shutil
 import subprocess
 import sys
 import threading
@@ -40,10 +46,10 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WORKLOADS = {
-    # name: (m, n, density, seed)
-    "c2": (10000, 100000, 0.01, 20260923),
-    "c3": (50000, 500000, 0.01, 20260924),
-    "small": (1000, 10000, 0.01, 20260923),
+    # name: (m, n, density, seed, generator)
+    "c2": (10000, 100000, 0.01, 20260923, "random_sparse_lp"),
+    "c3": (50000, 500000, 0.01, 20260924, "random_sparse_lp_large"),
+    "small": (1000, 10000, 0.01, 20260923, "random_sparse_lp"),
 }
 REF_ITERS_PER_STEP = 25
 
@@ -58,18 +64,59 @@ def default_cycle(m):
     return max(8, min(2048, max(clp_default_frequency(m), m // 5)))
 
 
-def build_workload(name):
+def step_iterations(name, cycle):
+    return 512 if name == "c3" else cycle
+
+
+def build_workload(name, local_rank=0):
+    """Returns (lp, start status or None, description of the start).  The c3 matrix (4 GB of host
+    arrays) is generated once per node by local rank 0 and shared through /dev/shm."""
     from clp_b200 import generators as G
 
-    m, n, dens, seed = WORKLOADS[name]
-    lp = G.random_sparse_lp(m, n, dens, seed, name=f"rand-{m}x{n}")
+    m, n, dens, seed, gen = WORKLOADS[name]
+    if name == "c3":
+        shm = "/dev/shm" if os.path.isdir("/dev/shm") else "/tmp"
+        path = os.path.join(shm, f"clpb_{name}_{m}x{n}_{seed}.npz")
+        if not os.path.exists(path):
+            if local_rank == 0:
+                lp = getattr(G, gen)(m, n, dens, seed, name=f"rand-{m}x{n}")
+                tmp = path + f".tmp{os.getpid()}.npz"
+                np.savez(tmp, name=lp.name, m=lp.m, n=lp.n, col_start=lp.col_start, row_index=lp.row_index,
+                         element=lp.element, col_lower=lp.col_lower, col_upper=lp.col_upper,
+                         objective=lp.objective, row_lower=lp.row_lower, row_upper=lp.row_upper,
+                         known_objective=lp.known_objective, expect_status=0)
+                os.replace(tmp, path)
+            else:
+                t0 = time.time()
+                while not os.path.exists(path):
+                    time.sleep(1.0)
+                    if time.time() - t0 > 1200:
+                        raise SystemExit("bench.py: timed out waiting for the shared c3 matrix")
+        lp = G.LP.load(path)
+    else:
+        lp = getattr(G, gen)(m, n, dens, seed, name=f"rand-{m}x{n}")
     status, start = None, "all-slack basis"
-    fx = os.path.join(ROOT, "tests", "golden", "c2_status_it12000.npz")
-    if name == "c2" and os.path.exists(fx):
+    fx = os.path.join(ROOT, "tests", "golden", f"{name}_status.npz")
+    if name == "c2":
+        fx = os.path.join(ROOT, "tests", "golden", "c2_status_it12000.npz")
+    if os.path.exists(fx):
         z = np.load(fx)
         status = z["status"].astype(np.uint8)
-        start = f"basis of the CPU oracle after {int(z['iterations'])} iterations (tests/golden/c2_status_it12000.npz)"
+        who = "CPU oracle" if name == "c2" else "GPU engine"
+        start = f"basis of the {who} after {int(z['iterations'])} iterations (tests/golden/{os.path.basename(fx)})"
     return lp, status, start
+
+
+def workload_config(name, lp, start, cycle, world):
+    """The `config` object -- identical for the b200 arm and the reference arm of the same run."""
+    si = step_iterations(name, cycle)
+    step = (f"{cycle} iterations + 1 refactorization" if si == cycle
+            else f"{si} iterations (1 refactorization per {cycle} iterations)")
+    return {"workload": lp.name, "m": lp.m, "n": lp.n, "nnz": lp.nnz, "start": start, "step": step,
+            "pricing": "dual steepest edge", "presolve": "off", "scaling": "off", "perturbation": "off",
+            "l2": "inputs larger than L2 (CSC copy >= 120 MB + factors), no flush",
+            "parallelism": "single GPU" if world == 1 else
+            f"{world} GPUs: column-sharded pricing, row-sharded factors, one all-gather per solve / pricing pass"}
 
 
 class ClockSampler:
@@ -124,30 +171,97 @@ def measured_peak_gbs():
     return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
 
 
-def run_reference(args, lp, status, start, cycle):
-    """CPU arm: the oracle port on all host cores; rank 0 only."""
+def oracle_sample(lp, status, cores, warm_iters, total_iters=None, seconds=None):
+    """The oracle port on the host cores over a bounded sample of the window; returns
+    (iterations/s, iterations, seconds, refactorizations, split)."""
     from oracle.oracle import OracleSimplex
 
-    cores = os.cpu_count() or 1
     o = OracleSimplex(lp)
     if status is not None:
         o.set_status(status)
     o.set_option("threads", cores)
-    o.set_option("warmupIterations", args.warmup * REF_ITERS_PER_STEP)
-    o.set_option("maximumIterations", (args.warmup + args.steps) * REF_ITERS_PER_STEP)
+    o.set_option("warmupIterations", warm_iters)
+    if total_iters is not None:
+        o.set_option("maximumIterations", total_iters)
+    if seconds is not None:
+        o.set_option("maximumSeconds", seconds)
     o.dual()
     sec, its = o.timed_window()
-    value = its / sec if sec > 0 else 0.0
+    return (its / sec if sec > 0 else 0.0), its, sec, o.refactorizations
+
+
+def highs_line(lp, seconds):
+    """External sanity line: HiGHS serial dual simplex on the same LP from its own
+    start for a bounded time -- different code, same algorithm class.  None when the module is absent."""
+    try:
+        from scipy.optimize._highspy import _core as hp
+    except Exception:
+        return None
+    try:
+        h = hp._Highs()
+        for k, v in (("output_flag", False), ("solver", "simplex"), ("simplex_strategy", 1), ("presolve", "off"),
+                     ("threads", 1), ("time_limit", float(seconds))):
+            h.setOptionValue(k, v)
+        inf = hp.kHighsInf
+
+        def cl(v):
+            v = np.array(v, dtype=float)
+            v[v >= 1e29] = inf
+            v[v <= -1e29] = -inf
+            return v
+        L = hp.HighsLp()
+        L.num_col_, L.num_row_ = lp.n, lp.m
+        L.col_cost_ = np.asarray(lp.objective, float)
+        L.col_lower_, L.col_upper_ = cl(lp.col_lower), cl(lp.col_upper)
+        L.row_lower_, L.row_upper_ = cl(lp.row_lower), cl(lp.row_upper)
+        L.a_matrix_.format_ = hp.MatrixFormat.kColwise
+        L.a_matrix_.start_ = np.asarray(lp.col_start, np.int32)
+        L.a_matrix_.index_ = np.asarray(lp.row_index, np.int32)
+        L.a_matrix_.value_ = np.asarray(lp.element, float)
+        h.passModel(L)
+        t = time.perf_counter()
+        h.run()
+        dt = time.perf_counter() - t
+        info = h.getInfo()
+        its = int(info.simplex_iteration_count)
+        return {"value": its / dt if dt > 0 else 0.0, "unit": "iterations/s", "cores": 1, "kind": "highs-ds",
+                "sample": f"HiGHS {getattr(hp, 'HIGHS_VERSION_MAJOR', '')} serial dual simplex, presolve off, from its own "
+                          f"all-slack start: {its} iterations in {dt:.1f} s (time limit {seconds:.0f} s), "
+                          f"model status {str(h.getModelStatus()).split('.')[-1]}"}
+    except Exception as ex:  # the sanity line must never break the bench
+        return {"value": None, "kind": "highs-ds", "sample": f"failed: {ex!r}"}
+
+
+def clp_probe():
+    """Run-time probe for a real Clp on the measurement box (BASELINE.md section 2 line 1)."""
+    exe = shutil.which("clp")
+    lib = None
+    try:
+        import ctypes.util
+
+        lib = ctypes.util.find_library("Clp")
+    except Exception:
+        pass
+    return {"clp_binary": exe, "libClp": lib,
+            "note": "coin-or/Clp not present on this box" if not (exe or lib) else "present (not timed: no MPS hand-off wired)"}
+
+
+def run_reference(args, name, lp, status, start, cycle):
+    """CPU arm: the oracle port on all host cores; rank 0 only."""
+    cores = os.cpu_count() or 1
+    value, its, sec, nref = oracle_sample(lp, status, cores, args.warmup * REF_ITERS_PER_STEP,
+                                          total_iters=(args.warmup + args.steps) * REF_ITERS_PER_STEP)
     sample = (f"{its} iterations ({args.steps} steps x {REF_ITERS_PER_STEP}) of the same window, after "
-              f"{args.warmup * REF_ITERS_PER_STEP} warm-up iterations; oracle/ port of Clp's dual path, "
-              f"{cores} threads in price, LU solves serial")
+              f"{args.warmup * REF_ITERS_PER_STEP} warm-up iterations, refactorizing at the reference's default "
+              f"frequency ({clp_default_frequency(lp.m)}; {nref} refactorizations in the run); oracle/ port of Clp's dual "
+              f"path, {cores} threads in price, LU solves serial")
     return {
         "metric": "dual_simplex_iterations_per_sec", "value": value, "unit": "iterations/s",
         "impl": "reference", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1000.0 * sec / max(1, args.steps), "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": lp.name, "m": lp.m, "n": lp.n, "nnz": lp.nnz, "start": start,
-                   "step": f"{REF_ITERS_PER_STEP} iterations (bounded sample of a {cycle}-iteration cycle)"},
+        "config": workload_config(name, lp, start, cycle, args.gpus),
+        "sample": f"each step is a bounded sample of {REF_ITERS_PER_STEP} iterations of the configured step",
         "cpu_baseline": {"value": value, "unit": "iterations/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -170,25 +284,28 @@ def main():
     ap.add_argument("--steps", type=int, default=8)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--cpu-seconds", type=float, default=20.0)
+    ap.add_argument("--no-optimal", action="store_true", help="skip the solve-to-optimality leg (N=1, c2)")
+    ap.add_argument("--save-status", default=None, help="write the status array after the run (fixture generation)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else max(args.warmup, 1)
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    name = args.workload or ("c2" if max(world, args.gpus) == 1 else "c3")
 
-    lp, status, start = (None, None, None)
-    m = WORKLOADS[args.workload][0]
+    m = WORKLOADS[name][0]
     cycle = default_cycle(m)
+    step_its = step_iterations(name, cycle)
 
     if args.impl == "reference":
         if rank != 0:
             return 0
-        lp, status, start = build_workload(args.workload)
-        print(json.dumps(run_reference(args, lp, status, start, cycle)), file=out, flush=True)
+        lp, status, start = build_workload(name, 0)
+        print(json.dumps(run_reference(args, name, lp, status, start, cycle)), file=out, flush=True)
         return 0
 
     os.environ.setdefault("NCCL_DEBUG", "WARN")  # NCCL's version banner would go to stdout
@@ -204,13 +321,14 @@ def main():
         import torch.distributed as dist
 
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    lp, status, start = build_workload(args.workload)
+    lp, status, start = build_workload(name, local_rank)
 
     def new_model(**params):
         s = clp_b200.ClpSimplex()
         s.loadLP(lp)
-        if status is not None:
+        if status is not None and not params.pop("_from_slack", False):
             s.copyinStatus(status)
+        params.pop("_from_slack", None)
         for k, v in params.items():
             s.setParameter(k, v)
         if world > 1:
@@ -228,8 +346,12 @@ def main():
         torch.cuda.synchronize()
 
     W, K = args.warmup, args.steps
-    # ---------------- device-timed run: inputs resident in HBM before the window opens
-    s = new_model(batch=args.batch, warmupIterations=W * cycle, maximumIterations=(W + K) * cycle,
+    nm = lp.n + lp.m
+    # ---------------- device-timed run: inputs resident in HBM before the window opens.  The same
+    # call is also the end-to-end measurement at N > 1 (host buffers in, solution read back).
+    barrier()
+    t_e2e = time.perf_counter()
+    s = new_model(batch=args.batch, warmupIterations=W * step_its, maximumIterations=(W + K) * step_its,
                   factorizationFrequency=cycle)
     sampler = ClockSampler(local_rank)
     barrier()
@@ -237,30 +359,48 @@ def main():
     st = s.dual()
     barrier()
     clocks = sampler.stop()
+    s.primalColumnSolution(); s.dualRowSolution(); s.statusArray(); s.objectiveValue()
+    wall_e2e = time.perf_counter() - t_e2e
     ms, its = s.timedWindow()
     if dist is not None:
-        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        t = torch.tensor([ms, wall_e2e], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+        ms, wall_e2e = float(t[0].item()), float(t[1].item())
     value = its / (ms / 1000.0) if ms > 0 else 0.0
-    steps_done = its / cycle
+    steps_done = its / step_its
     launches = s.kernelLaunches()
-    status_after = st
     nucleus = s.nucleusSize()
+    if args.save_status and rank == 0:
+        np.savez_compressed(args.save_status, status=s.statusArray(), iterations=s.numberIterations())
 
     result = {
         "metric": "dual_simplex_iterations_per_sec", "value": value, "unit": "iterations/s",
         "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / max(1e-9, steps_done),
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": lp.name, "m": lp.m, "n": lp.n, "nnz": lp.nnz, "start": start,
-                   "step": f"{cycle} iterations + 1 refactorization", "pricing": "dual steepest edge",
-                   "presolve": "off", "scaling": "off", "perturbation": "off",
-                   "l2": "inputs larger than L2 (CSC copy 120 MB + factors), no flush",
-                   "parallelism": "single GPU" if world == 1 else f"column-sharded pricing x{world}, replicated factors",
-                   "timed_iterations": its, "status_after_window": status_after, "nucleus_size": nucleus},
+        "config": workload_config(name, lp, start, cycle, world),
+        "timed_iterations": its, "status_after_window": st, "nucleus_size": nucleus,
+        "refactorizations": s.numberRefactorizations(),
         "clocks": clocks, "gpu_launches": int(launches),
     }
+    h2d = (4 * (lp.n + 1) + 12 * lp.nnz) + (4 * (lp.m + 1) + 12 * lp.nnz) + 8 * 7 * nm + nm + 12 * lp.m
+    d2h = 8 * 2 * nm + 8 * lp.m + nm + 4 * lp.m
+    if world > 1:
+        total_steps = max(1.0, s.numberIterations() / step_its)
+        result["e2e"] = {"value": s.numberIterations() / wall_e2e, "unit": "iterations/s",
+                         "h2d_bytes_per_step": int(h2d / total_steps), "d2h_bytes_per_step": int(d2h / total_steps),
+                         "includes": "per rank: Clpb_loadProblem (pageable host arrays -> HBM), NCCL communicator set-up, "
+                                     "basis hand-over, Clpb_dual for W+K steps, solution read-back; max over ranks",
+                         "wall_s": wall_e2e, "iterations": s.numberIterations()}
+        ref = os.path.join(ROOT, "profiles", f"r2_bench_{name}_n1.json")
+        if os.path.exists(ref):
+            try:
+                r1 = json.load(open(ref))
+                result["strong_scaling_reference"] = {"n1_value": r1["value"], "n1_ms_per_step": r1["ms_per_step"],
+                                                      "source": f"profiles/r2_bench_{name}_n1.json (python bench.py --gpus 1 --workload {name})",
+                                                      "speedup_vs_n1": value / r1["value"] if r1["value"] else None}
+            except Exception:
+                pass
 
     if rank == 0 and world == 1:
         # ---------------- per-kernel timing (CUDA events around single kernels, no graph replay)
@@ -271,7 +411,6 @@ def main():
         ph = p.phaseTimes()
         ns = max(1.0, ph["samples"])
         k = p.nucleusSize()
-        ldk = (k + 7) // 8 * 8
         peak, peak_src = measured_peak_gbs()
         nb = max(1, int((np.asarray(status) == 1)[: lp.n].sum())) if status is not None else 0
         kern = {
@@ -288,8 +427,10 @@ def main():
         # DRAM bytes per launch of that kernel from the committed ncu --set full capture (same
         # workload, same nucleus size); null when the nucleus differs from the captured one
         traffic, traffic_src, capture = None, None, None
-        tp = os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")
-        if os.path.exists(tp):
+        for tp in ("r2_ncu_traffic.json", "r1_ncu_traffic.json"):
+            tp = os.path.join(ROOT, "profiles", tp)
+            if not os.path.exists(tp):
+                continue
             rec = json.load(open(tp)).get(dom)
             if rec:
                 kc = int(rec.get("nucleus_size", 0))
@@ -301,48 +442,63 @@ def main():
                     traffic, traffic_src = rec["traffic"], rec["source"]
                 capture = {"nucleus_size": kc, "algorithmic_bytes": cap, "traffic": rec["traffic"],
                            "traffic_over_algorithmic": rec["traffic"] / cap, "source": rec["source"]}
+                break
         result["roofline"] = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
                               "frac": ach / peak, "frac_of_nominal_8TBps": ach / 8000.0, "traffic": traffic,
                               "traffic_source": traffic_src,
                               "traffic_capture": capture,
                               "peak_source": peak_src,
                               "bytes_per_launch": b, "ms_per_launch": t_ms, "nucleus_size": k,
-                              "all": {q: {"bytes": v[0], "ms": v[1], "GBps": (v[0] / (v[1] * 1e-3) / 1e9 if v[1] > 0 else 0.0)}
+                              "all": {q: {"bytes": v[0], "ms": v[1], "GBps": (v[0] / (v[1] * 1e-3) / 1e9 if v[1] > 0 else 0.0),
+                                          "frac": (v[0] / (v[1] * 1e-3) / 1e9 / peak if v[1] > 0 else 0.0)}
                                       for q, v in kern.items()},
                               "phase_us_per_iteration": {q: 1000.0 * ph[q] / ns for q in
                                                          ("chuzr", "btran", "price", "chuzc", "dualUpdate", "ftran", "update")},
                               "refactor_ms_total": ph["refactor"], "basic_structurals_at_start": nb}
+        del p
         # ---------------- end to end through the C ABI with host buffers
         t0 = time.perf_counter()
-        e = new_model(batch=args.batch, maximumIterations=min(K, 4) * cycle, factorizationFrequency=cycle)
+        e = new_model(batch=args.batch, maximumIterations=min(K, 4) * step_its, factorizationFrequency=cycle)
         e.dual()
-        x = e.primalColumnSolution(); e.dualRowSolution(); e.statusArray(); e.objectiveValue()
+        e.primalColumnSolution(); e.dualRowSolution(); e.statusArray(); e.objectiveValue()
         wall = time.perf_counter() - t0
-        nm = lp.n + lp.m
-        h2d = (4 * (lp.n + 1) + 12 * lp.nnz) + (4 * (lp.m + 1) + 12 * lp.nnz) + 8 * 7 * nm + nm + 12 * lp.m
-        d2h = 8 * 2 * nm + 8 * lp.m + nm + 4 * lp.m
         result["e2e"] = {"value": e.numberIterations() / wall, "unit": "iterations/s",
                          "h2d_bytes_per_step": int(h2d / max(1, min(K, 4))), "d2h_bytes_per_step": int(d2h / max(1, min(K, 4))),
                          "includes": "Clpb_loadProblem (pageable host arrays -> HBM), basis hand-over, "
                                      "Clpb_dual for min(K,4) steps, solution read-back", "wall_s": wall,
                          "iterations": e.numberIterations()}
-        # ---------------- CPU baseline: the oracle port on the host cores, bounded sample
-        from oracle.oracle import OracleSimplex
+        del e
+        # ---------------- wall-to-optimal (the other half of BASELINE.json's metric): the same LP from the
+        # all-slack basis through the public API, host buffers in, solution out, checked against the
+        # planted optimum c^T x* the generator certifies
+        if name in ("c2", "small") and not args.no_optimal:
+            t0 = time.perf_counter()
+            f = new_model(batch=args.batch, factorizationFrequency=cycle, maximumSeconds=600, _from_slack=True)
+            fst = f.dual()
+            xs = f.primalColumnSolution()
+            wall = time.perf_counter() - t0
+            rel = abs(f.objectiveValue() - lp.known_objective) / (1.0 + abs(lp.known_objective))
+            from oracle.oracle import kkt_violations  # checker only, outside every timed region
 
+            result["wall_to_optimal_s"] = wall
+            result["optimal"] = {"status": fst, "objective": f.objectiveValue(), "planted_objective": lp.known_objective,
+                                 "rel_diff": rel, "iterations": f.numberIterations(),
+                                 "refactorizations": f.numberRefactorizations(), "seconds_in_loop": f.secondsInLoop(),
+                                 "iterations_per_sec": f.numberIterations() / max(1e-9, f.secondsInLoop()),
+                                 "kkt_violations": int(kkt_violations(lp, xs, f.primalRowSolution(), f.dualColumnSolution())) if fst == 0 else None,
+                                 "n_basic": int((f.statusArray() == 1).sum()),
+                                 "parity_ok": bool(fst == 0 and rel <= 1e-8),
+                                 "includes": "Clpb_loadProblem, Clpb_dual from the all-slack basis to status 0, solution read-back"}
+            del f
+        # ---------------- CPU baselines on the host cores, bounded samples
         cores = os.cpu_count() or 1
-        o = OracleSimplex(lp)
-        if status is not None:
-            o.set_status(status)
-        o.set_option("threads", cores)
-        o.set_option("maximumSeconds", args.cpu_seconds)
-        o.set_option("warmupIterations", 5)
-        o.dual()
-        sec, cits = o.timed_window()
-        result["cpu_baseline"] = {"value": cits / sec if sec > 0 else 0.0, "unit": "iterations/s", "cores": cores,
-                                  "kind": "port",
+        v, cits, sec, nref = oracle_sample(lp, status, cores, 5, seconds=args.cpu_seconds)
+        result["cpu_baseline"] = {"value": v, "unit": "iterations/s", "cores": cores, "kind": "port",
                                   "sample": f"first {cits} iterations ({sec:.1f} s) of the same window on the host; "
                                             "oracle/ restatement of Clp's dual path (coin-or/Clp itself cannot be "
-                                            "built: CoinUtils absent)"}
+                                            "built: CoinUtils absent)",
+                                  "others": [x for x in (highs_line(lp, args.cpu_seconds),) if x],
+                                  "clp_probe": clp_probe()}
     if rank == 0:
         print(json.dumps(result), file=out, flush=True)
     if dist is not None:

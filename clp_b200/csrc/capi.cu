@@ -229,6 +229,12 @@ int Clpb_setParameter(Clpb_Simplex *model, const char *key, double value)
     e.scalingFlag = (int)value;
   else if (k == "perturbation")
     e.perturbation = (int)value;
+  else if (k == "shardMinNnzPerRank")
+    e.shardMinNnzPerRank = (long long)value;
+  else if (k == "factorMode")
+    e.factorMode = (int)value;
+  else if (k == "acceptablePivot")
+    e.acceptablePivot = value;
   else
     return -1;
   return 0;

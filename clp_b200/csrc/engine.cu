@@ -617,13 +617,23 @@ int Engine::readBasis(const char *fileName)
   return bad;
 }
 
+bool Engine::shardActive() const
+{
+  if (worldSize <= 1 || allGatherFn == nullptr || hColStart.empty())
+    return false;
+  const long long per = (n + worldSize - 1) / worldSize;
+  if (per * worldSize > nm) // the in-place all-gather of the row shards pads into the slack part
+    return false;
+  return (long long)hColStart[n] / worldSize >= shardMinNnzPerRank;
+}
+
 int Engine::setupDevice()
 {
   // what the device copy was built for: a later scaling() / factorizationFrequency / timing change
   // rebuilds it instead of being silently ignored
   const long long signature = (long long)scalingFlag * 1000003ll + (long long)factorizationFrequency * 101ll +
                               (timing ? 7 : 0) + (long long)worldSize * 13ll + (long long)rank * 17ll +
-                              (usePriceTma ? 3 : 0) + (long long)factorMode * 29ll;
+                              (usePriceTma ? 3 : 0) + (long long)factorMode * 29ll + (shardActive() ? 31 : 0);
   if (deviceReady && signature == readySignature)
     return 0;
   if (deviceReady)
@@ -660,9 +670,10 @@ int Engine::setupDevice()
   d.val = q;
   {
     // cut this rank's column range into tiles of whole columns, <= kPriceTile entries each
-    int per = (n + worldSize - 1) / worldSize;
-    int cb = worldSize > 1 ? std::min(n, rank * per) : 0;
-    int ce = worldSize > 1 ? std::min(n, cb + per) : n;
+    const bool sh = shardActive();
+    int per = sh ? (n + worldSize - 1) / worldSize : n;
+    int cb = sh ? std::min(n, rank * per) : 0;
+    int ce = sh ? std::min(n, cb + per) : n;
     std::vector<int> tiles;
     bool ok = true;
     int c = cb;
@@ -803,6 +814,25 @@ int Engine::setupDevice()
   d.dualTolerance = dualTolerance;
   d.zeroTolerance = zeroTolerance;
   d.flagged = dalloc<unsigned char>(m);
+  d.shardW = 1;
+  d.shardRank = 0;
+  d.shardPerK = d.shardPerM = roundUp(m, 8);
+  d.gatherY = d.gatherB = d.gatherP = nullptr;
+  if (shardActive()) {
+    d.shardW = worldSize;
+    d.shardRank = rank;
+    d.shardPerK = d.shardPerM = roundUp((m + worldSize - 1) / worldSize, 8);
+    d.gatherY = dalloc<double>((size_t)worldSize * 3 * d.shardPerK);
+    d.gatherB = dalloc<double>((size_t)worldSize * d.shardPerK);
+    d.gatherP = dalloc<double>((size_t)worldSize * 3 * d.shardPerM);
+    CUDA_OK(cudaMemset(d.gatherY, 0, sizeof(double) * worldSize * 3 * d.shardPerK));
+    CUDA_OK(cudaMemset(d.gatherB, 0, sizeof(double) * worldSize * d.shardPerK));
+    CUDA_OK(cudaMemset(d.gatherP, 0, sizeof(double) * worldSize * 3 * d.shardPerM));
+    g_shardCtx.W = worldSize;
+    g_shardCtx.rank = rank;
+    g_shardCtx.comm = ncclComm;
+    g_shardCtx.allGather = allGatherFn;
+  }
   CUDA_OK(cudaMemset(d.flagged, 0, m));
 
   CUDA_OK(cudaMemcpy(d.costTrue, wCost.data(), sizeof(double) * nm, cudaMemcpyHostToDevice));
@@ -1012,8 +1042,15 @@ int Engine::refactor()
       int kc = std::min(m, std::max(k + k / 4 + 64, 256));
       int ldc = roundUp(kc, 8);
       nucCap = (size_t)kc * ldc;
-      d.Ninv = dalloc<double>(nucCap);
-      d.NinvT = dalloc<double>(nucCap);
+      // the old (smaller) pair is released first: at m = 5e4 a factor pair is up to 40 GB
+      for (double *old : {d.Ninv, d.NinvT})
+        if (old) {
+          CUDA_OK(cudaFree(old));
+          allocs.erase(std::remove(allocs.begin(), allocs.end(), (void *)old), allocs.end());
+        }
+      // + worldSize columns: the in-place all-gather of the sharded inverse rounds k up to W*ceil(k/W)
+      d.Ninv = dalloc<double>(nucCap + (size_t)(worldSize + 1) * ldc);
+      d.NinvT = dalloc<double>(nucCap + (size_t)(worldSize + 1) * ldc);
     }
     d.k = k;
     d.ldk = ldk;
@@ -1049,7 +1086,10 @@ int Engine::refactor()
       CUDA_OK(cudaMemsetAsync(d.NinvT, 0, sizeof(double) * (size_t)k * ldk, stream));
       launch_gather_nucleus_matrix(d, d.NinvT, ldk, stream);
       info = dense_invert(d.NinvT, d.Ninv, k, ldk, dIpiv, dPerm, dInfo, hostIpiv.data(),
-                          hostPerm.data(), 1.0e-11, stream);
+                          hostPerm.data(), 1.0e-11, stream, d.shardW, d.shardRank,
+                          d.shardW > 1 ? allGatherFn : nullptr, ncclComm);
+      if (info < 0)
+        throw std::runtime_error("clp_b200: refactorization failed (allocation or collective)");
       kernelLaunches += 6 * ((k + 31) / 32) * 2;
     }
     if (info == 0) {
@@ -1138,6 +1178,15 @@ int Engine::refresh()
   launch_make_dual_feasible(d, currentDualBound, dCounters, stream);
   launch_compute_primals(d, dXn, dRhs, stream);
   kernelLaunches += 20;
+  if (logLevel > 0 && (numberRefactorizations % (logLevel > 1 ? 1 : 25)) == 0) {
+    // progress line (the reference prints objective / infeasibilities at every refactorization)
+    launch_objective(d, dObj, stream);
+    double obj2[2];
+    CUDA_OK(cudaMemcpyAsync(obj2, dObj, sizeof(double) * 2, cudaMemcpyDeviceToHost, stream));
+    CUDA_OK(cudaStreamSynchronize(stream));
+    fprintf(stderr, "clp_b200: it %d refactorizations %d nucleus %d objective %.10g sum primal inf %.6g\n",
+            numberIterations, numberRefactorizations, d.k, obj2[0] + objectiveOffset, obj2[1]);
+  }
   return 0;
 }
 
@@ -1155,7 +1204,7 @@ void Engine::enqueueIteration(bool timed, int slot)
   if (timed)
     cudaEventRecord(ev[2], stream);
   bool rowPassed = false;
-  if (worldSize > 1) {
+  if (d.shardW > 1) {
     // column-sharded pricing: this rank's block of raw dot products, then ONE exchange per pricing
     // pass -- an in-place all-gather of the row shards (padded to 'per' entries; the padding lands
     // on the slack part of the row, which the row kernels recompute from rho).  Everything after
@@ -1163,7 +1212,8 @@ void Engine::enqueueIteration(bool timed, int slot)
     int per = (n + worldSize - 1) / worldSize;
     int c0 = std::min(n, rank * per), c1 = std::min(n, c0 + per);
     launch_price(d, c0, c1, false, stream);
-    allGatherFn(ncclComm, d.alphaRow, sizeof(double) * per, stream);
+    if (allGatherFn(ncclComm, d.alphaRow, sizeof(double) * per, stream) != 0)
+      throw std::runtime_error("clp_b200: all-gather of the row shards failed");
   } else {
     launch_price(d, 0, n, false, stream);
   }
@@ -1197,7 +1247,7 @@ void Engine::enqueueIteration(bool timed, int slot)
   if (timed)
     cudaEventRecord(ev[7], stream);
   g_kernelTimers = nullptr;
-  kernelLaunches += rowPassed ? 3 + 1 + 1 + 4 + 1 : 3 + 2 + 4 + 3 + 5 + 1;
+  kernelLaunches += (rowPassed ? 3 + 1 + 1 + 4 + 1 : 3 + 2 + 4 + 3 + 5 + 1) + (d.shardW > 1 ? 2 : 0);
 }
 
 // start of a batch: stand-alone CHUZR (2 kernels)

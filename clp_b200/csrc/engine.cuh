@@ -168,6 +168,15 @@ struct DeviceModel {
   int recCap;
   // tolerances
   double primalTolerance, dualTolerance, zeroTolerance;
+  // row-sharded factors (multi-GPU, see DESIGN.md "Multi-GPU"): rank shardRank of shardW streams
+  // rows [rank*per_k, (rank+1)*per_k) of Ninv / NinvT (per_k = roundUp8(ceil(k/W)), k from
+  // FactorDesc) and positions [rank*shardPerM, ...) of the eta panel W; results go to gather buffers
+  // with a fixed per-rank chunk (shardPerK / shardPerM entries per vector) that ONE in-place
+  // all-gather per solve completes.  shardW == 1: plain single-GPU layout.
+  int shardW, shardRank, shardPerK, shardPerM;
+  double *gatherY; // [W][3][shardPerK]  FTRAN GEMV results
+  double *gatherB; // [W][shardPerK]     BTRAN GEMV results
+  double *gatherP; // [W][3][shardPerM]  eta-panel results
   unsigned char *flagged; // [m] by position: 1 = row is flagged (skipped by CHUZR until the next refactorization)
 };
 
@@ -177,6 +186,13 @@ struct KernelTimers {
 };
 extern KernelTimers *g_kernelTimers; // nullptr outside timing mode (engine.cu)
 extern int g_pfiApplyVariant;         // solve.cu
+// collectives of a sharded run (host side; set by Engine before it enqueues work)
+struct ShardCtx {
+  int W = 1, rank = 0;
+  void *comm = nullptr;
+  int (*allGather)(void *comm, void *buf, size_t bytesPerRank, void *stream) = nullptr; // in place
+};
+extern ShardCtx g_shardCtx;           // solve.cu
 
 // ---- launch wrappers (implemented in the .cu files) ---------------------------------------
 // solve.cu
@@ -213,7 +229,9 @@ void launch_unpack_column(const DeviceModel &d, int seq, double *out, cudaStream
 void launch_eta_append_test(const DeviceModel &d, int pivotRow, int seqIn, cudaStream_t s);
 // factor.cu
 int dense_invert(double *A, double *X, int k, int ld, int *dIpiv, int *dPerm, int *dInfo,
-                 int *hostIpiv, int *hostPerm, double singularTol, cudaStream_t s);
+                 int *hostIpiv, int *hostPerm, double singularTol, cudaStream_t s, int shardW = 1,
+                 int shardRank = 0, int (*allGather)(void *, void *, size_t, void *) = nullptr,
+                 void *comm = nullptr);
 void launch_transpose(const double *src, double *dst, int k, int ld, cudaStream_t s);
 
 } // namespace clpb

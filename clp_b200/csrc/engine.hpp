@@ -69,6 +69,11 @@ public:
   int rank = 0, worldSize = 1;
   void *ncclComm = nullptr; // ncclComm_t when worldSize > 1
   int (*allGatherFn)(void *comm, void *buf, size_t bytesPerRank, void *stream) = nullptr;
+  // sharding is used only when a rank's share of the matrix is large enough to amortise the
+  // collectives' latency (north_star: "only when n is large enough"); otherwise every rank runs the
+  // whole iteration on its own ("replicas only")
+  long long shardMinNnzPerRank = 4000000;
+  bool shardActive() const;
 
   // ---- solve (ClpSimplex::dual) ----
   int dual();

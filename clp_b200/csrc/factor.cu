@@ -491,7 +491,8 @@ __global__ void zero_padding_kernel(double *__restrict__ M, int k, int ld)
    dIpiv/dPerm/dInfo: device scratch.  Returns 0 or (1 + index of the first column without an
    acceptable pivot).  Synchronizes the stream once (pivot vector -> permutation). */
 int dense_invert(double *A, double *X, int k, int ld, int *dIpiv, int *dPerm, int *dInfo,
-                 int *hostIpiv, int *hostPerm, double singularTol, cudaStream_t s)
+                 int *hostIpiv, int *hostPerm, double singularTol, cudaStream_t s, int shardW,
+                 int shardRank, int (*allGather)(void *, void *, size_t, void *), void *comm)
 {
   if (k <= 0)
     return 0;
@@ -502,13 +503,18 @@ int dense_invert(double *A, double *X, int k, int ld, int *dIpiv, int *dPerm, in
   static unsigned int *barCounter = nullptr;
   static int numSMs = 0;
   if (!pubKey) {
-    cudaDeviceGetAttribute(&numSMs, cudaDevAttrMultiProcessorCount, 0);
+    int dev = 0;
+    cudaGetDevice(&dev); // one process drives one device
+    cudaDeviceGetAttribute(&numSMs, cudaDevAttrMultiProcessorCount, dev);
     if (numSMs <= 0)
       numSMs = 148;
-    cudaMalloc(&pubKey, sizeof(unsigned long long) * NB * numSMs);
-    cudaMalloc(&pubRows, sizeof(double) * NB * numSMs * NB);
-    cudaMalloc(&pubDiag, sizeof(double) * NB * NB);
-    cudaMalloc(&barCounter, sizeof(unsigned int));
+    if (cudaMalloc(&pubKey, sizeof(unsigned long long) * NB * numSMs) != cudaSuccess ||
+        cudaMalloc(&pubRows, sizeof(double) * NB * numSMs * NB) != cudaSuccess ||
+        cudaMalloc(&pubDiag, sizeof(double) * NB * NB) != cudaSuccess ||
+        cudaMalloc(&barCounter, sizeof(unsigned int)) != cudaSuccess) {
+      pubKey = nullptr;
+      return -99;
+    }
     cudaFuncSetAttribute(lu_panel_coop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          kPanelMaxRowsPerCta * kSlabPitch * (int)sizeof(double));
   }
@@ -529,9 +535,13 @@ int dense_invert(double *A, double *X, int k, int ld, int *dIpiv, int *dPerm, in
       double tolarg = singularTol;
       void *args[] = {&Aarg, &karg, &ldarg, &j0arg, &nbarg, &Rarg, &dIpiv, &dInfo, &tolarg,
                       &pubKey, &pubRows, &pubDiag, &barCounter, &barrierBase};
-      cudaLaunchCooperativeKernel((void *)lu_panel_coop_kernel, dim3(G), dim3(256), args,
-                                  (size_t)R * kSlabPitch * sizeof(double), s);
-      barrierBase += (unsigned int)nb * (unsigned int)G;
+      if (cudaLaunchCooperativeKernel((void *)lu_panel_coop_kernel, dim3(G), dim3(256), args,
+                                      (size_t)R * kSlabPitch * sizeof(double), s) != cudaSuccess) {
+        cudaGetLastError(); // the single-CTA panel kernel does the same work without a grid barrier
+        lu_panel_kernel<<<1, 1024, 0, s>>>(A, k, ld, j0, nb, dIpiv, dInfo, singularTol);
+      } else {
+        barrierBase += (unsigned int)nb * (unsigned int)G;
+      }
     } else {
       lu_panel_kernel<<<1, 1024, 0, s>>>(A, k, ld, j0, nb, dIpiv, dInfo, singularTol);
     }
@@ -571,18 +581,32 @@ int dense_invert(double *A, double *X, int k, int ld, int *dIpiv, int *dPerm, in
   // inside an outer block of OB columns, one rank-OB update per outer block for the rest (the bulk
   // of the 2k^3 flops then runs with K = OB, where the DGEMM is not bound by the C traffic).
   constexpr int OB = 128;
+  // Multi-GPU: the columns of X are independent in both substitutions, so rank r computes the block
+  // [xc0, xc1) only (2k^3/W of the 2k^3 flops of this phase) and ONE in-place all-gather of
+  // perC*ld doubles per rank completes X on every rank; the LU above (2/3 k^3) stays replicated.
+  int xc0 = 0, xc1 = k, perC = k;
+  if (shardW > 1 && allGather != nullptr) {
+    perC = (k + shardW - 1) / shardW;
+    xc0 = shardRank * perC < k ? shardRank * perC : k;
+    xc1 = xc0 + perC < k ? xc0 + perC : k;
+  }
+  double *const Xfull = X;
+  const int kfull = k; // rows of X (the substitutions run over all k rows of the column block)
+  X = Xfull + (size_t)xc0 * ld;
+  const int ncol = xc1 - xc0; // columns of this rank
   // forward: X := L^-1 X
   for (int J0 = 0; J0 < k; J0 += OB) {
     const int J1 = J0 + OB < k ? J0 + OB : k;
     for (int j0 = J0; j0 < J1; j0 += NB) {
       int nb = J1 - j0 < NB ? J1 - j0 : NB;
-      trsm_kernel<<<(k + 127) / 128, 128, 0, s>>>(A, ld, X, ld, j0, nb, 0, k, true);
+      if (ncol > 0)
+        trsm_kernel<<<(ncol + 127) / 128, 128, 0, s>>>(A, ld, X, ld, j0, nb, 0, ncol, true);
       int r0 = j0 + nb;
       if (r0 < J1)
-        gemm_sub(X + r0, ld, A + (size_t)j0 * ld + r0, ld, X + j0, ld, J1 - r0, k, nb, s);
+        gemm_sub(X + r0, ld, A + (size_t)j0 * ld + r0, ld, X + j0, ld, J1 - r0, ncol, nb, s);
     }
     if (J1 < k)
-      gemm_sub(X + J1, ld, A + (size_t)J0 * ld + J1, ld, X + J0, ld, k - J1, k, J1 - J0, s);
+      gemm_sub(X + J1, ld, A + (size_t)J0 * ld + J1, ld, X + J0, ld, k - J1, ncol, J1 - J0, s);
   }
   // backward: X := U^-1 X
   const int lastOuter = ((k - 1) / OB) * OB;
@@ -591,12 +615,19 @@ int dense_invert(double *A, double *X, int k, int ld, int *dIpiv, int *dPerm, in
     const int lastInner = J0 + ((J1 - J0 - 1) / NB) * NB;
     for (int j0 = lastInner; j0 >= J0; j0 -= NB) {
       int nb = J1 - j0 < NB ? J1 - j0 : NB;
-      trsm_kernel<<<(k + 127) / 128, 128, 0, s>>>(A, ld, X, ld, j0, nb, 0, k, false);
+      if (ncol > 0)
+        trsm_kernel<<<(ncol + 127) / 128, 128, 0, s>>>(A, ld, X, ld, j0, nb, 0, ncol, false);
       if (j0 > J0)
-        gemm_sub(X + J0, ld, A + (size_t)j0 * ld + J0, ld, X + j0, ld, j0 - J0, k, nb, s);
+        gemm_sub(X + J0, ld, A + (size_t)j0 * ld + J0, ld, X + j0, ld, j0 - J0, ncol, nb, s);
     }
     if (J0 > 0)
-      gemm_sub(X, ld, A + (size_t)J0 * ld, ld, X + J0, ld, J0, k, J1 - J0, s);
+      gemm_sub(X, ld, A + (size_t)J0 * ld, ld, X + J0, ld, J0, ncol, J1 - J0, s);
+  }
+  X = Xfull;
+  (void)kfull;
+  if (shardW > 1 && allGather != nullptr) {
+    if (allGather(comm, X, sizeof(double) * (size_t)perC * ld, s) != 0)
+      return -98;
   }
   zero_padding_kernel<<<(k + 255) / 256, 256, 0, s>>>(X, k, ld);
   return 0;

@@ -15,10 +15,13 @@
 // updateTwoColumnsFT fusion, plus the bound-flip column of ClpSimplexDual.cpp:1533).
 #include "kernels_common.cuh"
 
+#include <stdexcept>
+
 namespace clpb {
 
 static inline int roundUp8(int v) { return (v + 7) / 8 * 8; }
 
+ShardCtx g_shardCtx;
 int g_pfiApplyVariant = 0; // 0: warp per panel row, 1: GEMV-shaped (two rows per CTA); "pfiApplyVariant"
 
 // ---------------------------------------------------------------------------------------
@@ -52,18 +55,27 @@ template <int NRHS, int R, int DEPTH>
 __global__ void __launch_bounds__(256)
     gemv_rows_kernel(const FactorDesc *__restrict__ fd, int transposed,
                      const double *__restrict__ x, double *__restrict__ out, int ostride,
-                     const int *__restrict__ outIndex, const IterState *st, bool checkState)
+                     const int *__restrict__ outIndex, const IterState *st, bool checkState,
+                     int shardW, int shardRank, int shardPer)
 {
   if (checkState && !iter_active(st))
     return;
   __shared__ double part[8][R * NRHS];
   const int k = fd->k, ldk = fd->ldk;
+  // row-sharded run: this rank streams rows [rowBegin, rowEnd) and writes them to its chunk of the
+  // gather buffer out[rank][c][shardPer] (completed by one in-place all-gather)
+  int rowBegin = 0, rowEnd = k;
+  if (shardW > 1) {
+    const int perK = ((k + shardW - 1) / shardW + 7) & ~7;
+    rowBegin = min(k, shardRank * perK);
+    rowEnd = min(k, rowBegin + perK);
+  }
   const double *__restrict__ M = transposed ? fd->NinvT : fd->Ninv;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int half = ldk >> 1; // ldk is a multiple of 8, padding is zero
-  const int ngroups = (k + R - 1) / R;
+  const int ngroups = (rowEnd - rowBegin + R - 1) / R;
   for (int g = blockIdx.x; g < ngroups; g += gridDim.x) {
-    const int i0 = g * R;
+    const int i0 = rowBegin + g * R;
     const double2 *row[R];
 #pragma unroll
     for (int r = 0; r < R; r++) // rows beyond k alias the last row (results discarded)
@@ -112,14 +124,29 @@ __global__ void __launch_bounds__(256)
       for (int w = 0; w < 8; w++)
         sum += part[w][threadIdx.x];
       const int r = threadIdx.x / NRHS, c = threadIdx.x % NRHS;
-      if (i0 + r < k) {
-        const int o = outIndex ? outIndex[i0 + r] : i0 + r;
-        const int os = ostride < 0 ? ldk : ostride;
-        out[(size_t)c * os + o] = sum;
+      if (i0 + r < rowEnd) {
+        if (shardW > 1) {
+          out[((size_t)shardRank * NRHS + c) * shardPer + (i0 + r - rowBegin)] = sum;
+        } else {
+          const int o = outIndex ? outIndex[i0 + r] : i0 + r;
+          const int os = ostride < 0 ? ldk : ostride;
+          out[(size_t)c * os + o] = sum;
+        }
       }
     }
     __syncthreads();
   }
+}
+
+// entry j of GEMV result c: plain [c][ldk] layout, or the gathered [rank][c][shardPerK] layout
+template <int NRHS>
+__device__ __forceinline__ double gemv_result(const DeviceModel &d, const double *__restrict__ y, int c, int j,
+                                              int ldk, int perK)
+{
+  if (d.shardW == 1)
+    return y[(size_t)c * ldk + j];
+  const int rk = j / perK;
+  return y[((size_t)rk * NRHS + c) * d.shardPerK + (j - rk * perK)];
 }
 
 // x_N = yN ; x_C = S1*yN - b_C   (in place on b, 8 lanes per position).  etaTail: the last CTA
@@ -137,13 +164,14 @@ __global__ void __launch_bounds__(256)
   if (p < d.m) { // whole 8-lane groups take the same branch
     const unsigned gmask = 0xFFu << ((threadIdx.x & 31) & ~7);
     const int ldk = d.fd->ldk;
+    const int perK = d.shardW > 1 ? (((d.fd->k + d.shardW - 1) / d.shardW + 7) & ~7) : 1;
     const int *__restrict__ s1Col = d.fd->s1Col;
     const double *__restrict__ s1Val = d.fd->s1Val;
     const int ni = d.posToNuc[p];
     if (ni >= 0) {
       if (sub == 0)
         for (int c = 0; c < NRHS; c++)
-          b[(size_t)c * bstride + p] = y[(size_t)c * ldk + ni];
+          b[(size_t)c * bstride + p] = gemv_result<NRHS>(d, y, c, ni, ldk, perK);
     } else {
       double acc[NRHS];
 #pragma unroll
@@ -156,7 +184,7 @@ __global__ void __launch_bounds__(256)
           int j = s1Col[e];
 #pragma unroll
           for (int c = 0; c < NRHS; c++)
-            acc[c] = fma(v, y[(size_t)c * ldk + j], acc[c]);
+            acc[c] = fma(v, gemv_result<NRHS>(d, y, c, j, ldk, perK), acc[c]);
         }
       }
 #pragma unroll
@@ -336,10 +364,15 @@ __global__ void __launch_bounds__(256) pfi_apply_warp_kernel(DeviceModel d, doub
   if (checkState && !iter_active(d.st))
     return;
   const int t = d.st->numEtas;
-  if (t > 0) {
+  // row-sharded run: this rank's positions only, results into its chunk of gatherP (written even
+  // when there is no eta: the all-gather and the merge that follow are part of a fixed sequence)
+  const bool sharded = d.shardW > 1;
+  const int pBegin = sharded ? min(d.m, d.shardRank * d.shardPerM) : 0;
+  const int pEnd = sharded ? min(d.m, pBegin + d.shardPerM) : d.m;
+  if (t > 0 || sharded) {
     const int lane = threadIdx.x & 31;
     const int warpsPerBlock = blockDim.x >> 5;
-    for (int p = blockIdx.x * warpsPerBlock + (threadIdx.x >> 5); p < d.m;
+    for (int p = pBegin + blockIdx.x * warpsPerBlock + (threadIdx.x >> 5); p < pEnd;
          p += gridDim.x * warpsPerBlock) {
       const double *wrow = d.W + (size_t)p * d.tmax;
       double acc[NRHS];
@@ -363,9 +396,36 @@ __global__ void __launch_bounds__(256) pfi_apply_warp_kernel(DeviceModel d, doub
       for (int c = 0; c < NRHS; c++)
         acc[c] = warp_sum(acc[c]);
       if (lane == 0)
-        for (int c = 0; c < NRHS; c++)
-          x[(size_t)c * xstride + p] -= acc[c];
+        for (int c = 0; c < NRHS; c++) {
+          if (sharded)
+            d.gatherP[((size_t)d.shardRank * NRHS + c) * d.shardPerM + (p - pBegin)] = x[(size_t)c * xstride + p] - acc[c];
+          else
+            x[(size_t)c * xstride + p] -= acc[c];
+        }
     }
+  }
+  if (!pivotTail || sharded) // sharded: the gate runs as the tail of pfi_merge_kernel, after the gather
+    return;
+  if (!last_block_done(d.tailCounter + TAIL_PFI_APPLY))
+    return;
+  if (threadIdx.x == 0)
+    pivot_scalars_body(d);
+}
+
+// sharded run, after the all-gather of gatherP: x_c[p] = gathered value (thread per position);
+// pivotTail as in pfi_apply_warp_kernel
+template <int NRHS>
+__global__ void __launch_bounds__(256) pfi_merge_kernel(DeviceModel d, double *__restrict__ x, int xstride,
+                                                        bool checkState, bool pivotTail)
+{
+  if (checkState && !iter_active(d.st))
+    return;
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < d.m) {
+    const int rk = p / d.shardPerM, off = p - rk * d.shardPerM;
+#pragma unroll
+    for (int c = 0; c < NRHS; c++)
+      x[(size_t)c * xstride + p] = d.gatherP[((size_t)rk * NRHS + c) * d.shardPerM + off];
   }
   if (!pivotTail)
     return;
@@ -373,6 +433,25 @@ __global__ void __launch_bounds__(256) pfi_apply_warp_kernel(DeviceModel d, doub
     return;
   if (threadIdx.x == 0)
     pivot_scalars_body(d);
+}
+
+// rho[nucRow[i]] = gathered BTRAN GEMV result i (sharded run)
+__global__ void btran_scatter_kernel(DeviceModel d, double *__restrict__ rhoOut, bool checkState)
+{
+  if (checkState && !iter_active(d.st))
+    return;
+  const int k = d.fd->k;
+  const int perK = ((k + d.shardW - 1) / d.shardW + 7) & ~7;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < k; i += gridDim.x * blockDim.x) {
+    const int rk = i / perK;
+    rhoOut[d.nucRow[i]] = d.gatherB[(size_t)rk * d.shardPerK + (i - rk * perK)];
+  }
+}
+
+static void shard_all_gather(void *buf, size_t bytesPerRank, cudaStream_t s)
+{
+  if (g_shardCtx.allGather(g_shardCtx.comm, buf, bytesPerRank, s) != 0)
+    throw std::runtime_error("clp_b200: all-gather failed");
 }
 
 template <int NRHS>
@@ -391,16 +470,29 @@ static void ftran_impl(const DeviceModel &d, double *b, bool applyEtas, bool che
   int blocks = maxk < 148 * 8 ? maxk : 148 * 8;
   if (g_kernelTimers && checkState)
     cudaEventRecord(g_kernelTimers->ftranGemv[0], s);
+  const bool sharded = d.shardW > 1;
+  double *y = sharded ? d.gatherY : d.ywork;
   if (NRHS == 1)
-    gemv_rows_kernel<NRHS, 1, 8><<<blocks, 256, 0, s>>>(d.fd, 0, xg, d.ywork, -1, nullptr, d.st, checkState);
+    gemv_rows_kernel<NRHS, 1, 8><<<blocks, 256, 0, s>>>(d.fd, 0, xg, y, -1, nullptr, d.st, checkState,
+                                                        d.shardW, d.shardRank, d.shardPerK);
   else
-    gemv_rows_kernel<NRHS, 2, 2><<<blocks, 256, 0, s>>>(d.fd, 0, xg, d.ywork, -1, nullptr, d.st, checkState);
+    gemv_rows_kernel<NRHS, 2, 2><<<blocks, 256, 0, s>>>(d.fd, 0, xg, y, -1, nullptr, d.st, checkState,
+                                                        d.shardW, d.shardRank, d.shardPerK);
   if (g_kernelTimers && checkState)
     cudaEventRecord(g_kernelTimers->ftranGemv[1], s);
-  ftran_spread_kernel<NRHS><<<(m * 8 + 255) / 256, 256, 0, s>>>(d, b, m, d.ywork, checkState, applyEtas);
+  if (sharded)
+    shard_all_gather(d.gatherY, sizeof(double) * NRHS * d.shardPerK, s);
+  ftran_spread_kernel<NRHS><<<(m * 8 + 255) / 256, 256, 0, s>>>(d, b, m, y, checkState, applyEtas);
   if (applyEtas) {
     pfi_mu_kernel<NRHS><<<d.tmax, 256, 0, s>>>(d, checkState);
-    if (g_pfiApplyVariant == 1) {
+    if (sharded) {
+      int pblocks = (d.shardPerM + 7) / 8;
+      if (pblocks > 148 * 8)
+        pblocks = 148 * 8;
+      pfi_apply_warp_kernel<NRHS><<<pblocks, 256, 0, s>>>(d, b, m, checkState, false);
+      shard_all_gather(d.gatherP, sizeof(double) * NRHS * d.shardPerM, s);
+      pfi_merge_kernel<NRHS><<<(m + 255) / 256, 256, 0, s>>>(d, b, m, checkState, pivotTail);
+    } else if (g_pfiApplyVariant == 1) {
       int pblocks = (m + 1) / 2;
       if (pblocks > 148 * 8)
         pblocks = 148 * 8;
@@ -599,10 +691,16 @@ static void btran_gemv(const DeviceModel &d, double *rhoOut, bool checkState, cu
   int blocks = d.m < 148 * 8 ? d.m : 148 * 8;
   if (g_kernelTimers && checkState)
     cudaEventRecord(g_kernelTimers->btranGemv[0], s);
-  gemv_rows_kernel<1, 1, 8><<<blocks, 256, 0, s>>>(d.fd, 1, d.swork, rhoOut, d.m, d.nucRow, d.st,
-                                                   checkState);
+  const bool sharded = d.shardW > 1;
+  gemv_rows_kernel<1, 1, 8><<<blocks, 256, 0, s>>>(d.fd, 1, d.swork, sharded ? d.gatherB : rhoOut, d.m,
+                                                   d.nucRow, d.st, checkState, d.shardW, d.shardRank, d.shardPerK);
   if (g_kernelTimers && checkState)
     cudaEventRecord(g_kernelTimers->btranGemv[1], s);
+  if (sharded) {
+    shard_all_gather(d.gatherB, sizeof(double) * d.shardPerK, s);
+    int sb = (d.m + 255) / 256;
+    btran_scatter_kernel<<<sb > 148 * 4 ? 148 * 4 : sb, 256, 0, s>>>(d, rhoOut, checkState);
+  }
 }
 
 // rho = B_t^-T e_r with r = st->pivotRow ; result in d.rho

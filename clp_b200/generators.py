@@ -258,6 +258,12 @@ def random_sparse_lp(m, n, density, seed, name=None, tight_frac=0.3) -> LP:
     import scipy.sparse as sp
 
     A = sp.csc_matrix((el, row, start), shape=(m, n))
+    return _planted_rim(rng, A, m, n, tight_frac, name or f"rand-{m}x{n}", start, row, el)
+
+
+def _planted_rim(rng, A, m, n, tight_frac, name, start, row, el) -> LP:
+    """Bounds, row ranges and costs around a planted primal vertex / dual vector (shared by the two
+    random generators; the order of the rng calls is part of the fixtures' identity)."""
     # planted primal vertex: a few columns strictly inside their box (fewer than the number of
     # tight rows, so the planted point is a non-degenerate-ish vertex), the rest at a bound
     tight = rng.uniform(size=m) < tight_frac
@@ -274,8 +280,41 @@ def random_sparse_lp(m, n, density, seed, name=None, tight_frac=0.3) -> LP:
     red = rng.uniform(0.05, 1.0, size=n)
     red = np.where(xs == 0.0, red, np.where(xs == 1.0, -red, 0.0))
     c = A.T @ y + red
-    return LP(name or f"rand-{m}x{n}", m, n, start.astype(np.int32), row, el, np.zeros(n),
+    return LP(name, m, n, np.asarray(start, dtype=np.int32), row, el, np.zeros(n),
               np.ones(n), c, row_lower, row_upper, known_objective=float(c @ xs))
+
+
+def random_sparse_lp_large(m, n, density, seed, name=None, tight_frac=0.3) -> LP:
+    """BASELINE.json configs[2] (C3, m=50k n=500k, 2.5e8 nonzeros): the recipe of random_sparse_lp
+    with a sort-free, chunked matrix generator (the argsort de-duplication of random_sparse_lp needs
+    ~15 GB and 3 minutes at this size).  Column j gets k_j ~ Binomial(m, density) (>= 1) rows, one per
+    stratum of width m/k_j (distinct and ascending by construction), values U(0.05,1) with a random
+    sign; rim vectors from _planted_rim."""
+    import scipy.sparse as sp
+
+    rng = np.random.default_rng(seed)
+    k = np.maximum(1, rng.binomial(m, density, size=n)).astype(np.int64)
+    start = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(k, out=start[1:])
+    nnz = int(start[-1])
+    row = np.empty(nnz, dtype=np.int32)
+    el = np.empty(nnz, dtype=np.float64)
+    chunk = 20000
+    for c0 in range(0, n, chunk):
+        c1 = min(n, c0 + chunk)
+        e0, e1 = int(start[c0]), int(start[c1])
+        kk = k[c0:c1]
+        col_of = np.repeat(np.arange(c1 - c0, dtype=np.int64), kk)
+        within = np.arange(e1 - e0, dtype=np.int64) - (start[c0:c1] - e0)[col_of]
+        kc = kk[col_of]
+        lo = within * m // kc            # integer strata [lo, hi): disjoint, non-empty because k_j <= m
+        hi = (within + 1) * m // kc
+        r = lo + np.floor(rng.uniform(size=e1 - e0) * (hi - lo)).astype(np.int64)
+        np.minimum(r, hi - 1, out=r)
+        row[e0:e1] = r
+        el[e0:e1] = rng.uniform(0.05, 1.0, size=e1 - e0) * rng.choice([-1.0, 1.0], size=e1 - e0)
+    A = sp.csc_matrix((el, row, start), shape=(m, n))
+    return _planted_rim(rng, A, m, n, tight_frac, name or f"rand-{m}x{n}", start, row, el)
 
 
 def staircase_lp(stages=40, block=500, seed=0) -> LP:

@@ -28,9 +28,9 @@ for w in which:
     for params in variants:
         params = dict(params, **extra)
         s = clp_b200.ClpSimplex(); s.loadLP(lp)
+        s.setParameter("maximumSeconds", 900)
         for k, v in params.items():
             s.setParameter(k, v)
-        s.setParameter("maximumSeconds", 900)
         t = time.time(); st = s.dual(); el = time.time() - t
         kkt = O.kkt_violations(lp, s.primalColumnSolution(), s.primalRowSolution(), s.dualColumnSolution()) if st == 0 else None
         expect = lp.known_objective if lp.known_objective is not None else ref.get(name, {}).get("objective")

@@ -21,6 +21,7 @@ lp = G.random_sparse_lp(int(m), int(n), dens, int(seed))
 s = clp_b200.ClpSimplex(); s.loadLP(lp)
 uid = clp_b200.ClpSimplex.ncclUniqueId() if rank == 0 else np.zeros(128, dtype=np.uint8)
 uid = broadcast_unique_id(uid, src=0)
+s.setParameter("shardMinNnzPerRank", 0)  # small test problem: force the sharded path
 s.initSharding(rank, world, uid)
 if len(sys.argv) > 5:
     s.setMaximumIterations(int(sys.argv[5]))
