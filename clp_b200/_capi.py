@@ -68,7 +68,23 @@ SIGNATURES = {
     "Clpb_times": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_double, c_double_p, c_double_p]),
     "Clpb_dualColumn": (ctypes.c_int, [ctypes.c_void_p, c_double_p, c_double_p, c_ubyte_p, ctypes.c_int,
                                        ctypes.c_double, c_double_p]),
+    "Clpb_dualColumnRowPass": (ctypes.c_int, [ctypes.c_void_p, c_double_p, c_double_p, c_ubyte_p, ctypes.c_int,
+                                              ctypes.c_double, c_double_p]),
     "Clpb_denseInvert": (ctypes.c_int, [ctypes.c_int, c_double_p, c_double_p]),
+    "Clpb_pivotRow": (ctypes.c_int, [ctypes.c_void_p, c_int_p, c_int_p, c_double_p]),
+    "Clpb_updateColumnTransposeAndPrice": (ctypes.c_int, [ctypes.c_void_p, c_double_p, c_double_p]),
+    "Clpb_dualColumnDevice": (ctypes.c_int, [ctypes.c_void_p, c_double_p, c_double_p]),
+    "Clpb_updateWeights": (ctypes.c_double, [ctypes.c_void_p, c_int_p]),
+    "Clpb_unrollWeights": (ctypes.c_int, [ctypes.c_void_p]),
+    "Clpb_updatePrimalSolution": (ctypes.c_int, [ctypes.c_void_p, c_double_p]),
+    "Clpb_saveWeights": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
+    "Clpb_updateColumnFT": (ctypes.c_int, [ctypes.c_void_p, c_double_p]),
+    "Clpb_updateTwoColumnsFT": (ctypes.c_int, [ctypes.c_void_p, c_double_p, c_double_p]),
+    "Clpb_replaceColumnChecked": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_double]),
+    "Clpb_updateColumnPacked": (ctypes.c_int, [ctypes.c_void_p, c_int_p, c_int_p, c_double_p]),
+    "Clpb_updateColumnTransposePacked": (ctypes.c_int, [ctypes.c_void_p, c_int_p, c_int_p, c_double_p]),
+    "Clpb_transposeTimesPacked": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_double, ctypes.c_int, c_int_p, c_double_p,
+                                                 c_int_p, c_int_p, c_double_p]),
     "Clpb_startup": (ctypes.c_int, [ctypes.c_void_p]),
     "Clpb_iterate": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "Clpb_getWeights": (None, [ctypes.c_void_p, c_double_p]),

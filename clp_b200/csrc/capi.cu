@@ -424,6 +424,113 @@ int Clpb_dualColumn(Clpb_Simplex *model, const double *alphaRow, const double *d
   return guarded(
       [&] { return model->e.dualColumnTest(alphaRow, dj, status, direction, infeasibility, theta); });
 }
+int Clpb_pivotRow(Clpb_Simplex *model, int *sequenceOut, int *direction, double *infeasibility)
+{
+  return guarded([&] { return model->e.pivotRowStep(sequenceOut, direction, infeasibility); });
+}
+int Clpb_updateColumnTransposeAndPrice(Clpb_Simplex *model, double *rho, double *alphaRow)
+{
+  return guarded([&] { return model->e.btranPriceStep(rho, alphaRow); });
+}
+int Clpb_dualColumnDevice(Clpb_Simplex *model, double *theta, double *alpha)
+{
+  return guarded([&] { return model->e.dualColumnStep(theta, alpha); });
+}
+double Clpb_updateWeights(Clpb_Simplex *model, int *returnCode)
+{
+  double alpha = 0.0;
+  const int rc = guarded([&] {
+    alpha = model->e.updateWeightsStep(returnCode);
+    return 0;
+  });
+  if (rc != 0 && returnCode)
+    *returnCode = rc;
+  return alpha;
+}
+int Clpb_updatePrimalSolution(Clpb_Simplex *model, double *changeInObjective)
+{
+  return guarded([&] { return model->e.updatePrimalStep(changeInObjective); });
+}
+int Clpb_saveWeights(Clpb_Simplex *model, int mode)
+{
+  return guarded([&] {
+    model->e.saveWeights(mode);
+    return 0;
+  });
+}
+int Clpb_unrollWeights(Clpb_Simplex *model) { return model->e.unrollWeights(); }
+int Clpb_updateColumnFT(Clpb_Simplex *model, double *region)
+{
+  return guarded([&] { return model->e.updateColumnFT(region); });
+}
+int Clpb_updateTwoColumnsFT(Clpb_Simplex *model, double *regionFT, double *regionOther)
+{
+  // ClpFactorization::updateTwoColumnsFT (hpp:125): the FT column keeps its spike, the other is a plain FTRAN
+  return guarded([&] {
+    int rc = model->e.updateColumn(regionOther);
+    if (rc != 0)
+      return rc;
+    return model->e.updateColumnFT(regionFT);
+  });
+}
+int Clpb_replaceColumnChecked(Clpb_Simplex *model, int sequenceIn, int pivotRow, double pivotCheck,
+                              double acceptablePivot)
+{
+  return guarded([&] { return model->e.replaceColumnChecked(sequenceIn, pivotRow, pivotCheck, acceptablePivot); });
+}
+// packed (CoinIndexedVector packedMode) forms: number / indices[] / elements[] in and out, the caller's
+// arrays have capacity m (n for transposeTimes); entries below the zero tolerance are dropped
+static int packDense(const std::vector<double> &v, double zeroTol, int *indices, double *elements)
+{
+  int nz = 0;
+  for (int i = 0; i < (int)v.size(); i++)
+    if (std::fabs(v[i]) > zeroTol) {
+      indices[nz] = i;
+      elements[nz++] = v[i];
+    }
+  return nz;
+}
+int Clpb_updateColumnPacked(Clpb_Simplex *model, int *number, int *indices, double *elements)
+{
+  return guarded([&] {
+    std::vector<double> v(model->e.m, 0.0);
+    for (int q = 0; q < *number; q++)
+      v[indices[q]] = elements[q];
+    const int rc = model->e.updateColumn(v.data());
+    *number = packDense(v, model->e.zeroTolerance, indices, elements);
+    return rc;
+  });
+}
+int Clpb_updateColumnTransposePacked(Clpb_Simplex *model, int *number, int *indices, double *elements)
+{
+  return guarded([&] {
+    std::vector<double> v(model->e.m, 0.0);
+    for (int q = 0; q < *number; q++)
+      v[indices[q]] = elements[q];
+    const int rc = model->e.updateColumnTranspose(v.data());
+    *number = packDense(v, model->e.zeroTolerance, indices, elements);
+    return rc;
+  });
+}
+int Clpb_transposeTimesPacked(Clpb_Simplex *model, double scalar, int numberPi, const int *indexPi,
+                              const double *elementPi, int *numberZ, int *indexZ, double *elementZ)
+{
+  return guarded([&] {
+    std::vector<double> pi(model->e.m, 0.0), z(model->e.n, 0.0);
+    for (int q = 0; q < numberPi; q++)
+      pi[indexPi[q]] = elementPi[q];
+    model->e.transposeTimes(scalar, pi.data(), z.data());
+    *numberZ = packDense(z, model->e.zeroTolerance, indexZ, elementZ);
+    return 0;
+  });
+}
+int Clpb_dualColumnRowPass(Clpb_Simplex *model, const double *alphaRow, const double *dj,
+                           const unsigned char *status, int direction, double infeasibility, double *theta)
+{
+  return guarded([&] {
+    return model->e.dualColumnTest(alphaRow, dj, status, direction, infeasibility, theta, true);
+  });
+}
 int Clpb_startup(Clpb_Simplex *model)
 {
   return guarded([&] { return model->e.startup(); });

@@ -1719,7 +1719,9 @@ int Engine::replaceColumn(int sequenceIn, int pivotRow)
 {
   fetchState();
   if (hState->numEtas >= d.tmax)
-    return 5;
+    return 3; // no room in the update buffers (ClpFactorization.hpp:86)
+  if (hState->numEtas >= tmax)
+    return 5; // maximum pivots reached (:87)
   launch_unpack_column(d, sequenceIn, d.rhs3, stream);
   launch_ftran_buffer(d, d.rhs3, 1, true, stream);
   double alpha = 0.0;
@@ -1752,7 +1754,7 @@ void Engine::times(double scalar, const double *x, double *y)
 }
 
 int Engine::dualColumnTest(const double *alphaRow, const double *dj, const unsigned char *stat,
-                           int sigma, double infeas, double *theta)
+                           int sigma, double infeas, double *theta, bool rowPass)
 {
   setupDevice();
   resetStateForRun();
@@ -1770,8 +1772,22 @@ int Engine::dualColumnTest(const double *alphaRow, const double *dj, const unsig
   CUDA_OK(cudaMemsetAsync(d.histMin, 0xFF, sizeof(unsigned long long) * kHistBuckets, stream));
   CUDA_OK(cudaMemsetAsync(d.hist2Weight, 0, sizeof(unsigned long long) * kHist2Buckets, stream));
   CUDA_OK(cudaMemsetAsync(d.hist2Min, 0xFF, sizeof(unsigned long long) * kHist2Buckets, stream));
-  launch_histogram(d, stream);
-  launch_chuzc(d, stream);
+  if (rowPass) {
+    // the cooperative kernel of the fused iteration: it derives the slack part of the row from rho
+    // (alpha_{n+i} = -rho_i) and also runs the dual update / flips / right-hand sides that follow
+    std::vector<double> negRho(m);
+    for (int i = 0; i < m; i++)
+      negRho[i] = -alphaRow[n + i];
+    CUDA_OK(cudaMemcpy(d.rho, negRho.data(), sizeof(double) * m, cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemset(d.posToNuc, 0xFF, sizeof(int) * m)); // no factorization in this entry point
+    CUDA_OK(cudaMemsetAsync(d.segTotal, 0, sizeof(unsigned long long) * (kHistBuckets / 1024), stream));
+    CUDA_OK(cudaMemsetAsync(d.segLast, 0xFF, sizeof(int) * (kHistBuckets / 1024), stream));
+    if (!launch_row_pass(d, stream))
+      throw std::runtime_error("row pass launch failed");
+  } else {
+    launch_histogram(d, stream);
+    launch_chuzc(d, stream);
+  }
   fetchState();
   *theta = hState->thetaDual;
   if (hState->stop != 0)
@@ -1796,6 +1812,202 @@ int Engine::iterate(int count)
     count -= c;
   }
   return total;
+}
+
+// ---------------------------------------------------------------------------------------
+// One iteration as separate plug-in calls.  The fused kernels decide where the cuts fall:
+//   pivotRowStep      = ClpDualRowSteepest::pivotRow (src/ClpDualRowSteepest.cpp:179)
+//   btranPriceStep    = ClpFactorization::updateColumnTranspose (:2993) + ClpPackedMatrix::transposeTimes (:706)
+//   dualColumnStep    = ClpSimplexDual::dualColumn (:4192) + updateDualsInDual (:2430) + flipBounds (one kernel)
+//   updateWeightsStep = ClpDualRowSteepest::updateWeights (:375): the FT-FTRAN pair (+ flip column) and the
+//                       BTRAN/FTRAN pivot agreement gate; returns alpha.  The weights themselves are
+//                       written by updatePrimalStep, so a rejected pivot leaves them untouched and
+//                       unrollWeights (:1022) has nothing to restore
+//   updatePrimalStep  = updatePrimalSolution (:630) + the DSE recurrence (:501-538) + replaceColumn (eta
+//                       append) + ClpSimplex::housekeeping (src/ClpSimplex.cpp:2065)
+int Engine::pivotRowStep(int *sequenceOut, int *direction, double *infeasibility)
+{
+  CUDA_OK(cudaMemsetAsync(&d.st->stop, 0, sizeof(int), stream));
+  launch_chuzr(d, stream);
+  kernelLaunches += 2;
+  fetchState();
+  if (hState->stop == STOP_NO_ROW || hState->stop == STOP_ETAS_FULL) {
+    const int why = hState->stop;
+    CUDA_OK(cudaMemsetAsync(&d.st->stop, 0, sizeof(int), stream));
+    return why == STOP_NO_ROW ? -1 : -2; // -2: the update buffer is full, factorize first
+  }
+  if (sequenceOut)
+    *sequenceOut = hState->seqOut;
+  if (direction)
+    *direction = hState->sigma;
+  if (infeasibility)
+    *infeasibility = hState->infeas;
+  return hState->pivotRow;
+}
+
+int Engine::btranPriceStep(double *rho, double *alphaRow)
+{
+  launch_btran_unit(d, true, stream);
+  launch_price(d, 0, n, false, stream);
+  kernelLaunches += 4;
+  std::vector<double> r(m);
+  CUDA_OK(cudaMemcpyAsync(r.data(), d.rho, sizeof(double) * m, cudaMemcpyDeviceToHost, stream));
+  if (alphaRow)
+    CUDA_OK(cudaMemcpyAsync(alphaRow, d.alphaRow, sizeof(double) * n, cudaMemcpyDeviceToHost, stream));
+  CUDA_OK(cudaStreamSynchronize(stream));
+  int nz = 0;
+  for (int i = 0; i < m; i++)
+    nz += r[i] != 0.0;
+  if (rho)
+    std::copy(r.begin(), r.end(), rho);
+  return nz;
+}
+
+int Engine::dualColumnStep(double *theta, double *alpha)
+{
+  if (!launch_row_pass(d, stream))
+    throw std::runtime_error("row pass launch failed");
+  kernelLaunches += 1;
+  fetchState();
+  if (hState->stop == STOP_NO_COLUMN) {
+    CUDA_OK(cudaMemsetAsync(&d.st->stop, 0, sizeof(int), stream));
+    return -1;
+  }
+  if (theta)
+    *theta = hState->thetaDual;
+  if (alpha)
+    *alpha = hState->alphaRow;
+  return hState->seqIn;
+}
+
+double Engine::updateWeightsStep(int *returnCode)
+{
+  launch_ftran_iteration(d, true, stream);
+  kernelLaunches += 4;
+  fetchState();
+  int rc = 0;
+  if (hState->stop == STOP_INACCURATE || hState->stop == STOP_TINY_PIVOT) {
+    rc = hState->stop == STOP_INACCURATE ? 1 : 2; // 1: refactorize and retry, 2: no usable pivot
+    CUDA_OK(cudaMemsetAsync(&d.st->stop, 0, sizeof(int), stream));
+  }
+  if (returnCode)
+    *returnCode = rc;
+  return hState->alphaCol;
+}
+
+int Engine::updatePrimalStep(double *changeInObjective)
+{
+  fetchState();
+  const int r = hState->pivotRow, q = hState->seqIn;
+  const double gain = hState->thetaDual * hState->infeas; // dual objective gain of the step
+  launch_pivot_updates(d, stream);
+  kernelLaunches += 1;
+  fetchState();
+  if (changeInObjective)
+    *changeInObjective = gain;
+  if (r >= 0 && r < m && q >= 0)
+    hPivot[r] = q;
+  // the tail of the update kernel already decoded the next pivot row; the stepwise caller asks for it
+  // again through pivotRowStep, so a "no row" stop raised here is not an error
+  if (hState->stop != 0)
+    CUDA_OK(cudaMemsetAsync(&d.st->stop, 0, sizeof(int), stream));
+  return hState->numEtas;
+}
+
+// ClpDualRowSteepest::saveWeights (src/ClpDualRowSteepest.cpp:773): weights travel with their VARIABLE
+// across a refactorization.  1 remember which sequence sits at every position (+ snapshot); 2 re-map the
+// snapshot onto the new pivot order (new basics get 1.0, clip at DEVEX_TRY_NORM) and snapshot again;
+// 4 restore the snapshot; 5 / 7 initialise to 1.0; 3 / 6 nothing to do here (no infeasibility list is kept:
+// CHUZR scans every position).
+void Engine::saveWeights(int mode)
+{
+  if (!deviceReady)
+    return;
+  std::vector<int> pv(m);
+  std::vector<double> w(m);
+  CUDA_OK(cudaMemcpy(pv.data(), d.pivotVariable, sizeof(int) * m, cudaMemcpyDeviceToHost));
+  CUDA_OK(cudaMemcpy(w.data(), d.weights, sizeof(double) * m, cudaMemcpyDeviceToHost));
+  if (mode == 1) {
+    savedWeightSeq = pv;
+    savedWeightVal = w;
+  } else if (mode == 5 || mode == 7 || ((mode == 2 || mode == 4) && savedWeightSeq.empty())) {
+    w.assign(m, 1.0);
+    CUDA_OK(cudaMemcpy(d.weights, w.data(), sizeof(double) * m, cudaMemcpyHostToDevice));
+    savedWeightSeq = pv;
+    savedWeightVal = w;
+  } else if (mode == 2 || mode == 4) {
+    std::vector<int> back(nm, -1);
+    for (int i = 0; i < m; i++)
+      back[savedWeightSeq[i]] = i;
+    for (int i = 0; i < m; i++) {
+      const int b = back[pv[i]];
+      w[i] = b >= 0 ? std::max(savedWeightVal[b], kDevexTryNorm) : 1.0;
+    }
+    CUDA_OK(cudaMemcpy(d.weights, w.data(), sizeof(double) * m, cudaMemcpyHostToDevice));
+    savedWeightSeq = pv;
+    savedWeightVal = w;
+  }
+}
+
+int Engine::unrollWeights()
+{
+  return 0;
+}
+
+// ClpFactorization::updateColumnFT (src/ClpFactorization.hpp:113): FTRAN in place; the result is also
+// what replaceColumn needs (in product form the "spike" is the FTRAN'd column itself), so it stays in
+// the first right-hand-side slot on the device.  Returns the number of nonzeros, or -1 when there is
+// no room for another update (hpp:120-123: negative = no room).
+int Engine::updateColumnFT(double *vec)
+{
+  fetchState();
+  if (hState->numEtas >= d.tmax)
+    return -1;
+  CUDA_OK(cudaMemcpyAsync(d.rhs3, vec, sizeof(double) * m, cudaMemcpyHostToDevice, stream));
+  launch_ftran_buffer(d, d.rhs3, 1, true, stream);
+  CUDA_OK(cudaMemcpyAsync(vec, d.rhs3, sizeof(double) * m, cudaMemcpyDeviceToHost, stream));
+  CUDA_OK(cudaStreamSynchronize(stream));
+  int nz = 0;
+  for (int i = 0; i < m; i++) {
+    if (std::fabs(vec[i]) < zeroTolerance)
+      vec[i] = 0.0;
+    nz += vec[i] != 0.0;
+  }
+  return nz;
+}
+
+// ClpFactorization::replaceColumn with its checks (hpp:82-89; CoinAbcTypeFactorization::checkPivot,
+// src/CoinAbcBaseFactorization4.cpp:94-131): 0 ok, 1 pivot agrees with pivotCheck only to 1e-8 relative
+// ("probably ok", the update is made), 2 singular or inaccurate (nothing changed), 3 no room in the
+// update buffers, 5 the maximum number of pivots (factorizationFrequency) is reached.
+int Engine::replaceColumnChecked(int sequenceIn, int pivotRow, double pivotCheck, double acceptable)
+{
+  fetchState();
+  const int t = hState->numEtas;
+  if (t >= d.tmax)
+    return 3;
+  if (t >= tmax)
+    return 5;
+  launch_unpack_column(d, sequenceIn, d.rhs3, stream);
+  launch_ftran_buffer(d, d.rhs3, 1, true, stream);
+  double alpha = 0.0;
+  CUDA_OK(cudaMemcpyAsync(&alpha, d.rhs3 + pivotRow, sizeof(double), cudaMemcpyDeviceToHost, stream));
+  CUDA_OK(cudaStreamSynchronize(stream));
+  if (!(std::fabs(alpha) > 1.0e-8) || std::fabs(alpha) < acceptable)
+    return 2;
+  int rc = 0;
+  if (pivotCheck != 0.0) {
+    const double checkTolerance = t < 2 ? 1.0e-5 : t < 10 ? 1.0e-6 : t < 50 ? 1.0e-8 : 1.0e-10;
+    const double rel = std::fabs(1.0 - std::fabs(alpha / pivotCheck));
+    if (rel >= checkTolerance)
+      rc = (std::fabs(std::fabs(pivotCheck) - std::fabs(alpha)) < 1.0e-12 || rel < 1.0e-8) ? 1 : 2;
+    if (rc == 2)
+      return 2;
+  }
+  launch_eta_append_test(d, pivotRow, sequenceIn, stream);
+  CUDA_OK(cudaStreamSynchronize(stream));
+  hPivot[pivotRow] = sequenceIn;
+  return rc;
 }
 
 void Engine::getWeights(double *w)

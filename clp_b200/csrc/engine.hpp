@@ -106,8 +106,21 @@ public:
   void transposeTimes(double scalar, const double *pi, double *z);
   void times(double scalar, const double *x, double *y);
   int dualColumnTest(const double *alphaRow, const double *dj, const unsigned char *stat,
-                     int sigma, double infeas, double *theta);
+                     int sigma, double infeas, double *theta, bool rowPass = false);
   int iterate(int count);                   // run 'count' iterations from the current state
+  // ---- the iteration one plug-in call at a time (ClpDualRowPivot / ClpFactorization / ClpMatrixBase
+  // methods in the order ClpSimplexDual::whileIterating calls them); device state carries over
+  int pivotRowStep(int *sequenceOut, int *direction, double *infeasibility); // ClpDualRowPivot::pivotRow; -1 = none
+  int btranPriceStep(double *rho, double *alphaRow);  // updateColumnTranspose(e_r) + transposeTimes; nnz(rho)
+  int dualColumnStep(double *theta, double *alpha);   // dualColumn + updateDualsInDual + flips; sequenceIn or -1
+  double updateWeightsStep(int *returnCode);          // ClpDualRowPivot::updateWeights (updateTwoColumnsFT); alpha
+  int updatePrimalStep(double *changeInObjective);    // updatePrimalSolution + DSE recurrence + replaceColumn + housekeeping
+  void saveWeights(int mode);                         // ClpDualRowSteepest::saveWeights modes 1..7
+  int unrollWeights();                                // nothing to undo before updatePrimalStep (returns 0)
+  int updateColumnFT(double *vec);                    // FTRAN that also keeps the spike for replaceColumn
+  int replaceColumnChecked(int sequenceIn, int pivotRow, double pivotCheck, double acceptablePivot);
+  std::vector<int> savedWeightSeq;
+  std::vector<double> savedWeightVal;
   void getWeights(double *w);
   void getDeviceVector(const char *name, double *out);
   int startup();                            // status -> basis, factorize, compute primals/duals

@@ -287,6 +287,83 @@ class ClpSimplex:
                                               float(infeasibility), ctypes.byref(theta)))
         return q, theta.value
 
+    def dualColumnRowPass(self, alphaRow, dj, status, direction, infeasibility):
+        a = np.ascontiguousarray(alphaRow, dtype=np.float64)
+        d = np.ascontiguousarray(dj, dtype=np.float64)
+        s = np.ascontiguousarray(status, dtype=np.uint8)
+        theta = ctypes.c_double(0.0)
+        q = self._chk(self._L.Clpb_dualColumnRowPass(self._h, _dp(a), _dp(d), _up(s), int(direction),
+                                                     float(infeasibility), ctypes.byref(theta)))
+        return q, theta.value
+
+    # ---- ClpDualRowPivot surface, one iteration at a time (include/clp_b200.h)
+    def pivotRow(self):
+        """ClpDualRowPivot::pivotRow -> (row or -1/-2, sequenceOut, direction, infeasibility)"""
+        so, di, inf = ctypes.c_int(-1), ctypes.c_int(0), ctypes.c_double(0.0)
+        r = self._chk(self._L.Clpb_pivotRow(self._h, ctypes.byref(so), ctypes.byref(di), ctypes.byref(inf)))
+        return r, so.value, di.value, inf.value
+
+    def updateColumnTransposeAndPrice(self):
+        rho, row = np.zeros(self.numberRows()), np.zeros(self.numberColumns())
+        nz = self._chk(self._L.Clpb_updateColumnTransposeAndPrice(self._h, _dp(rho), _dp(row)))
+        return nz, rho, row
+
+    def dualColumnDevice(self):
+        th, al = ctypes.c_double(0.0), ctypes.c_double(0.0)
+        q = self._chk(self._L.Clpb_dualColumnDevice(self._h, ctypes.byref(th), ctypes.byref(al)))
+        return q, th.value, al.value
+
+    def updateWeights(self):
+        rc = ctypes.c_int(0)
+        alpha = self._L.Clpb_updateWeights(self._h, ctypes.byref(rc))
+        return alpha, rc.value
+
+    def unrollWeights(self): return self._L.Clpb_unrollWeights(self._h)
+
+    def updatePrimalSolution(self):
+        ch = ctypes.c_double(0.0)
+        t = self._chk(self._L.Clpb_updatePrimalSolution(self._h, ctypes.byref(ch)))
+        return t, ch.value
+
+    def saveWeights(self, mode): return self._chk(self._L.Clpb_saveWeights(self._h, int(mode)))
+
+    def updateColumnFT(self, region):
+        r = np.ascontiguousarray(region, dtype=np.float64).copy()
+        nz = self._chk(self._L.Clpb_updateColumnFT(self._h, _dp(r)))
+        return nz, r
+
+    def updateTwoColumnsFT(self, regionFT, regionOther):
+        a = np.ascontiguousarray(regionFT, dtype=np.float64).copy()
+        b = np.ascontiguousarray(regionOther, dtype=np.float64).copy()
+        nz = self._chk(self._L.Clpb_updateTwoColumnsFT(self._h, _dp(a), _dp(b)))
+        return nz, a, b
+
+    def replaceColumnChecked(self, sequenceIn, pivotRow, pivotCheck, acceptablePivot=1e-8):
+        return self._L.Clpb_replaceColumnChecked(self._h, int(sequenceIn), int(pivotRow), float(pivotCheck),
+                                                 float(acceptablePivot))
+
+    def _packed(self, fn, indices, elements, cap):
+        idx = np.zeros(cap, dtype=np.int32); el = np.zeros(cap)
+        k = len(indices)
+        idx[:k] = indices; el[:k] = elements
+        num = ctypes.c_int(k)
+        self._chk(fn(self._h, ctypes.byref(num), _ip(idx), _dp(el)))
+        return idx[:num.value].copy(), el[:num.value].copy()
+
+    def updateColumnPacked(self, indices, elements):
+        return self._packed(self._L.Clpb_updateColumnPacked, indices, elements, self.numberRows())
+
+    def updateColumnTransposePacked(self, indices, elements):
+        return self._packed(self._L.Clpb_updateColumnTransposePacked, indices, elements, self.numberRows())
+
+    def transposeTimesPacked(self, scalar, indices, elements):
+        ip = np.ascontiguousarray(indices, dtype=np.int32); ep = np.ascontiguousarray(elements, dtype=np.float64)
+        iz = np.zeros(self.numberColumns(), dtype=np.int32); ez = np.zeros(self.numberColumns())
+        nz = ctypes.c_int(0)
+        self._chk(self._L.Clpb_transposeTimesPacked(self._h, float(scalar), len(ip), _ip(ip), _dp(ep),
+                                                    ctypes.byref(nz), _ip(iz), _dp(ez)))
+        return iz[:nz.value].copy(), ez[:nz.value].copy()
+
     def startup(self): return self._chk(self._L.Clpb_startup(self._h))
     def iterate(self, count): return self._chk(self._L.Clpb_iterate(self._h, int(count)))
 

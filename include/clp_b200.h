@@ -45,7 +45,7 @@ Clpb_Simplex *Clpb_presolvedModel(Clpb_Simplex *model, int *status);
 int Clpb_postsolve(Clpb_Simplex *model, Clpb_Simplex *presolved);
 void Clpb_setSolution(Clpb_Simplex *model, const double *x, const double *rowPrice,
                       const unsigned char *status, int problemStatus);
-/* Clp_writeMps :120 (ClpModel::writeMps src/ClpModel.cpp:3986): the model as loaded, default names
+/* Clp_writeMps :123 (ClpModel::writeMps src/ClpModel.cpp:3986): the model as loaded, default names
    R%7.7d / C%7.7d, 17 significant digits; formatType / numberAcross / objSense are accepted for
    signature compatibility.  0 ok, -1 cannot open.  Host only. */
 int Clpb_writeMps(Clpb_Simplex *model, const char *filename, int formatType, int numberAcross,
@@ -54,18 +54,18 @@ int Clpb_writeMps(Clpb_Simplex *model, const char *filename, int formatType, int
 int Clpb_numberRows(Clpb_Simplex *model);
 int Clpb_numberColumns(Clpb_Simplex *model);
 long long Clpb_getNumElements(Clpb_Simplex *model);
-/* problem data as loaded (for callers that used readMps): Clp_getColLower etc. :236-262 */
+/* problem data as loaded (for callers that used readMps): Clp_getRowLower ... Clp_getColUpper :459-475 */
 void Clpb_getProblem(Clpb_Simplex *model, int *start, int *index, double *value, double *collb,
                      double *colub, double *obj, double *rowlb, double *rowub);
 /* Clp_setPrimalTolerance :179, Clp_setDualTolerance :182, Clp_setDualBound :382,
    Clp_setMaximumIterations :199, Clp_setMaximumSeconds :202, Clp_setLogLevel :314,
    ClpFactorization::maximumPivots (src/ClpFactorization.hpp:149).  Keys: "primalTolerance",
    "dualTolerance", "dualBound", "maximumIterations", "maximumSeconds", "logLevel",
-   "factorizationFrequency", "scaling", "perturbation" (Clp_setPerturbation :302: 50 on,
+   "factorizationFrequency", "scaling", "perturbation" (Clp_setPerturbation :395: 50 on,
    100 automatic, 102 off = default here; ClpSimplexDual::perturb src/ClpSimplexDual.cpp:6533), "batch" (iterations enqueued per host sync), "timing" (0/1: per-phase
    CUDA events, no graph replay), "useGraph" (0/1), "warmupIterations", "objectiveOffset". */
 int Clpb_setParameter(Clpb_Simplex *model, const char *key, double value);
-/* Clp_scaling :268 (ClpModel::scaling(int mode), src/ClpModel.hpp): 0 off (default here; the
+/* Clp_scaling :354 (ClpModel::scaling(int mode), src/ClpModel.hpp): 0 off (default here; the
    benchmark configuration is unscaled), 1 equilibrium, 2 geometric, 3 automatic (Clp's default),
    4 automatic-dynamic (treated as 3).  The same value can be set with the key "scaling".
    Clpb_scaleFactors runs ClpPackedMatrix::scale (src/ClpPackedMatrix.cpp:4120) on the host and
@@ -129,8 +129,26 @@ int Clpb_factorize(Clpb_Simplex *model, const int *basicSequence, int *pivotVari
    region[m] dense, in place */
 int Clpb_updateColumn(Clpb_Simplex *model, double *region);
 int Clpb_updateColumnTranspose(Clpb_Simplex *model, double *region);
-/* ClpFactorization::replaceColumn (hpp:89): 0 ok, 2 singular (nothing changed), 5 max pivots */
+/* ClpFactorization::replaceColumn (hpp:89, return codes hpp:82-88): 0 ok, 1 probably ok (pivot agrees
+   with pivotCheck only to 1e-8; the update is made), 2 singular / inaccurate (nothing changed), 3 no room
+   in the update buffers, 5 maximum pivots (factorizationFrequency) reached.  Clpb_replaceColumn is the
+   unchecked form (codes 0 / 2 / 3 / 5); the checked form restates CoinAbcTypeFactorization::checkPivot
+   (src/CoinAbcBaseFactorization4.cpp:94-131) with pivotCheck = the pivot taken from the BTRAN row. */
 int Clpb_replaceColumn(Clpb_Simplex *model, int sequenceIn, int pivotRow);
+int Clpb_replaceColumnChecked(Clpb_Simplex *model, int sequenceIn, int pivotRow, double pivotCheck,
+                              double acceptablePivot);
+/* ClpFactorization::updateColumnFT (hpp:113) / updateTwoColumnsFT (hpp:125): FTRAN in place that also
+   keeps what replaceColumn needs (in product form the spike is the FTRAN'd column itself).  Returns the
+   number of nonzeros, negative when there is no room for another update (hpp:120-123). */
+int Clpb_updateColumnFT(Clpb_Simplex *model, double *region);
+int Clpb_updateTwoColumnsFT(Clpb_Simplex *model, double *regionFT, double *regionOther);
+/* Packed forms (CoinIndexedVector packedMode: number / indices / elements): in place, arrays
+   of capacity m (n for the z of transposeTimes), entries <= zeroTolerance dropped as
+   ClpPackedMatrix::transposeTimes does (src/ClpPackedMatrix.cpp:931-932). */
+int Clpb_updateColumnPacked(Clpb_Simplex *model, int *number, int *indices, double *elements);
+int Clpb_updateColumnTransposePacked(Clpb_Simplex *model, int *number, int *indices, double *elements);
+int Clpb_transposeTimesPacked(Clpb_Simplex *model, double scalar, int numberPi, const int *indexPi,
+                              const double *elementPi, int *numberZ, int *indexZ, double *elementZ);
 /* ClpMatrixBase::transposeTimes (src/ClpMatrixBase.hpp:287) z[n] = scalar*A^T pi ;
    ClpMatrixBase::times (hpp:275) y[m] = scalar*A x */
 int Clpb_transposeTimes(Clpb_Simplex *model, double scalar, const double *pi, double *z);
@@ -141,10 +159,48 @@ int Clpb_times(Clpb_Simplex *model, double scalar, const double *x, double *y);
 int Clpb_dualColumn(Clpb_Simplex *model, const double *alphaRow, const double *dj,
                     const unsigned char *status, int direction, double infeasibility,
                     double *theta);
+/* The same test run by the cooperative row kernel of the fused iteration (rowpass.cu), which also
+   performs the dual update and the bound flips that follow it on the device copy of dj / status. */
+int Clpb_dualColumnRowPass(Clpb_Simplex *model, const double *alphaRow, const double *dj,
+                           const unsigned char *status, int direction, double infeasibility,
+                           double *theta);
 /* The dense kernel of the refactorization on its own (CoinAbcDgetrf + inverse,
    src/AbcSimplexParallel.cpp:2491): a[k*k] column-major in, x = a^-1 column-major out.
    Returns 0, or 1 + the index of the first column without an acceptable pivot. */
 int Clpb_denseInvert(int k, const double *a, double *x);
+/* ---- ClpDualRowPivot (src/ClpDualRowPivot.hpp:23-130) and the calls whileIterating makes around it,
+   ONE iteration at a time on the device-resident state (after Clpb_startup).  The fused kernels decide
+   where the cuts fall:
+     Clpb_pivotRow                       ClpDualRowPivot::pivotRow :30  -> pivot row, -1 none (primal
+                                         feasible), -2 update buffers full (factorize first); also the
+                                         leaving sequence, its direction (+1 to upper / -1 to lower) and
+                                         primal infeasibility
+     Clpb_updateColumnTransposeAndPrice  ClpFactorization::updateColumnTranspose(e_r) hpp:135 +
+                                         ClpMatrixBase::transposeTimes hpp:308; rho[m] / alphaRow[n]
+                                         copied out when not NULL; returns nnz(rho)
+     Clpb_dualColumnDevice               ClpSimplexDual::dualColumn + updateDualsInDual + flipBounds
+                                         (src/ClpSimplexDual.cpp:4192, :2430, :6345 -- one kernel);
+                                         returns sequenceIn or -1, *theta the dual step, *alpha the pivot
+                                         element from the row
+     Clpb_updateWeights                  ClpDualRowPivot::updateWeights :34 (performs the FT-FTRAN pair
+                                         like the reference's, returns alpha from the column); *returnCode
+                                         0 ok, 1 pivot disagrees with the row (refactorize), 2 no usable pivot.
+                                         The DSE recurrence is applied by the next call, so a rejected
+                                         pivot leaves the weights untouched
+     Clpb_unrollWeights                  ClpDualRowPivot::unrollWeights :67 -- nothing to undo (see above)
+     Clpb_updatePrimalSolution           ClpDualRowPivot::updatePrimalSolution :47 + the weight recurrence +
+                                         ClpFactorization::replaceColumn + ClpSimplex::housekeeping (one
+                                         kernel); *changeInObjective = dual objective gain; returns the
+                                         number of updates since the last factorization
+     Clpb_saveWeights                    ClpDualRowPivot::saveWeights :63, modes 1..7 of
+                                         ClpDualRowSteepest::saveWeights (src/ClpDualRowSteepest.cpp:773) */
+int Clpb_pivotRow(Clpb_Simplex *model, int *sequenceOut, int *direction, double *infeasibility);
+int Clpb_updateColumnTransposeAndPrice(Clpb_Simplex *model, double *rho, double *alphaRow);
+int Clpb_dualColumnDevice(Clpb_Simplex *model, double *theta, double *alpha);
+double Clpb_updateWeights(Clpb_Simplex *model, int *returnCode);
+int Clpb_unrollWeights(Clpb_Simplex *model);
+int Clpb_updatePrimalSolution(Clpb_Simplex *model, double *changeInObjective);
+int Clpb_saveWeights(Clpb_Simplex *model, int mode);
 /* run the startup of dual() (basis from status, factorize, computePrimals/Duals) and then
    'count' iterations; DSE weights by pivot row (ClpDualRowSteepest::weights_) */
 int Clpb_startup(Clpb_Simplex *model);
