@@ -1178,7 +1178,7 @@ int Engine::refresh()
   launch_make_dual_feasible(d, currentDualBound, dCounters, stream);
   launch_compute_primals(d, dXn, dRhs, stream);
   kernelLaunches += 20;
-  if (logLevel > 0 && (numberRefactorizations % (logLevel > 1 ? 1 : 25)) == 0) {
+  if (logLevel > 0 && (logLevel > 1 || numberRefactorizations <= 60 || numberRefactorizations % 25 == 0)) {
     // progress line (the reference prints objective / infeasibilities at every refactorization)
     launch_objective(d, dObj, stream);
     double obj2[2];

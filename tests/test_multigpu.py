@@ -1,5 +1,5 @@
-"""Column-sharded pricing across 2 GPUs (one process per GPU, one NCCL all-gather per pricing
-pass): every rank must take the same pivots as the single-GPU run."""
+"""Column-sharded pricing and row-sharded factors across 2 GPUs (one process per GPU, one NCCL
+all-gather per solve / pricing pass): all ranks take the same pivots and reach the single-GPU optimum."""
 import json
 import os
 import subprocess
@@ -39,7 +39,11 @@ def test_two_gpu_sharded_solve_matches_single_gpu():
     assert len(res) == 2
     for r in res:
         assert r["status"] == 0
-        assert r["iterations"] == s.numberIterations()          # identical pivot sequence
+        # every rank takes the same pivots (replicated decisions on identical gathered data); the
+        # count may differ from the single-GPU run: the inverse is assembled from per-rank column
+        # blocks, and the library DGEMM rounds differently for a different block width
+        assert r["iterations"] == res[0]["iterations"]
+        assert abs(r["iterations"] - s.numberIterations()) <= 0.05 * s.numberIterations()
         assert r["objective"] == res[0]["objective"]             # ranks bit-identical
         assert abs(r["objective"] - s.objectiveValue()) <= 1e-9 * (1 + abs(s.objectiveValue()))
         assert abs(r["objective"] - lp.known_objective) <= 1e-8 * (1 + abs(lp.known_objective))
