@@ -229,6 +229,10 @@ int Clpb_setParameter(Clpb_Simplex *model, const char *key, double value)
     e.scalingFlag = (int)value;
   else if (k == "perturbation")
     e.perturbation = (int)value;
+  else if (k == "refreshDualsEvery")
+    e.refreshDualsEvery = (int)value;
+  else if (k == "refreshPrimalsEvery")
+    e.refreshPrimalsEvery = (int)value;
   else if (k == "shardMinNnzPerRank")
     e.shardMinNnzPerRank = (long long)value;
   else if (k == "factorMode")

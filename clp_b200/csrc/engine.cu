@@ -998,19 +998,45 @@ int Engine::refactor()
       }
     const int k = (int)nucRow.size();
     const int ldk = std::max(8, roundUp(k, 8));
-    // ---- S1 = A[C rows, nucleus columns] as CSR over positions
-    std::vector<int> s1Start(m + 1, 0);
+    // ---- nucleus buffers and index sets go to the device first: the LU can start
+    if ((size_t)k * ldk > nucCap) {
+      int kc = std::min(m, std::max(k + k / 4 + 64, 256));
+      int ldc = roundUp(kc, 8);
+      nucCap = (size_t)kc * ldc;
+      // the old (smaller) pair is released first: at m = 5e4 a factor pair is up to 40 GB
+      for (double *old : {d.Ninv, d.NinvT})
+        if (old) {
+          CUDA_OK(cudaFree(old));
+          allocs.erase(std::remove(allocs.begin(), allocs.end(), (void *)old), allocs.end());
+        }
+      // + worldSize columns: the in-place all-gather of the sharded inverse rounds k up to W*ceil(k/W)
+      d.Ninv = dalloc<double>(nucCap + (size_t)(worldSize + 1) * ldc);
+      d.NinvT = dalloc<double>(nucCap + (size_t)(worldSize + 1) * ldc);
+    }
+    d.k = k;
+    d.ldk = ldk;
+    CUDA_OK(cudaMemcpyAsync(d.posToNuc, posToNuc.data(), sizeof(int) * m, cudaMemcpyHostToDevice, stream));
+    if (k > 0) {
+      CUDA_OK(cudaMemcpyAsync(d.nucRow, nucRow.data(), sizeof(int) * k, cudaMemcpyHostToDevice, stream));
+      CUDA_OK(cudaMemcpyAsync(d.nucCol, nucCol.data(), sizeof(int) * k, cudaMemcpyHostToDevice, stream));
+    }
+    std::vector<int> s1Start, s1Col, s1cStart, s1cRow;
+    std::vector<double> s1Val, s1cVal;
+    auto buildS1 = [&]() {
+      // ---- S1 = A[C rows, nucleus columns] as CSR over positions (host work, overlapped with the LU)
+    s1Start.assign(m + 1, 0);
     for (int j = 0; j < k; j++)
       for (int e = hColStart[nucCol[j]]; e < hColStart[nucCol[j] + 1]; e++)
         if (posToNuc[hRow[e]] < 0)
           s1Start[hRow[e] + 1]++;
     for (int i = 0; i < m; i++)
       s1Start[i + 1] += s1Start[i];
-    std::vector<int> s1Col(s1Start[m]);
-    std::vector<double> s1Val(s1Start[m]);
+    s1Col.resize(s1Start[m]);
+    s1Val.resize(s1Start[m]);
     // the same entries by nucleus column (this loop visits them in that order)
-    std::vector<int> s1cStart(k + 1, 0), s1cRow(s1Start[m]);
-    std::vector<double> s1cVal(s1Start[m]);
+    s1cStart.assign(k + 1, 0);
+    s1cRow.resize(s1Start[m]);
+    s1cVal.resize(s1Start[m]);
     {
       std::vector<int> fill(s1Start.begin(), s1Start.end() - 1);
       int atc = 0;
@@ -1029,6 +1055,25 @@ int Engine::refactor()
         s1cStart[j + 1] = atc;
       }
     }
+    };
+    int info = 0;
+    if (k > 0) {
+      // row-major nucleus N in NinvT == column-major N^T ; inverse comes out as row-major N^-1
+      CUDA_OK(cudaMemsetAsync(d.NinvT, 0, sizeof(double) * (size_t)k * ldk, stream));
+      launch_gather_nucleus_matrix(d, d.NinvT, ldk, stream);
+      struct Ctx {
+        decltype(buildS1) *fn;
+      } ctx{&buildS1};
+      info = dense_invert(d.NinvT, d.Ninv, k, ldk, dIpiv, dPerm, dInfo, hostIpiv.data(),
+                          hostPerm.data(), 1.0e-11, stream, d.shardW, d.shardRank,
+                          d.shardW > 1 ? allGatherFn : nullptr, ncclComm,
+                          [](void *c) { (*static_cast<Ctx *>(c)->fn)(); }, &ctx);
+      if (info < 0)
+        throw std::runtime_error("clp_b200: refactorization failed (allocation or collective)");
+      kernelLaunches += 6 * ((k + 31) / 32) * 2;
+    } else {
+      buildS1();
+    }
     if ((size_t)s1Start[m] > s1Cap) {
       s1Cap = (size_t)s1Start[m] * 3 / 2 + 1024;
       dS1Col = dalloc<int>(s1Cap);
@@ -1038,22 +1083,6 @@ int Engine::refactor()
     }
     d.s1Col = dS1Col;
     d.s1Val = dS1Val;
-    if ((size_t)k * ldk > nucCap) {
-      int kc = std::min(m, std::max(k + k / 4 + 64, 256));
-      int ldc = roundUp(kc, 8);
-      nucCap = (size_t)kc * ldc;
-      // the old (smaller) pair is released first: at m = 5e4 a factor pair is up to 40 GB
-      for (double *old : {d.Ninv, d.NinvT})
-        if (old) {
-          CUDA_OK(cudaFree(old));
-          allocs.erase(std::remove(allocs.begin(), allocs.end(), (void *)old), allocs.end());
-        }
-      // + worldSize columns: the in-place all-gather of the sharded inverse rounds k up to W*ceil(k/W)
-      d.Ninv = dalloc<double>(nucCap + (size_t)(worldSize + 1) * ldc);
-      d.NinvT = dalloc<double>(nucCap + (size_t)(worldSize + 1) * ldc);
-    }
-    d.k = k;
-    d.ldk = ldk;
     {
       FactorDesc hfd;
       hfd.k = k;
@@ -1064,13 +1093,8 @@ int Engine::refactor()
       hfd.s1Val = dS1Val;
       hfd.s1cRow = dS1cRow;
       hfd.s1cVal = dS1cVal;
+      // pageable source: the runtime stages the bytes before the call returns, hfd may go out of scope
       CUDA_OK(cudaMemcpyAsync(d.fd, &hfd, sizeof(FactorDesc), cudaMemcpyHostToDevice, stream));
-      CUDA_OK(cudaStreamSynchronize(stream)); // hfd is a stack object
-    }
-    CUDA_OK(cudaMemcpyAsync(d.posToNuc, posToNuc.data(), sizeof(int) * m, cudaMemcpyHostToDevice, stream));
-    if (k > 0) {
-      CUDA_OK(cudaMemcpyAsync(d.nucRow, nucRow.data(), sizeof(int) * k, cudaMemcpyHostToDevice, stream));
-      CUDA_OK(cudaMemcpyAsync(d.nucCol, nucCol.data(), sizeof(int) * k, cudaMemcpyHostToDevice, stream));
     }
     CUDA_OK(cudaMemcpyAsync(dS1RowStart, s1Start.data(), sizeof(int) * (m + 1), cudaMemcpyHostToDevice, stream));
     CUDA_OK(cudaMemcpyAsync(dS1cStart, s1cStart.data(), sizeof(int) * (k + 1), cudaMemcpyHostToDevice, stream));
@@ -1079,18 +1103,6 @@ int Engine::refactor()
       CUDA_OK(cudaMemcpyAsync(dS1Val, s1Val.data(), sizeof(double) * s1Start[m], cudaMemcpyHostToDevice, stream));
       CUDA_OK(cudaMemcpyAsync(dS1cRow, s1cRow.data(), sizeof(int) * s1Start[m], cudaMemcpyHostToDevice, stream));
       CUDA_OK(cudaMemcpyAsync(dS1cVal, s1cVal.data(), sizeof(double) * s1Start[m], cudaMemcpyHostToDevice, stream));
-    }
-    int info = 0;
-    if (k > 0) {
-      // row-major nucleus N in NinvT == column-major N^T ; inverse comes out as row-major N^-1
-      CUDA_OK(cudaMemsetAsync(d.NinvT, 0, sizeof(double) * (size_t)k * ldk, stream));
-      launch_gather_nucleus_matrix(d, d.NinvT, ldk, stream);
-      info = dense_invert(d.NinvT, d.Ninv, k, ldk, dIpiv, dPerm, dInfo, hostIpiv.data(),
-                          hostPerm.data(), 1.0e-11, stream, d.shardW, d.shardRank,
-                          d.shardW > 1 ? allGatherFn : nullptr, ncclComm);
-      if (info < 0)
-        throw std::runtime_error("clp_b200: refactorization failed (allocation or collective)");
-      kernelLaunches += 6 * ((k + 31) / 32) * 2;
     }
     if (info == 0) {
       if (k > 0)
@@ -1534,6 +1546,16 @@ int Engine::dual()
               numberIterations, hState->numEtas, d.k, hState->stop, hState->infeas,
               hState->thetaDual);
     const int stop = hState->stop;
+    if (done > 0 && refreshDualsEvery > 0 && hState->stop == STOP_NONE &&
+        (numberIterations / refreshDualsEvery) != ((numberIterations - done) / refreshDualsEvery)) {
+      launch_compute_duals(d, dPi, dZ, stream, true);
+      CUDA_OK(cudaMemsetAsync(dCounters, 0, sizeof(int) * 4, stream));
+      launch_make_dual_feasible(d, currentDualBound, dCounters, stream);
+      launch_compute_primals(d, dXn, dRhs, stream, true); // the flips moved nonbasic values
+    } else if (done > 0 && refreshPrimalsEvery > 0 && hState->stop == STOP_NONE &&
+               (numberIterations / refreshPrimalsEvery) != ((numberIterations - done) / refreshPrimalsEvery)) {
+      launch_compute_primals(d, dXn, dRhs, stream, true);
+    }
     if (done > 0 && currentAcceptablePivot < acceptablePivot && hState->numEtas >= 5)
       setAcceptablePivot(acceptablePivot); // acceptablePivot_ = fabs(...) once pivots() >= 5 (:2070-2074)
     if (stop == STOP_NONE) {
@@ -1718,10 +1740,10 @@ int Engine::updateColumnTranspose(double *vec)
 int Engine::replaceColumn(int sequenceIn, int pivotRow)
 {
   fetchState();
-  if (hState->numEtas >= d.tmax)
-    return 3; // no room in the update buffers (ClpFactorization.hpp:86)
   if (hState->numEtas >= tmax)
-    return 5; // maximum pivots reached (:87)
+    return 5; // maximum pivots reached (ClpFactorization.hpp:87)
+  if (hState->numEtas >= d.tmax)
+    return 3; // no room in the update buffers (:86)
   launch_unpack_column(d, sequenceIn, d.rhs3, stream);
   launch_ftran_buffer(d, d.rhs3, 1, true, stream);
   double alpha = 0.0;
@@ -1984,10 +2006,10 @@ int Engine::replaceColumnChecked(int sequenceIn, int pivotRow, double pivotCheck
 {
   fetchState();
   const int t = hState->numEtas;
-  if (t >= d.tmax)
-    return 3;
   if (t >= tmax)
-    return 5;
+    return 5; // maximum pivots: the update buffers are sized for exactly that many, so
+  if (t >= d.tmax)
+    return 3; // "no room" (:86) can only be seen if the two limits are ever decoupled
   launch_unpack_column(d, sequenceIn, d.rhs3, stream);
   launch_ftran_buffer(d, d.rhs3, 1, true, stream);
   double alpha = 0.0;

@@ -218,8 +218,8 @@ void launch_chuzr(const DeviceModel &d, cudaStream_t s); // stand-alone CHUZR (s
 void launch_dual_update_and_flips(const DeviceModel &d, unsigned int *flipBits, cudaStream_t s);
 void launch_pivot_updates(const DeviceModel &d, cudaStream_t s);
 void launch_make_dual_feasible(const DeviceModel &d, double dualBound, int *counters, cudaStream_t s);
-void launch_compute_primals(const DeviceModel &d, double *xn, double *rhs, cudaStream_t s);
-void launch_compute_duals(const DeviceModel &d, double *pi, double *z, cudaStream_t s);
+void launch_compute_primals(const DeviceModel &d, double *xn, double *rhs, cudaStream_t s, bool withEtas = false);
+void launch_compute_duals(const DeviceModel &d, double *pi, double *z, cudaStream_t s, bool withEtas = false);
 void launch_objective(const DeviceModel &d, double *out, cudaStream_t s);
 void launch_permute_weights(const double *wOld, double *wNew, const int *srcPos, int m,
                             cudaStream_t s);
@@ -231,7 +231,7 @@ void launch_eta_append_test(const DeviceModel &d, int pivotRow, int seqIn, cudaS
 int dense_invert(double *A, double *X, int k, int ld, int *dIpiv, int *dPerm, int *dInfo,
                  int *hostIpiv, int *hostPerm, double singularTol, cudaStream_t s, int shardW = 1,
                  int shardRank = 0, int (*allGather)(void *, void *, size_t, void *) = nullptr,
-                 void *comm = nullptr);
+                 void *comm = nullptr, void (*hostOverlap)(void *) = nullptr, void *overlapCtx = nullptr);
 void launch_transpose(const double *src, double *dst, int k, int ld, cudaStream_t s);
 
 } // namespace clpb

@@ -42,6 +42,7 @@ public:
   int factorizationFrequency = 0; // 0 = default formula
   int logLevel = 0;
   int batch = 16;                 // iterations enqueued per host synchronisation
+  int refreshDualsEvery = 0, refreshPrimalsEvery = 0; // experiments: recompute from scratch inside a cycle
   bool timing = false;
   bool useGraph = true;
   bool usePriceTma = false;       // TMA-staged price kernel (default: LDG-direct kernel, 26% faster)

@@ -29,15 +29,20 @@ constexpr int NB = 32;
 constexpr int kSlabPitch = NB + 1;       // padded row pitch in shared memory (bank conflicts)
 constexpr int kPanelMaxRowsPerCta = 640; // 640 rows x 33 x 8 B = 165 KB of shared memory
 
+// Monotone arrival counter (never reset inside a factorization: 'target' grows by gridDim.x per
+// barrier).  One acq_rel atomic per CTA + an acquire spin -- the formulation rowpass.cu measured at
+// ~1.5 us against ~3.5 us for fence + atomic + volatile spin + fence; with one barrier per matrix
+// column that difference is half of the panel time.
 __device__ __forceinline__ void grid_barrier(unsigned int *counter, unsigned int target)
 {
   __syncthreads();
   if (threadIdx.x == 0) {
-    __threadfence();
-    atomicAdd(counter, 1u);
-    while (*((volatile unsigned int *)counter) < target)
-      ;
-    __threadfence();
+    unsigned int o;
+    asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], %2;" : "=r"(o) : "l"(counter), "r"(1u) : "memory");
+    unsigned int v;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+    } while (v < target);
   }
   __syncthreads();
 }
@@ -262,22 +267,51 @@ __global__ void __launch_bounds__(1024)
   }
 }
 
-// apply the panel's row interchanges to columns [c0,c1) (thread per column)
-__global__ void lu_swap_kernel(double *__restrict__ A, int ld, int j0, int nb,
-                               const int *__restrict__ ipiv, int c0, int c1)
+// apply the panel's row interchanges to columns [c0,c1) (thread per column).  The nb interchanges
+// touch at most 2*nb rows; thread 0 composes them into one permutation of those rows (where does the
+// final content of each touched row come from), then every column is ONE round of independent loads
+// and one round of stores instead of nb dependent read-modify-write steps.
+__global__ void __launch_bounds__(128) lu_swap_kernel(double *__restrict__ A, int ld, int j0, int nb,
+                                                      const int *__restrict__ ipiv, int c0, int c1)
 {
-  int c = c0 + blockIdx.x * blockDim.x + threadIdx.x;
+  __shared__ int rows[2 * NB], from[2 * NB];
+  __shared__ int count;
+  if (threadIdx.x == 0) {
+    int n = 0;
+    auto find = [&](int r) {
+      for (int i = 0; i < n; i++)
+        if (rows[i] == r)
+          return i;
+      rows[n] = r;
+      from[n] = r;
+      return n++;
+    };
+    for (int jj = 0; jj < nb; jj++) {
+      const int j = j0 + jj, p = ipiv[j];
+      if (p != j) {
+        const int a = find(j), b = find(p);
+        const int t = from[a];
+        from[a] = from[b];
+        from[b] = t;
+      }
+    }
+    count = n;
+  }
+  __syncthreads();
+  const int c = c0 + blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= c1)
     return;
   double *col = A + (size_t)c * ld;
-  for (int jj = 0; jj < nb; jj++) {
-    int j = j0 + jj, p = ipiv[j];
-    if (p != j) {
-      double a = col[j];
-      col[j] = col[p];
-      col[p] = a;
-    }
-  }
+  const int n = count;
+  double v[2 * NB];
+#pragma unroll
+  for (int i = 0; i < 2 * NB; i++)
+    if (i < n)
+      v[i] = col[from[i]];
+#pragma unroll
+  for (int i = 0; i < 2 * NB; i++)
+    if (i < n && from[i] != rows[i])
+      col[rows[i]] = v[i];
 }
 
 // B[j0..j0+nb, c] := T^-1 B[.., c] for columns c in [c0,c1); T = nb x nb triangle of A at (j0,j0)
@@ -492,7 +526,8 @@ __global__ void zero_padding_kernel(double *__restrict__ M, int k, int ld)
    acceptable pivot).  Synchronizes the stream once (pivot vector -> permutation). */
 int dense_invert(double *A, double *X, int k, int ld, int *dIpiv, int *dPerm, int *dInfo,
                  int *hostIpiv, int *hostPerm, double singularTol, cudaStream_t s, int shardW,
-                 int shardRank, int (*allGather)(void *, void *, size_t, void *), void *comm)
+                 int shardRank, int (*allGather)(void *, void *, size_t, void *), void *comm,
+                 void (*hostOverlap)(void *), void *overlapCtx)
 {
   if (k <= 0)
     return 0;
@@ -523,7 +558,14 @@ int dense_invert(double *A, double *X, int k, int ld, int *dIpiv, int *dPerm, in
   for (int j0 = 0; j0 < k; j0 += NB) {
     int nb = k - j0 < NB ? k - j0 : NB;
     const int nrows = k - j0;
-    int G = (nrows + 31) / 32; // at least 32 rows per CTA
+    static int minRows = 0; // rows per CTA of the panel kernel: fewer, fatter CTAs make the per-column grid barrier cheaper
+    if (minRows == 0) {
+      const char *e = getenv("CLPB_PANEL_ROWS");
+      minRows = e ? atoi(e) : 32;
+      if (minRows < 32)
+        minRows = 32;
+    }
+    int G = (nrows + minRows - 1) / minRows;
     if (G > numSMs)
       G = numSMs;
     if (G < 1)
@@ -559,6 +601,8 @@ int dense_invert(double *A, double *X, int k, int ld, int *dIpiv, int *dPerm, in
   int info = 0;
   cudaMemcpyAsync(hostIpiv, dIpiv, sizeof(int) * k, cudaMemcpyDeviceToHost, s);
   cudaMemcpyAsync(&info, dInfo, sizeof(int), cudaMemcpyDeviceToHost, s);
+  if (hostOverlap)
+    hostOverlap(overlapCtx); // host work of the caller (S1 of the new basis) while the LU runs
   cudaStreamSynchronize(s);
   if (info != 0)
     return info;

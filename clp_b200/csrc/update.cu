@@ -707,26 +707,26 @@ void launch_make_dual_feasible(const DeviceModel &d, double dualBound, int *coun
 {
   make_dual_feasible_kernel<<<(d.nm + 255) / 256, 256, 0, s>>>(d, dualBound, counters);
 }
-void launch_compute_primals(const DeviceModel &d, double *xn, double *rhs, cudaStream_t s)
+void launch_compute_primals(const DeviceModel &d, double *xn, double *rhs, cudaStream_t s, bool withEtas)
 {
   // rhs = -A x_N + (nonbasic row values) ; x_B = B0^-1 rhs   (no etas: fresh factorization)
   if (d.n > 0)
     nonbasic_x_kernel<<<(d.n + 255) / 256, 256, 0, s>>>(d, xn);
   launch_times_rows(d, xn, rhs, -1.0, s);
   primal_rhs_slack_kernel<<<(d.m + 255) / 256, 256, 0, s>>>(d, rhs);
-  launch_ftran_buffer(d, rhs, 1, false, s);
+  launch_ftran_buffer(d, rhs, 1, withEtas, s);
   scatter_basic_kernel<<<(d.m + 255) / 256, 256, 0, s>>>(d, rhs);
   // one step of iterative refinement (ClpSimplex::computePrimals, src/ClpSimplex.cpp:1057-1110):
   // r = y - A x over ALL variables, x_B += B0^-1 r
   launch_times_rows(d, d.sol, rhs, -1.0, s);
   primal_residual_rows_kernel<<<(d.m + 255) / 256, 256, 0, s>>>(d, rhs);
-  launch_ftran_buffer(d, rhs, 1, false, s);
+  launch_ftran_buffer(d, rhs, 1, withEtas, s);
   add_basic_kernel<<<(d.m + 255) / 256, 256, 0, s>>>(d, rhs);
 }
-void launch_compute_duals(const DeviceModel &d, double *pi, double *z, cudaStream_t s)
+void launch_compute_duals(const DeviceModel &d, double *pi, double *z, cudaStream_t s, bool withEtas)
 {
   gather_basic_cost_kernel<<<(d.m + 255) / 256, 256, 0, s>>>(d, pi);
-  launch_btran_dense(d, pi, false, s);
+  launch_btran_dense(d, pi, withEtas, s);
   launch_transpose_times(d, pi, z, 1.0, s);
   reduced_cost_kernel<<<(d.nm + 255) / 256, 256, 0, s>>>(d, z, pi);
 }
