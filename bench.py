@@ -6,8 +6,8 @@
 Workloads
   N = 1 (default c2): BASELINE.json configs[1] -- synthetic random LP m=10k n=100k 1% nnz, fp64, dual
       steepest edge, no presolve / scaling / perturbation.  A *step* is one factorization cycle of the
-      hot path: `cycle` = 2000 dual simplex iterations plus the refactorization + recompute that ends
-      the cycle.  The timed window starts from a mid-solve basis (tests/golden/c2_status_it12000.npz:
+      hot path: `cycle` = 550 dual simplex iterations (twice the reference's default interval) plus the
+      refactorization + recompute that ends the cycle.  The timed window starts from a mid-solve basis (tests/golden/c2_status_it12000.npz:
       the basis the CPU oracle reaches after 12 000 iterations) so that the nucleus of the basis has a
       representative size.  After the window the SAME LP is solved from the all-slack basis to
       optimality: `wall_to_optimal_s`, final status and the planted optimum check.
@@ -15,8 +15,7 @@ Workloads
       north_star assigns to several GPUs.  One process per GPU; the matrix is column-sharded for the
       pricing pass and the factors (rows of the nucleus inverse, rows of the eta panel) are row-sharded;
       every rank holds the same m-vectors after ONE in-place NCCL all-gather per solve / pricing pass.
-      A step is 512 iterations (a quarter of the 2048-iteration factorization cycle, so the window
-      holds one refactorization per four steps).  `python bench.py --gpus 1 --workload c3` measures the
+      A step is half a factorization cycle (541 iterations; one refactorization per two steps).  `python bench.py --gpus 1 --workload c3` measures the
       same workload on one GPU (profiles/ holds that line; quoted in `strong_scaling_reference`).
   Inputs are larger than L2 (CSC copy of A >= 120 MB + factors), no L2 flush is needed.
 
@@ -60,12 +59,12 @@ def clp_default_frequency(m):
 
 
 def default_cycle(m):
-    # Engine::setupDevice (clp_b200/csrc/engine.cu): max(Clp default, m/5), capped at 2048
-    return max(8, min(2048, max(clp_default_frequency(m), m // 5)))
+    # Engine::setupDevice (clp_b200/csrc/engine.cu): twice Clp's default, capped at 2048
+    return max(8, min(2048, 2 * clp_default_frequency(m)))
 
 
 def step_iterations(name, cycle):
-    return 512 if name == "c3" else cycle
+    return cycle // 2 if name == "c3" else cycle
 
 
 def build_workload(name, local_rank=0):

@@ -157,378 +157,7 @@ void Engine::buildRowCopy(const std::vector<double> &val, std::vector<int> &rowS
     }
 }
 
-// Row and column scale factors, restating ClpPackedMatrix::scale (src/ClpPackedMatrix.cpp:4120-4640):
-// scaled a_ij = a_ij * rowScale[i] * columnScale[j].  Mode 1 equilibrium (row maxima), 2 geometric
-// (three passes of sqrt(min*max), the last column round skipped), 3/4 "auto": equilibrium first,
-// then geometric, keeping geometric only if its smallest/largest ratio is more than twice as good
-// (:4493-4513).  The final column pass (:4531-4581) makes the largest entry of every useful column
-// overallLargest.  Returns 1 (and leaves the problem unscaled) when the matrix entries already lie
-// in [0.5, 2] (:4262), 0 otherwise.  Tiny elements (<= 1e-20) are ignored rather than deleted.
-int Engine::computeScaling()
-{
-  rowScale.clear();
-  columnScale.clear();
-  if (scalingFlag <= 0 || m == 0 || n == 0)
-    return 1;
-  std::vector<char> useful(n, 0);
-  double largest = 0.0, smallest = 1.0e50;
-  for (int j = 0; j < n; j++) {
-    if (hUpper[j] > hLower[j] + 1.0e-12 || (haveUserStatus && hStatus[j] == basic)) {
-      for (int e = hColStart[j]; e < hColStart[j + 1]; e++) {
-        const double v = std::fabs(hVal[e]);
-        if (v > 1.0e-20) {
-          useful[j] = 1;
-          largest = std::max(largest, v);
-          smallest = std::min(smallest, v);
-        }
-      }
-    }
-  }
-  if (smallest >= 0.5 && largest <= 2.0)
-    return 1; // CLP_PACKEDSCALE_FORGET
-  std::vector<int> rowStart, colIdx;
-  std::vector<double> rval;
-  buildRowCopy(hVal, rowStart, colIdx, rval);
-  int scalingMethod = scalingFlag;
-  if (scalingMethod == 4)
-    scalingMethod = 3;
-  else if (scalingMethod >= 5)
-    scalingMethod = 2;
-  double savedOverallRatio = 0.0;
-  const double tolerance = 5.0 * primalTolerance;
-  double overallSmallest = 1.0e20;
-  bool finished = false;
-  rowScale.assign(m, 1.0);
-  columnScale.assign(n, 1.0);
-  while (!finished) {
-    int numberPass = 3;
-    std::fill(rowScale.begin(), rowScale.end(), 1.0);
-    std::fill(columnScale.begin(), columnScale.end(), 1.0);
-    if (scalingMethod == 1 || scalingMethod == 3) {
-      for (int i = 0; i < m; i++) { // maximum in each row
-        double big = 1.0e-10;
-        for (int e = rowStart[i]; e < rowStart[i + 1]; e++)
-          if (useful[colIdx[e]])
-            big = std::max(big, std::fabs(rval[e]));
-        rowScale[i] = 1.0 / big;
-      }
-    } else {
-      while (numberPass) {
-        numberPass--;
-        for (int i = 0; i < m; i++) { // geometric mean on row scales
-          double big = 1.0e-50, small = 1.0e50;
-          for (int e = rowStart[i]; e < rowStart[i + 1]; e++) {
-            const int j = colIdx[e];
-            if (useful[j]) {
-              const double v = std::fabs(rval[e]) * columnScale[j];
-              big = std::max(big, v);
-              small = std::min(small, v);
-            }
-          }
-          rowScale[i] = 1.0 / std::sqrt(small * big);
-        }
-        if (numberPass == 1)
-          break; // skip last column round
-        for (int j = 0; j < n; j++) { // geometric mean on column scales
-          if (!useful[j])
-            continue;
-          double big = 1.0e-50, small = 1.0e50;
-          for (int e = hColStart[j]; e < hColStart[j + 1]; e++) {
-            const double v = std::fabs(hVal[e]) * rowScale[hRow[e]];
-            big = std::max(big, v);
-            small = std::min(small, v);
-          }
-          columnScale[j] = 1.0 / std::sqrt(small * big);
-        }
-      }
-    }
-    // if ranges will make horrid then scale (:4459)
-    for (int i = 0; i < m; i++) {
-      const double difference = hUpper[n + i] - hLower[n + i];
-      const double scaledDifference = difference * rowScale[i];
-      if (scaledDifference > tolerance && scaledDifference < 1.0e-4) {
-        rowScale[i] *= 1.0e-4 / scaledDifference;
-        rowScale[i] = std::max(1.0e-10, std::min(1.0e10, rowScale[i]));
-      }
-    }
-    // what the smallest entry will be if the largest of its column is 1 (:4471)
-    overallSmallest = 1.0e50;
-    for (int j = 0; j < n; j++) {
-      if (!useful[j])
-        continue;
-      double big = 1.0e-20, small = 1.0e50;
-      for (int e = hColStart[j]; e < hColStart[j + 1]; e++) {
-        const double v = std::fabs(hVal[e] * rowScale[hRow[e]]);
-        big = std::max(big, v);
-        small = std::min(small, v);
-      }
-      if (overallSmallest * big > small)
-        overallSmallest = small / big;
-    }
-    if (scalingMethod == 1 || scalingMethod == 2) {
-      finished = true;
-    } else if (savedOverallRatio == 0.0 && scalingMethod != 4) {
-      savedOverallRatio = overallSmallest;
-      scalingMethod = 4;
-    } else {
-      if (overallSmallest > 2.0 * savedOverallRatio)
-        finished = true; // geometric was better
-      else
-        scalingMethod = 1; // redo equilibrium
-    }
-  }
-  double overallLargest = 1.0;
-  if (overallSmallest < 1.0e-1)
-    overallLargest = 1.0 / std::sqrt(overallSmallest);
-  overallLargest = std::min(100.0, overallLargest);
-  std::vector<char> usedRow(m, 0);
-  for (int j = 0; j < n; j++) {
-    if (hUpper[j] > hLower[j] + 1.0e-12 && hColStart[j + 1] > hColStart[j]) {
-      double big = 1.0e-20;
-      for (int e = hColStart[j]; e < hColStart[j + 1]; e++) {
-        usedRow[hRow[e]] = 1;
-        big = std::max(big, std::fabs(hVal[e] * rowScale[hRow[e]]));
-      }
-      columnScale[j] = overallLargest / big;
-      const double difference = hUpper[j] - hLower[j];
-      if (difference < 1.0e-5 * columnScale[j])
-        columnScale[j] = difference / 1.0e-5; // make gap larger
-    } else {
-      columnScale[j] = 1.0;
-    }
-  }
-  for (int i = 0; i < m; i++)
-    if (!usedRow[i])
-      rowScale[i] = 1.0;
-  return 0;
-}
-
-// ClpSimplex::createRim (src/ClpSimplex.cpp:7895ff) for the scaled problem: columns x' = x/c,
-// bounds/c, cost*c; rows activity' = r*activity, bounds*r.  Infinite bounds stay infinite.
-void Engine::prepareWorkingProblem()
-{
-  wVal = hVal;
-  wLower = hLower;
-  wUpper = hUpper;
-  wCost = hCost;
-  if (computeScaling() != 0)
-    return;
-  for (int j = 0; j < n; j++) {
-    const double c = columnScale[j];
-    for (int e = hColStart[j]; e < hColStart[j + 1]; e++)
-      wVal[e] = hVal[e] * rowScale[hRow[e]] * c;
-    if (wLower[j] > -kInf)
-      wLower[j] /= c;
-    if (wUpper[j] < kInf)
-      wUpper[j] /= c;
-    wCost[j] *= c;
-  }
-  for (int i = 0; i < m; i++) {
-    const double r = rowScale[i];
-    if (wLower[n + i] > -kInf)
-      wLower[n + i] *= r;
-    if (wUpper[n + i] < kInf)
-      wUpper[n + i] *= r;
-  }
-}
-
-// Dual (cost) perturbation before the first iteration, restating ClpSimplexDual::perturb
-// (src/ClpSimplexDual.cpp:6533-6964) for the default setting perturbation_ = 50 / 100: every
-// nonbasic, non-fixed column gets a cost change of the sign that keeps its reduced cost on the
-// feasible side, of a size that grows with the column length (weight[] table :6790) and is kept
-// inside [smallestAllowed, largestAllowed] (:6800-6803, :6862-6874).  Row costs are not modified
-// (:6754).  The random factors come from a fixed splitmix64 stream instead of CoinThreadRandom
-// (CoinUtils, not in the reference tree), so the individual perturbations are not the reference's;
-// the optimum is: the perturbed costs are handled like cost shifts -- removed at the first
-// "optimal" basis, after which the dual simplex continues on the true costs (engine.cu dual(),
-// the branch the reference takes through statusOfProblemInDual :5415ff).
-int Engine::perturbCosts(std::vector<double> &cost) const
-{
-  const double dualTol = dualTolerance;
-  const double largeValue = 1.0e15; // ClpSimplex::largeValue_
-  double perturbationSize = 1.0e-20;
-  double maximumFraction = 1.0e-5;
-  const double constantPerturbation = 100.0 * dualTol;
-  int maxLength = 0, minLength = m;
-  double averageCost = 0.0;
-  int numberNonZero = 0;
-  {
-    std::vector<double> sort(n);
-    for (int j = 0; j < n; j++) {
-      const double v = std::fabs(hCost[j]); // objective BEFORE scaling
-      sort[j] = v;
-      averageCost += v;
-      if (v != 0.0)
-        numberNonZero++;
-    }
-    averageCost = numberNonZero ? averageCost / numberNonZero : 1.0;
-    std::sort(sort.begin(), sort.end());
-    int number = n > 0 ? 1 : 0;
-    for (int j = 1; j < n; j++)
-      if (sort[j] != sort[j - 1])
-        number++;
-    if (!numberNonZero && perturbation < 55)
-      return 1; // the reference says "safer to use primal"
-    if (perturbation >= 100 && number * 4 > n)
-      return 1; // good enough: many distinct costs
-  }
-  for (int j = 0; j < n; j++)
-    if (wLower[j] < wUpper[j]) {
-      const int length = hColStart[j + 1] - hColStart[j];
-      if (length > 2) {
-        maxLength = std::max(maxLength, length);
-        minLength = std::min(minLength, length);
-      }
-    }
-  double smallestNonZero = 1.0e100;
-  {
-    perturbationSize = 1.0e-8;
-    bool allSame = true;
-    double lastValue = 0.0, lastValue2 = 0.0;
-    auto track = [&](double b, double &last) {
-      b = std::fabs(b);
-      if (last == 0.0)
-        last = b;
-      else if (std::fabs(b - last) > 1.0e-7)
-        allSame = false;
-    };
-    for (int i = 0; i < m; i++) {
-      const double lo = wLower[n + i], up = wUpper[n + i];
-      if (lo != 0.0 && lo > -1.0e10)
-        track(lo, lastValue);
-      if (up != 0.0 && up < 1.0e10)
-        track(up, lastValue);
-    }
-    for (int j = 0; j < n; j++) {
-      const double lo = wLower[j], up = wUpper[j];
-      if (lo < up) {
-        const double v = std::fabs(cost[j]);
-        perturbationSize = std::max(perturbationSize, v);
-        if (v != 0.0)
-          smallestNonZero = std::min(smallestNonZero, v);
-      }
-      if (lo != 0.0 && lo > -1.0e10)
-        track(lo, lastValue2);
-      if (up != 0.0 && up < 1.0e10)
-        track(up, lastValue2);
-    }
-    if (allSame) {
-      // all bounds alike: if the matrix entries are alike too, "really hit perturbation" (:6703)
-      double sn = 0.0, ln = 0.0, sp = 0.0, lp = 0.0;
-      bool first = true, firstP = true;
-      for (size_t e = 0; e < wVal.size(); e++) {
-        const double v = wVal[e];
-        if (v < 0.0) {
-          sn = first ? v : std::max(sn, v);
-          ln = first ? v : std::min(ln, v);
-          first = false;
-        } else if (v > 0.0) {
-          sp = firstP ? v : std::min(sp, v);
-          lp = firstP ? v : std::max(lp, v);
-          firstP = false;
-        }
-      }
-      if (sn == ln && sp == lp) {
-        const double adjust = std::min(100.0 * maximumFraction, 1.0e-3 * std::max(lastValue, lastValue2));
-        maximumFraction = std::max(adjust, maximumFraction);
-      }
-    }
-    perturbationSize = std::min(perturbationSize, smallestNonZero / maximumFraction);
-  }
-  const double weight[] = {1.0e-4, 1.0e-2, 5.0e-1, 1.0, 2.0, 5.0, 10.0, 20.0, 30.0, 40.0, 100.0};
-  const double factor = maxLength ? 3.0 / (double)minLength : 1.0;
-  const double m1 = 0.5;
-  const double smallestAllowed = std::min(1.0e-2 * dualTol, maximumFraction);
-  const double largestAllowed = std::max(1.0e3 * dualTol, maximumFraction * averageCost);
-  unsigned long long rngState = 0x9E3779B97F4A7C15ull;
-  auto rnd = [&]() { // splitmix64 -> [0,1)
-    unsigned long long z = (rngState += 0x9E3779B97F4A7C15ull);
-    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-    z ^= z >> 31;
-    return (double)(z >> 11) * (1.0 / 9007199254740992.0);
-  };
-  double largestZero = 0.0, largest = 0.0;
-  for (int j = 0; j < n; j++) {
-    const double r1 = rnd(), r2 = rnd(); // perturbationArray_[2j], [2j+1]
-    if (!(wLower[j] < wUpper[j]) || hStatus[j] == basic)
-      continue;
-    double value = perturbationSize;
-    const double currentValue = cost[j];
-    value = std::min(value, constantPerturbation +
-                                maximumFraction * (std::fabs(currentValue) + 1.0e-1 * perturbationSize + 1.0e-8));
-    double value2 = constantPerturbation + 1.0e-1 * smallestNonZero;
-    if (wLower[j] > -largeValue) {
-      if (std::fabs(wLower[j]) < std::fabs(wUpper[j])) {
-        value *= (1.0 - m1 + m1 * r1);
-        value2 *= (1.0 - m1 + m1 * r2);
-      } else {
-        value = 0.0;
-      }
-    } else if (wUpper[j] < largeValue) {
-      value *= -(1.0 - m1 + m1 * r1);
-      value2 *= -(1.0 - m1 + m1 * r2);
-    } else {
-      value = 0.0;
-    }
-    if (value == 0.0)
-      continue;
-    int length = hColStart[j + 1] - hColStart[j];
-    if (length > 3) {
-      length = (int)((double)length * factor);
-      length = std::max(3, length);
-    }
-    value *= length < 10 ? weight[length] : weight[10];
-    value = std::min(value, value2);
-    if (std::fabs(value) <= smallestAllowed) { // get in range
-      value *= 10.0;
-      while (std::fabs(value) <= smallestAllowed)
-        value *= 10.0;
-    } else if (std::fabs(value) > largestAllowed) {
-      value *= 0.1;
-      while (std::fabs(value) > largestAllowed)
-        value *= 0.1;
-    }
-    if (currentValue != 0.0)
-      largest = std::max(largest, std::fabs(value));
-    else
-      largestZero = std::max(largestZero, std::fabs(value));
-    if (hStatus[j] == atUpperBound)
-      value = -value; // but negative if at ub
-    cost[j] += value;
-  }
-  if (largestZero > largest && largest != 0.0) {
-    const double test = std::max(1.0e-8, largest);
-    for (int j = 0; j < n; j++)
-      if (hCost[j] == 0.0) {
-        double c = cost[j];
-        while (std::fabs(c) > test)
-          c *= 0.5;
-        cost[j] = c;
-      }
-  }
-  return 0;
-}
-
-// Host-only preview used by the CPU test-suite: builds the working problem (scaling included),
-// normalises the status array the way resetStateForRun does, and applies perturbCosts.
-int Engine::previewPerturbation(double *costOut)
-{
-  prepareWorkingProblem();
-  int nBasic = 0;
-  for (int j = 0; j < nm; j++)
-    if (hStatus[j] == basic)
-      nBasic++;
-  if (nBasic != m) {
-    hStatus.assign(nm, atLowerBound);
-    for (int i = 0; i < m; i++)
-      hStatus[n + i] = basic;
-  }
-  std::vector<double> pc(wCost.begin(), wCost.begin() + n);
-  const int rc = perturbCosts(pc);
-  std::copy(pc.begin(), pc.end(), costOut);
-  return rc;
-}
+// computeScaling / prepareWorkingProblem / perturbCosts / previewPerturbation: rim_prep.cpp
 
 // MPS basis file, restating ClpSimplexOther::writeBasis (src/ClpSimplexOther.cpp:1018-1133, the
 // branch without names and without values): every basic column is paired with the next nonbasic
@@ -731,6 +360,8 @@ int Engine::setupDevice()
   d.pivotVariable = dalloc<int>(m);
   d.weights = dalloc<double>(m);
   dWeightsTmp = dalloc<double>(m);
+  dSolOld = dalloc<double>(nm);
+  dDrift = dalloc<unsigned long long>(1);
   dSrcPos = dalloc<int>(m);
   d.posToNuc = dalloc<int>(m);
   d.nucRow = dalloc<int>(m);
@@ -739,11 +370,14 @@ int Engine::setupDevice()
   d.s1RowStart = dS1RowStart;
   dS1cStart = dalloc<int>(m + 1);
   d.s1cStart = dS1cStart;
-  // Clp's default frequency balances its sparse FT update against a sparse refactorization; here
-  // an eta costs one extra 8m-byte panel column per solve while a refactorization costs O(k^3)
-  // flops, so the default cycle is longer (the accuracy gate still forces early refactorizations)
-  tmax = factorizationFrequency > 0 ? factorizationFrequency
-                                    : std::max(defaultFactorizationFrequency(), m / 5);
+  // Refactorization interval.  The cost model alone (an eta costs one 8m-byte panel column per solve,
+  // a refactorization O(k^3) flops) would put it near 2000 at m = 1e4, but measured on the full-size
+  // random LP the long cycle costs ~10x more ITERATIONS to reach the same objective: the basic values
+  // carried by the update recurrence drift by 1e-4 .. 1 relative inside such a cycle (Engine::refresh
+  // measures it) and the row choice degrades.  Twice the reference's own default
+  // (ClpSimplex::defaultFactorizationFrequency) keeps the iteration quality of the reference's cadence
+  // (profiles/README.md: cycle experiments) at half its refactorization count.
+  tmax = factorizationFrequency > 0 ? factorizationFrequency : 2 * defaultFactorizationFrequency();
   tmax = std::max(8, std::min(tmax, 2048));
   d.tmax = roundUp(tmax, 8);
   d.W = dalloc<double>((size_t)m * d.tmax);
@@ -1183,6 +817,14 @@ int Engine::refactor()
 
 int Engine::refresh()
 {
+  // keep the recurrence-updated solution: its distance from the recomputed one is the accuracy monitor
+  // of the update cycle (ClpSimplexDual::statusOfProblemInDual compares saved and recomputed values the
+  // same way, src/ClpSimplexDual.cpp:5170-5195, and shortens the cycle through forceFactorization_)
+  const bool measure = numberRefactorizations > 0;
+  if (measure) {
+    CUDA_OK(cudaMemcpyAsync(dSolOld, d.sol, sizeof(double) * nm, cudaMemcpyDeviceToDevice, stream));
+    CUDA_OK(cudaMemsetAsync(dDrift, 0, sizeof(unsigned long long), stream));
+  }
   if (refactor() != 0)
     return -1;
   launch_compute_duals(d, dPi, dZ, stream);
@@ -1190,14 +832,21 @@ int Engine::refresh()
   launch_make_dual_feasible(d, currentDualBound, dCounters, stream);
   launch_compute_primals(d, dXn, dRhs, stream);
   kernelLaunches += 20;
+  if (measure) {
+    unsigned long long bits = 0ull;
+    launch_primal_drift(d, dSolOld, dDrift, stream);
+    CUDA_OK(cudaMemcpyAsync(&bits, dDrift, sizeof(bits), cudaMemcpyDeviceToHost, stream));
+    CUDA_OK(cudaStreamSynchronize(stream));
+    memcpy(&lastPrimalDrift, &bits, sizeof(double));
+  }
   if (logLevel > 0 && (logLevel > 1 || numberRefactorizations <= 60 || numberRefactorizations % 25 == 0)) {
     // progress line (the reference prints objective / infeasibilities at every refactorization)
     launch_objective(d, dObj, stream);
     double obj2[2];
     CUDA_OK(cudaMemcpyAsync(obj2, dObj, sizeof(double) * 2, cudaMemcpyDeviceToHost, stream));
     CUDA_OK(cudaStreamSynchronize(stream));
-    fprintf(stderr, "clp_b200: it %d refactorizations %d nucleus %d objective %.10g sum primal inf %.6g\n",
-            numberIterations, numberRefactorizations, d.k, obj2[0] + objectiveOffset, obj2[1]);
+    fprintf(stderr, "clp_b200: it %d refactorizations %d nucleus %d objective %.10g sum primal inf %.6g drift %.3g\n",
+            numberIterations, numberRefactorizations, d.k, obj2[0] + objectiveOffset, obj2[1], lastPrimalDrift);
   }
   return 0;
 }

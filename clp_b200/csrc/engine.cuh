@@ -221,6 +221,7 @@ void launch_make_dual_feasible(const DeviceModel &d, double dualBound, int *coun
 void launch_compute_primals(const DeviceModel &d, double *xn, double *rhs, cudaStream_t s, bool withEtas = false);
 void launch_compute_duals(const DeviceModel &d, double *pi, double *z, cudaStream_t s, bool withEtas = false);
 void launch_objective(const DeviceModel &d, double *out, cudaStream_t s);
+void launch_primal_drift(const DeviceModel &d, const double *xold, unsigned long long *out, cudaStream_t s);
 void launch_permute_weights(const double *wOld, double *wNew, const int *srcPos, int m,
                             cudaStream_t s);
 void launch_gather_nucleus_matrix(const DeviceModel &d, double *N, int ld, cudaStream_t s);

@@ -151,6 +151,10 @@ private:
   std::vector<void *> allocs;
   double *dXn = nullptr, *dRhs = nullptr, *dPi = nullptr, *dZ = nullptr, *dObj = nullptr;
   double *dWeightsTmp = nullptr;
+  double *dSolOld = nullptr;             // recurrence-updated solution kept across a refresh (drift measure)
+  unsigned long long *dDrift = nullptr;
+  double lastPrimalDrift = 0.0;          // relative, of the last refresh
+  int currentCycle = 0;                  // refactorization interval in force (adapted from the drift)
   int *dSrcPos = nullptr, *dCounters = nullptr;
   unsigned char *dFlipFlag = nullptr;
   int *dIpiv = nullptr, *dPerm = nullptr, *dInfo = nullptr;

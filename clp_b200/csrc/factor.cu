@@ -12,6 +12,7 @@
 // Everything is fp64 FMA; the matrix is column major with leading dimension ld.
 #include "engine.cuh"
 
+#include <cstdio>
 #include <cstdlib>
 #include <dlfcn.h>
 
@@ -267,51 +268,71 @@ __global__ void __launch_bounds__(1024)
   }
 }
 
-// apply the panel's row interchanges to columns [c0,c1) (thread per column).  The nb interchanges
-// touch at most 2*nb rows; thread 0 composes them into one permutation of those rows (where does the
-// final content of each touched row come from), then every column is ONE round of independent loads
-// and one round of stores instead of nb dependent read-modify-write steps.
-__global__ void __launch_bounds__(128) lu_swap_kernel(double *__restrict__ A, int ld, int j0, int nb,
-                                                      const int *__restrict__ ipiv, int c0, int c1)
+// Row interchanges of a panel applied to the columns left and right of it.  The nb interchanges touch
+// at most 2*nb rows; lu_perm_kernel composes them into ONE permutation of those rows (perm[0] = count,
+// perm[1+i] = touched row, perm[1+2*NB+i] = the row its final content comes from).  The elements are
+// then moved by two fully parallel kernels through a scratch buffer -- one thread per (column, touched
+// row): gather tmp[i][c] = A[from_i][c], scatter A[row_i][c] = tmp[i][c].  (One thread per column doing
+// its 2*nb strided loads serially left the GPU idle: 93 us per call at k = 4.7k.)
+__global__ void lu_perm_kernel(const int *__restrict__ ipiv, int j0, int nb, int *__restrict__ perm)
 {
-  __shared__ int rows[2 * NB], from[2 * NB];
-  __shared__ int count;
-  if (threadIdx.x == 0) {
-    int n = 0;
-    auto find = [&](int r) {
-      for (int i = 0; i < n; i++)
-        if (rows[i] == r)
-          return i;
-      rows[n] = r;
-      from[n] = r;
-      return n++;
-    };
-    for (int jj = 0; jj < nb; jj++) {
-      const int j = j0 + jj, p = ipiv[j];
-      if (p != j) {
-        const int a = find(j), b = find(p);
-        const int t = from[a];
-        from[a] = from[b];
-        from[b] = t;
-      }
+  int *rows = perm + 1, *from = perm + 1 + 2 * NB;
+  int n = 0;
+  for (int jj = 0; jj < nb; jj++) {
+    const int j = j0 + jj, p = ipiv[j];
+    if (p == j)
+      continue;
+    int a = -1, b = -1;
+    for (int i = 0; i < n; i++) {
+      if (rows[i] == j)
+        a = i;
+      if (rows[i] == p)
+        b = i;
     }
-    count = n;
+    if (a < 0) {
+      a = n++;
+      rows[a] = j;
+      from[a] = j;
+    }
+    if (b < 0) {
+      b = n++;
+      rows[b] = p;
+      from[b] = p;
+    }
+    const int t = from[a];
+    from[a] = from[b];
+    from[b] = t;
   }
-  __syncthreads();
-  const int c = c0 + blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= c1)
+  perm[0] = n;
+}
+// columns are indexed linearly over [0, left) U [right0, right0 + nright)
+__global__ void __launch_bounds__(128)
+    lu_swap_gather_kernel(const double *__restrict__ A, int ld, const int *__restrict__ perm, int left,
+                          int right0, int ncols, double *__restrict__ tmp)
+{
+  const int i = blockIdx.y;
+  if (i >= perm[0])
     return;
-  double *col = A + (size_t)c * ld;
-  const int n = count;
-  double v[2 * NB];
-#pragma unroll
-  for (int i = 0; i < 2 * NB; i++)
-    if (i < n)
-      v[i] = col[from[i]];
-#pragma unroll
-  for (int i = 0; i < 2 * NB; i++)
-    if (i < n && from[i] != rows[i])
-      col[rows[i]] = v[i];
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= ncols)
+    return;
+  const int c = q < left ? q : q - left + right0;
+  tmp[(size_t)i * ncols + q] = A[(size_t)c * ld + perm[1 + 2 * NB + i]];
+}
+__global__ void __launch_bounds__(128)
+    lu_swap_scatter_kernel(double *__restrict__ A, int ld, const int *__restrict__ perm, int left,
+                           int right0, int ncols, const double *__restrict__ tmp)
+{
+  const int i = blockIdx.y;
+  if (i >= perm[0])
+    return;
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= ncols)
+    return;
+  if (perm[1 + i] == perm[1 + 2 * NB + i])
+    return;
+  const int c = q < left ? q : q - left + right0;
+  A[(size_t)c * ld + perm[1 + i]] = tmp[(size_t)i * ncols + q];
 }
 
 // B[j0..j0+nb, c] := T^-1 B[.., c] for columns c in [c0,c1); T = nb x nb triangle of A at (j0,j0)
@@ -537,6 +558,21 @@ int dense_invert(double *A, double *X, int k, int ld, int *dIpiv, int *dPerm, in
   static double *pubRows = nullptr, *pubDiag = nullptr;
   static unsigned int *barCounter = nullptr;
   static int numSMs = 0;
+  static int *permBuf = nullptr;     // composed row permutation of the current panel (lu_perm_kernel)
+  static double *swapTmp = nullptr;  // [2*NB][k] staging of the interchanged rows
+  static size_t swapCap = 0;
+  if ((size_t)k > swapCap) {
+    if (swapTmp)
+      cudaFree(swapTmp);
+    swapCap = (size_t)k + k / 4 + 64;
+    if (cudaMalloc(&swapTmp, sizeof(double) * 2 * NB * swapCap) != cudaSuccess) {
+      swapTmp = nullptr;
+      swapCap = 0;
+      return -99;
+    }
+  }
+  if (!permBuf && cudaMalloc(&permBuf, sizeof(int) * (1 + 4 * NB)) != cudaSuccess)
+    return -99;
   if (!pubKey) {
     int dev = 0;
     cudaGetDevice(&dev); // one process drives one device
@@ -552,6 +588,15 @@ int dense_invert(double *A, double *X, int k, int ld, int *dIpiv, int *dPerm, in
     }
     cudaFuncSetAttribute(lu_panel_coop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          kPanelMaxRowsPerCta * kSlabPitch * (int)sizeof(double));
+  }
+  static int trace = -1;
+  if (trace < 0)
+    trace = getenv("CLPB_REFACTOR_TRACE") ? 1 : 0;
+  cudaEvent_t tev[6];
+  if (trace) {
+    for (auto &e : tev)
+      cudaEventCreate(&e);
+    cudaEventRecord(tev[0], s);
   }
   cudaMemsetAsync(barCounter, 0, sizeof(unsigned int), s);
   unsigned int barrierBase = 0;
@@ -588,17 +633,25 @@ int dense_invert(double *A, double *X, int k, int ld, int *dIpiv, int *dPerm, in
       lu_panel_kernel<<<1, 1024, 0, s>>>(A, k, ld, j0, nb, dIpiv, dInfo, singularTol);
     }
     // interchanges on the columns left and right of the panel
-    if (j0 > 0)
-      lu_swap_kernel<<<(j0 + 127) / 128, 128, 0, s>>>(A, ld, j0, nb, dIpiv, 0, j0);
     int c0 = j0 + nb;
+    {
+      const int ncols = j0 + (k - c0);
+      if (ncols > 0) {
+        lu_perm_kernel<<<1, 1, 0, s>>>(dIpiv, j0, nb, permBuf);
+        dim3 grid((ncols + 127) / 128, 2 * NB);
+        lu_swap_gather_kernel<<<grid, 128, 0, s>>>(A, ld, permBuf, j0, c0, ncols, swapTmp);
+        lu_swap_scatter_kernel<<<grid, 128, 0, s>>>(A, ld, permBuf, j0, c0, ncols, swapTmp);
+      }
+    }
     if (c0 < k) {
-      lu_swap_kernel<<<(k - c0 + 127) / 128, 128, 0, s>>>(A, ld, j0, nb, dIpiv, c0, k);
       trsm_kernel<<<(k - c0 + 127) / 128, 128, 0, s>>>(A, ld, A, ld, j0, nb, c0, k, true);
       gemm_sub(A + (size_t)c0 * ld + c0, ld, A + (size_t)j0 * ld + c0, ld,
                A + (size_t)c0 * ld + j0, ld, k - c0, k - c0, nb, s);
     }
   }
   int info = 0;
+  if (trace)
+    cudaEventRecord(tev[1], s);
   cudaMemcpyAsync(hostIpiv, dIpiv, sizeof(int) * k, cudaMemcpyDeviceToHost, s);
   cudaMemcpyAsync(&info, dInfo, sizeof(int), cudaMemcpyDeviceToHost, s);
   if (hostOverlap)
@@ -652,6 +705,8 @@ int dense_invert(double *A, double *X, int k, int ld, int *dIpiv, int *dPerm, in
     if (J1 < k)
       gemm_sub(X + J1, ld, A + (size_t)J0 * ld + J1, ld, X + J0, ld, k - J1, ncol, J1 - J0, s);
   }
+  if (trace)
+    cudaEventRecord(tev[2], s);
   // backward: X := U^-1 X
   const int lastOuter = ((k - 1) / OB) * OB;
   for (int J0 = lastOuter; J0 >= 0; J0 -= OB) {
@@ -669,6 +724,17 @@ int dense_invert(double *A, double *X, int k, int ld, int *dIpiv, int *dPerm, in
   }
   X = Xfull;
   (void)kfull;
+  if (trace) {
+    cudaEventRecord(tev[3], s);
+    cudaEventSynchronize(tev[3]);
+    float a = 0, b = 0, c = 0;
+    cudaEventElapsedTime(&a, tev[0], tev[1]);
+    cudaEventElapsedTime(&b, tev[1], tev[2]);
+    cudaEventElapsedTime(&c, tev[2], tev[3]);
+    fprintf(stderr, "clp_b200: dense_invert k %d: LU %.2f ms, host sync + forward %.2f ms, backward %.2f ms\n", k, a, b, c);
+    for (auto &e : tev)
+      cudaEventDestroy(e);
+  }
   if (shardW > 1 && allGather != nullptr) {
     if (allGather(comm, X, sizeof(double) * (size_t)perC * ld, s) != 0)
       return -98;

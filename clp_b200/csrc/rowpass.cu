@@ -266,14 +266,25 @@ __global__ void __launch_bounds__(1024, 1) row_pass_kernel(DeviceModel d)
     hist_min_aggregated(d.hist2Min, sb, bits, in, &sHotMin);
     // candidates of the crossing bucket and the next one: the short list every CTA scans for the
     // Harris bound and the pivot (see P4/P5) -- unordered, min/max do not care
-    if (flags[e] & F_CAND) {
+    {
+      // one atomic per warp (the candidates of the window are hundreds to thousands: one same-address
+      // atomic each would serialise in L2)
       const int bk = (int)(bits >> 48) & (kHistBuckets - 1);
-      if (bk >= bucket1 && bk <= bucket1 + kWindowBuckets) {
-        const int at = atomicAdd(d.candCount, 1);
-        if (at < kListCap) {
-          d.candA[at] = aabs[e];
-          d.candD[at] = dtil[e];
-          d.candJ[at] = gtid + e * gthreads;
+      const bool inWin = (flags[e] & F_CAND) && bk >= bucket1 && bk <= bucket1 + kWindowBuckets;
+      const unsigned wm = __ballot_sync(0xffffffffu, inWin);
+      if (wm) {
+        int base = 0;
+        const int leader = __ffs(wm) - 1;
+        if (lane == leader)
+          base = atomicAdd(d.candCount, __popc(wm));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (inWin) {
+          const int at = base + __popc(wm & ((1u << lane) - 1u));
+          if (at < kListCap) {
+            d.candA[at] = aabs[e];
+            d.candD[at] = dtil[e];
+            d.candJ[at] = gtid + e * gthreads;
+          }
         }
       }
     }

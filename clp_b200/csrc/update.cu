@@ -702,6 +702,29 @@ void launch_eta_append_test(const DeviceModel &d, int pivotRow, int seqIn, cudaS
   eta_append_finish_kernel<<<1, 1, 0, s>>>(d, seqIn);
 }
 
+// largest relative change of a basic value between the recurrence-updated solution (xold) and the one
+// recomputed from scratch: out[0] = max_p |x - xold| / (1 + |x|) as double bits (positive => ordered)
+__global__ void primal_drift_kernel(DeviceModel d, const double *__restrict__ xold, unsigned long long *out)
+{
+  double worst = 0.0;
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < d.m; p += gridDim.x * blockDim.x) {
+    const int seq = d.pivotVariable[p];
+    const double x = d.sol[seq];
+    const double r = fabs(x - xold[seq]) / (1.0 + fabs(x));
+    worst = r > worst ? r : worst; // NaN never wins
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+    worst = fmax(worst, __shfl_xor_sync(0xffffffffu, worst, o));
+  if ((threadIdx.x & 31) == 0 && worst > 0.0)
+    atomicMax(out, (unsigned long long)__double_as_longlong(worst));
+}
+void launch_primal_drift(const DeviceModel &d, const double *xold, unsigned long long *out, cudaStream_t s)
+{
+  int blocks = (d.m + 255) / 256;
+  primal_drift_kernel<<<blocks > 148 * 4 ? 148 * 4 : blocks, 256, 0, s>>>(d, xold, out);
+}
+
 // ---- host wrappers used by engine.cu
 void launch_make_dual_feasible(const DeviceModel &d, double dualBound, int *counters, cudaStream_t s)
 {
