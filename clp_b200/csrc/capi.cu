@@ -233,6 +233,8 @@ int Clpb_setParameter(Clpb_Simplex *model, const char *key, double value)
     e.refreshDualsEvery = (int)value;
   else if (k == "refreshPrimalsEvery")
     e.refreshPrimalsEvery = (int)value;
+  else if (k == "shardPanel")
+    e.shardPanelMode = (int)value;
   else if (k == "shardMinNnzPerRank")
     e.shardMinNnzPerRank = (long long)value;
   else if (k == "factorMode")

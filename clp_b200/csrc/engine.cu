@@ -262,7 +262,7 @@ int Engine::setupDevice()
   // rebuilds it instead of being silently ignored
   const long long signature = (long long)scalingFlag * 1000003ll + (long long)factorizationFrequency * 101ll +
                               (timing ? 7 : 0) + (long long)worldSize * 13ll + (long long)rank * 17ll +
-                              (usePriceTma ? 3 : 0) + (long long)factorMode * 29ll + (shardActive() ? 31 : 0);
+                              (usePriceTma ? 3 : 0) + (long long)factorMode * 29ll + (shardActive() ? 31 : 0) + (long long)(shardPanelMode + 1) * 37ll;
   if (deviceReady && signature == readySignature)
     return 0;
   if (deviceReady)
@@ -449,11 +449,17 @@ int Engine::setupDevice()
   d.zeroTolerance = zeroTolerance;
   d.flagged = dalloc<unsigned char>(m);
   d.shardW = 1;
+  d.shardPanel = 0;
   d.shardRank = 0;
   d.shardPerK = d.shardPerM = roundUp(m, 8);
   d.gatherY = d.gatherB = d.gatherP = nullptr;
   if (shardActive()) {
     d.shardW = worldSize;
+    // the eta panel streams 8*m*t bytes (t = updates since the last refactorization, on average half
+    // the cycle); sharding it costs one more all-gather per iteration (~50 us inside the graph, measured
+    // at C3), so it is sharded only when the average replicated pass is slower than that
+    d.shardPanel = shardPanelMode >= 0 ? shardPanelMode
+                                       : ((8.0 * m * (tmaxHint() / 2.0)) / 2.8e12 * (1.0 - 1.0 / worldSize) > 120e-6 ? 1 : 0);
     d.shardRank = rank;
     d.shardPerK = d.shardPerM = roundUp((m + worldSize - 1) / worldSize, 8);
     d.gatherY = dalloc<double>((size_t)worldSize * 3 * d.shardPerK);

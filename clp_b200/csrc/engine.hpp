@@ -8,6 +8,7 @@
 #pragma once
 #include "engine.cuh"
 
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -74,6 +75,8 @@ public:
   // collectives' latency (north_star: "only when n is large enough"); otherwise every rank runs the
   // whole iteration on its own ("replicas only")
   long long shardMinNnzPerRank = 4000000;
+  int shardPanelMode = -1; // -1 decide from the panel size, 0 replicate the eta panel, 1 shard it
+  int tmaxHint() const { return factorizationFrequency > 0 ? factorizationFrequency : std::min(2048, 2 * defaultFactorizationFrequency()); }
   bool shardActive() const;
 
   // ---- solve (ClpSimplex::dual) ----

@@ -12,6 +12,8 @@
 // Everything is fp64 FMA; the matrix is column major with leading dimension ld.
 #include "engine.cuh"
 
+#include <cooperative_groups.h>
+
 #include <cstdio>
 #include <cstdlib>
 #include <dlfcn.h>
@@ -173,6 +175,114 @@ __global__ void __launch_bounds__(256)
     }
     __syncthreads();
   }
+  for (int c = 0; c < nb; c++)
+    for (int q = tid; q < rowsLocal; q += 256)
+      A[(size_t)(j0 + c) * ld + r0 + q] = slab[q * kSlabPitch + c];
+}
+
+// ---- the same panel on ONE thread-block cluster (16 CTAs of one GPC, distributed shared memory).
+// The per-column pivot exchange of lu_panel_coop_kernel costs a grid barrier plus two dependent L2 round
+// trips (~4 us per column, ncu launch list r2: 129 us per 32-column panel); inside a cluster the candidate
+// keys, the pivot row and the diagonal row are read straight out of the peers' shared memory and the two
+// synchronisations are hardware cluster barriers.  Panels of up to 16 x kPanelMaxRowsPerCta rows.
+constexpr int kPanelCluster = 16;
+
+__global__ void __launch_bounds__(256)
+    lu_panel_cluster_kernel(double *__restrict__ A, int k, int ld, int j0, int nb, int R,
+                            int *__restrict__ ipiv, int *__restrict__ info, double singularTol)
+{
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  extern __shared__ double slab[]; // [R][kSlabPitch], same offset in every CTA of the cluster
+  __shared__ unsigned long long sBest[8];
+  __shared__ unsigned long long sKey;  // this CTA's candidate of the current column
+  __shared__ unsigned long long sWin;
+  __shared__ double urow[NB], drow[NB];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int cta = (int)cluster.block_rank();
+  const int r0 = j0 + cta * R;
+  const int rowsLocal = max(0, min(R, k - r0));
+  for (int c = 0; c < nb; c++)
+    for (int q = tid; q < rowsLocal; q += 256)
+      slab[q * kSlabPitch + c] = A[(size_t)(j0 + c) * ld + r0 + q];
+  __syncthreads();
+  for (int jj = 0; jj < nb; jj++) {
+    const int j = j0 + jj;
+    const int ownerJ = (j - j0) / R;
+    unsigned long long best = 0ull;
+    for (int q = tid; q < rowsLocal; q += 256) {
+      const int gi = r0 + q;
+      if (gi >= j) {
+        const double a = fabs(slab[q * kSlabPitch + jj]);
+        best = max(best, ((unsigned long long)__double_as_longlong(a) & ~0xFFFFFull) |
+                             (unsigned long long)(0xFFFFF - (gi - j0)));
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+      best = max(best, __shfl_xor_sync(0xffffffffu, best, o));
+    if (lane == 0)
+      sBest[warp] = best;
+    __syncthreads();
+    if (tid == 0) {
+      unsigned long long cand = 0ull;
+#pragma unroll
+      for (int w = 0; w < 8; w++)
+        cand = max(cand, sBest[w]);
+      sKey = cand;
+    }
+    cluster.sync(); // every CTA's candidate is published
+    if (warp == 0) {
+      unsigned long long v = 0ull;
+      if (lane < kPanelCluster)
+        v = *cluster.map_shared_rank(&sKey, lane);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1)
+        v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+      if (lane == 0)
+        sWin = v;
+    }
+    __syncthreads();
+    const unsigned long long wkey = sWin;
+    const double pivAbs = __longlong_as_double((long long)(wkey & ~0xFFFFFull));
+    const int piv = j0 + (0xFFFFF - (int)(wkey & 0xFFFFFull));
+    const bool singular = (wkey == 0ull) || !(pivAbs >= singularTol);
+    if (cta == 0 && tid == 0) {
+      ipiv[j] = singular ? j : piv;
+      if (singular && *info == 0)
+        *info = j + 1;
+    }
+    if (singular) {
+      cluster.sync(); // keep the barrier count uniform
+      continue;
+    }
+    const int ownerP = (piv - j0) / R;
+    if (tid < NB) { // pivot row and diagonal row out of their owners' slabs (distributed shared memory)
+      const double *ps = cluster.map_shared_rank(slab, ownerP);
+      const double *ds = cluster.map_shared_rank(slab, ownerJ);
+      urow[tid] = ps[(piv - (j0 + ownerP * R)) * kSlabPitch + tid];
+      drow[tid] = ds[(j - (j0 + ownerJ * R)) * kSlabPitch + tid];
+    }
+    cluster.sync(); // everybody holds both rows: the owners may overwrite them now
+    if (piv != j && ownerP == cta && tid < NB)
+      slab[(piv - r0) * kSlabPitch + tid] = drow[tid];
+    __syncthreads();
+    if (ownerJ == cta && tid < NB)
+      slab[(j - r0) * kSlabPitch + tid] = urow[tid];
+    __syncthreads();
+    const double inv = 1.0 / urow[jj];
+    for (int q = tid; q < rowsLocal; q += 256) {
+      if (r0 + q > j) {
+        double *r = slab + q * kSlabPitch;
+        const double l = r[jj] * inv;
+        r[jj] = l;
+        for (int c = jj + 1; c < nb; c++)
+          r[c] = fma(-l, urow[c], r[c]);
+      }
+    }
+    __syncthreads();
+  }
+  cluster.sync(); // nobody exits while a peer may still read its shared memory
   for (int c = 0; c < nb; c++)
     for (int q = tid; q < rowsLocal; q += 256)
       A[(size_t)(j0 + c) * ld + r0 + q] = slab[q * kSlabPitch + c];
@@ -558,6 +668,7 @@ int dense_invert(double *A, double *X, int k, int ld, int *dIpiv, int *dPerm, in
   static double *pubRows = nullptr, *pubDiag = nullptr;
   static unsigned int *barCounter = nullptr;
   static int numSMs = 0;
+  static int clusterState = getenv("CLPB_NO_CLUSTER_PANEL") ? -1 : 0; // 0 untried, 1 usable, -1 refused
   static int *permBuf = nullptr;     // composed row permutation of the current panel (lu_perm_kernel)
   static double *swapTmp = nullptr;  // [2*NB][k] staging of the interchanged rows
   static size_t swapCap = 0;
@@ -616,7 +727,44 @@ int dense_invert(double *A, double *X, int k, int ld, int *dIpiv, int *dPerm, in
     if (G < 1)
       G = 1;
     int R = (nrows + G - 1) / G;
-    if (R <= kPanelMaxRowsPerCta) {
+    bool panelDone = false;
+    if (clusterState >= 0 && nrows <= kPanelCluster * kPanelMaxRowsPerCta) {
+      // one 16-CTA cluster (non-portable size: opted in once); falls back for good if the launch is refused
+      const int Rc = (nrows + kPanelCluster - 1) / kPanelCluster;
+      const size_t smem = (size_t)Rc * kSlabPitch * sizeof(double);
+      if (clusterState == 0) {
+        clusterState = 1;
+        if (cudaFuncSetAttribute(lu_panel_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess ||
+            cudaFuncSetAttribute(lu_panel_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 kPanelMaxRowsPerCta * kSlabPitch * (int)sizeof(double)) != cudaSuccess) {
+          cudaGetLastError();
+          clusterState = -1;
+        }
+      }
+      if (clusterState > 0) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(kPanelCluster);
+        cfg.blockDim = dim3(256);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = s;
+        cudaLaunchAttribute attr;
+        attr.id = cudaLaunchAttributeClusterDimension;
+        attr.val.clusterDim.x = kPanelCluster;
+        attr.val.clusterDim.y = 1;
+        attr.val.clusterDim.z = 1;
+        cfg.attrs = &attr;
+        cfg.numAttrs = 1;
+        if (cudaLaunchKernelEx(&cfg, lu_panel_cluster_kernel, A, k, ld, j0, nb, Rc, dIpiv, dInfo, singularTol) ==
+            cudaSuccess) {
+          panelDone = true;
+        } else {
+          cudaGetLastError();
+          clusterState = -1;
+        }
+      }
+    }
+    if (panelDone) {
+    } else if (R <= kPanelMaxRowsPerCta) {
       double *Aarg = A;
       int karg = k, ldarg = ld, j0arg = j0, nbarg = nb, Rarg = R;
       double tolarg = singularTol;

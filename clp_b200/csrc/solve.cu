@@ -366,7 +366,7 @@ __global__ void __launch_bounds__(256) pfi_apply_warp_kernel(DeviceModel d, doub
   const int t = d.st->numEtas;
   // row-sharded run: this rank's positions only, results into its chunk of gatherP (written even
   // when there is no eta: the all-gather and the merge that follow are part of a fixed sequence)
-  const bool sharded = d.shardW > 1;
+  const bool sharded = d.shardW > 1 && d.shardPanel;
   const int pBegin = sharded ? min(d.m, d.shardRank * d.shardPerM) : 0;
   const int pEnd = sharded ? min(d.m, pBegin + d.shardPerM) : d.m;
   if (t > 0 || sharded) {
@@ -485,7 +485,7 @@ static void ftran_impl(const DeviceModel &d, double *b, bool applyEtas, bool che
   ftran_spread_kernel<NRHS><<<(m * 8 + 255) / 256, 256, 0, s>>>(d, b, m, y, checkState, applyEtas);
   if (applyEtas) {
     pfi_mu_kernel<NRHS><<<d.tmax, 256, 0, s>>>(d, checkState);
-    if (sharded) {
+    if (sharded && d.shardPanel) {
       int pblocks = (d.shardPerM + 7) / 8;
       if (pblocks > 148 * 8)
         pblocks = 148 * 8;

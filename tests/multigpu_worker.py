@@ -22,6 +22,7 @@ s = clp_b200.ClpSimplex(); s.loadLP(lp)
 uid = clp_b200.ClpSimplex.ncclUniqueId() if rank == 0 else np.zeros(128, dtype=np.uint8)
 uid = broadcast_unique_id(uid, src=0)
 s.setParameter("shardMinNnzPerRank", 0)  # small test problem: force the sharded path
+s.setParameter("shardPanel", 1)          # ... including the row-sharded eta panel
 s.initSharding(rank, world, uid)
 if len(sys.argv) > 5:
     s.setMaximumIterations(int(sys.argv[5]))

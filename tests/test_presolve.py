@@ -138,3 +138,38 @@ def test_initial_solve_with_presolve_on_the_device(name, seed):
     assert s.initialSolve(presolve=True) == 0
     assert abs(s.objectiveValue() - ref.objective_value) <= 1e-8 * (1 + abs(ref.objective_value))
     full_audit(lp, s)
+
+
+def test_presolve_to_an_empty_model_is_solved_on_the_host():
+    """every row a singleton: presolve folds all rows into column bounds and the reduced model has no
+    rows -- Engine::dual must not launch zero-block kernels for it (host-only trivial solve), and
+    initialSolve reports the optimum of the ORIGINAL model"""
+    n = 12
+    rng = np.random.default_rng(3)
+    start = np.arange(n + 1, dtype=np.int32)
+    rows = np.arange(n, dtype=np.int32)
+    el = rng.choice([-2.0, 0.5, 3.0], size=n)
+    cost = rng.standard_normal(n)
+    lp = G.LP("all-singleton", n, n, start, rows, el, np.full(n, -5.0), np.full(n, 7.0), cost,
+              np.full(n, -4.0), np.full(n, 6.0))
+    s = clp_b200.ClpSimplex()
+    s.loadLP(lp)
+    assert s.initialSolve() == 0          # no CUDA device is needed for this model
+    assert s.status() == 0
+    o = O.OracleSimplex(lp)
+    assert o.dual() == 0
+    assert abs(s.objectiveValue() - o.objective_value) <= 1e-9 * (1 + abs(o.objective_value))
+    assert O.kkt_violations(lp, s.primalColumnSolution(), s.primalRowSolution(), s.dualColumnSolution()) == 0
+
+
+def test_presolve_infeasibility_is_reported_on_the_original_model():
+    """a singleton row that contradicts the column bounds: presolve proves infeasibility itself and
+    the original model must say so (status 1), not keep a stale -1"""
+    start = np.array([0, 1, 2], dtype=np.int32)
+    lp = G.LP("contradiction", 2, 2, start, np.array([0, 1], dtype=np.int32), np.array([1.0, 1.0]),
+              np.array([0.0, 0.0]), np.array([1.0, 1.0]), np.array([1.0, 1.0]),
+              np.array([3.0, -1e30]), np.array([1e30, 5.0]))
+    s = clp_b200.ClpSimplex()
+    s.loadLP(lp)
+    assert s.initialSolve() == 1
+    assert s.status() == 1 and s.isProvenPrimalInfeasible()
