@@ -43,6 +43,11 @@ SIGNATURES = {
     "Clpb_copyinStatus": (None, [ctypes.c_void_p, c_ubyte_p]),
     "Clpb_writeBasis": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int, ctypes.c_int]),
     "Clpb_readBasis": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p]),
+    "Clpb_chgColumnLower": (None, [ctypes.c_void_p, c_double_p]),
+    "Clpb_chgColumnUpper": (None, [ctypes.c_void_p, c_double_p]),
+    "Clpb_chgRowLower": (None, [ctypes.c_void_p, c_double_p]),
+    "Clpb_chgRowUpper": (None, [ctypes.c_void_p, c_double_p]),
+    "Clpb_lastSolveWasHot": (ctypes.c_int, [ctypes.c_void_p]),
     "Clpb_dual": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "Clpb_status": (ctypes.c_int, [ctypes.c_void_p]),
     "Clpb_objectiveValue": (ctypes.c_double, [ctypes.c_void_p]),

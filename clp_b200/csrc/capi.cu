@@ -117,6 +117,7 @@ Clpb_Simplex *Clpb_presolvedModel(Clpb_Simplex *model, int *status)
   red->e.useRowPass = model->e.useRowPass;
   red->e.usePriceTma = model->e.usePriceTma;
   red->e.factorMode = model->e.factorMode;
+  red->e.dualRowPivot = model->e.dualRowPivot;
   red->e.rank = model->e.rank;
   red->e.worldSize = model->e.worldSize;
   red->e.ncclComm = model->e.ncclComm;
@@ -233,6 +234,10 @@ int Clpb_setParameter(Clpb_Simplex *model, const char *key, double value)
     e.refreshDualsEvery = (int)value;
   else if (k == "refreshPrimalsEvery")
     e.refreshPrimalsEvery = (int)value;
+  else if (k == "hotStart")
+    e.hotStart = value != 0.0;
+  else if (k == "dualRowPivot")
+    e.dualRowPivot = (int)value;
   else if (k == "shardPanel")
     e.shardPanelMode = (int)value;
   else if (k == "shardMinNnzPerRank")
@@ -267,6 +272,11 @@ void Clpb_copyinStatus(Clpb_Simplex *model, const unsigned char *statusArray)
 {
   model->e.setStatus(statusArray);
 }
+void Clpb_chgColumnLower(Clpb_Simplex *model, const double *columnLower) { model->e.chgBounds(columnLower, nullptr, nullptr, nullptr); }
+void Clpb_chgColumnUpper(Clpb_Simplex *model, const double *columnUpper) { model->e.chgBounds(nullptr, columnUpper, nullptr, nullptr); }
+void Clpb_chgRowLower(Clpb_Simplex *model, const double *rowLower) { model->e.chgBounds(nullptr, nullptr, rowLower, nullptr); }
+void Clpb_chgRowUpper(Clpb_Simplex *model, const double *rowUpper) { model->e.chgBounds(nullptr, nullptr, nullptr, rowUpper); }
+int Clpb_lastSolveWasHot(Clpb_Simplex *model) { return model->e.lastSolveWasHot ? 1 : 0; }
 int Clpb_dual(Clpb_Simplex *model, int)
 {
   return guarded([&] { return model->e.dual(); });

@@ -61,6 +61,7 @@ void Engine::freeAll()
     cudaStreamDestroy(stream);
   stream = nullptr;
   deviceReady = false;
+  factorsValid = false;
   nucCap = 0;
   s1Cap = 0;
 }
@@ -135,6 +136,7 @@ void Engine::setStatus(const unsigned char *st)
 {
   hStatus.assign(st, st + nm);
   haveUserStatus = true;
+  factorsValid = false; // a basis handed in from outside is factorized afresh
 }
 
 void Engine::buildRowCopy(const std::vector<double> &val, std::vector<int> &rowStart,
@@ -262,7 +264,7 @@ int Engine::setupDevice()
   // rebuilds it instead of being silently ignored
   const long long signature = (long long)scalingFlag * 1000003ll + (long long)factorizationFrequency * 101ll +
                               (timing ? 7 : 0) + (long long)worldSize * 13ll + (long long)rank * 17ll +
-                              (usePriceTma ? 3 : 0) + (long long)factorMode * 29ll + (shardActive() ? 31 : 0) + (long long)(shardPanelMode + 1) * 37ll;
+                              (usePriceTma ? 3 : 0) + (long long)factorMode * 29ll + (shardActive() ? 31 : 0) + (long long)(shardPanelMode + 1) * 37ll + (long long)dualRowPivot * 41ll;
   if (deviceReady && signature == readySignature)
     return 0;
   if (deviceReady)
@@ -448,6 +450,7 @@ int Engine::setupDevice()
   d.dualTolerance = dualTolerance;
   d.zeroTolerance = zeroTolerance;
   d.flagged = dalloc<unsigned char>(m);
+  d.dantzig = dualRowPivot == 1 ? 1 : 0;
   d.shardW = 1;
   d.shardPanel = 0;
   d.shardRank = 0;
@@ -760,6 +763,7 @@ int Engine::refactor()
       CUDA_OK(cudaMemsetAsync(&d.st->numFlagged, 0, sizeof(int), stream));
       CUDA_OK(cudaStreamSynchronize(stream));
       hPivot = newPivot;
+      factorsValid = true;
       numberRefactorizations++;
       lastNucleusSize = k;
       if (timing) {
@@ -1063,6 +1067,67 @@ int Engine::trivialSolve()
   return problemStatus;
 }
 
+void Engine::boundsToWorking()
+{
+  wLower = hLower;
+  wUpper = hUpper;
+  if (rowScale.empty())
+    return;
+  const auto finite = [](double v) { return v > -kInf && v < kInf; };
+  for (int j = 0; j < n; j++) {
+    if (finite(wLower[j]))
+      wLower[j] /= columnScale[j];
+    if (finite(wUpper[j]))
+      wUpper[j] /= columnScale[j];
+  }
+  for (int i = 0; i < m; i++) {
+    if (finite(wLower[n + i]))
+      wLower[n + i] *= rowScale[i];
+    if (finite(wUpper[n + i]))
+      wUpper[n + i] *= rowScale[i];
+  }
+}
+
+void Engine::chgBounds(const double *columnLower, const double *columnUpper, const double *rowLower,
+                       const double *rowUpper)
+{
+  auto lo = [](double v) { return v < -1.0e29 ? -kInf : v; };
+  auto up = [](double v) { return v > 1.0e29 ? kInf : v; };
+  for (int j = 0; j < n; j++) {
+    if (columnLower)
+      hLower[j] = lo(columnLower[j]);
+    if (columnUpper)
+      hUpper[j] = up(columnUpper[j]);
+  }
+  for (int i = 0; i < m; i++) {
+    if (rowLower)
+      hLower[n + i] = lo(rowLower[i]);
+    if (rowUpper)
+      hUpper[n + i] = up(rowUpper[i]);
+  }
+  if (deviceReady)
+    boundsToWorking(); // the scale factors of the device copy stay in force
+}
+
+// Re-impose the bounds on the device-resident state of the previous solve and recompute x_B through the
+// factors + eta file that are already there (no upload of the matrix, no refactorization).
+int Engine::hotPrepare()
+{
+  CUDA_OK(cudaMemcpyAsync(d.lowerTrue, wLower.data(), sizeof(double) * nm, cudaMemcpyHostToDevice, stream));
+  CUDA_OK(cudaMemcpyAsync(d.upperTrue, wUpper.data(), sizeof(double) * nm, cudaMemcpyHostToDevice, stream));
+  CUDA_OK(cudaMemsetAsync(&d.st->stop, 0, sizeof(int), stream));
+  CUDA_OK(cudaMemsetAsync(d.flagged, 0, m, stream));
+  CUDA_OK(cudaMemsetAsync(&d.st->numFlagged, 0, sizeof(int), stream));
+  setAcceptablePivot(acceptablePivot);
+  currentDualBound = dualBound;
+  CUDA_OK(cudaMemsetAsync(dCounters, 0, sizeof(int) * 4, stream));
+  launch_make_dual_feasible(d, currentDualBound, dCounters, stream);
+  launch_compute_primals(d, dXn, dRhs, stream, true);
+  kernelLaunches += 12;
+  CUDA_OK(cudaStreamSynchronize(stream));
+  return 0;
+}
+
 int Engine::startup()
 {
   setupDevice();
@@ -1096,7 +1161,8 @@ int Engine::dual()
   phase = PhaseTimes();
   if (m == 0 || n == 0)
     return trivialSolve();
-  if (startup() != 0) {
+  lastSolveWasHot = hotStart && deviceReady && factorsValid;
+  if ((lastSolveWasHot ? hotPrepare() : startup()) != 0) {
     problemStatus = 4;
     return problemStatus;
   }

@@ -174,6 +174,7 @@ struct DeviceModel {
   // with a fixed per-rank chunk (shardPerK / shardPerM entries per vector) that ONE in-place
   // all-gather per solve completes.  shardW == 1: plain single-GPU layout.
   int shardW, shardRank, shardPerK, shardPerM;
+  int dantzig;    // 1: ClpDualRowDantzig (largest infeasibility, weights ignored and left alone); 0: dual steepest edge
   int shardPanel; // 1: the eta panel is row-sharded too (pays only when 8*m*t bytes outweigh one more all-gather)
   double *gatherY; // [W][3][shardPerK]  FTRAN GEMV results
   double *gatherB; // [W][shardPerK]     BTRAN GEMV results

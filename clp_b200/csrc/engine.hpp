@@ -42,6 +42,9 @@ public:
   double maximumSeconds = 1.0e30;
   int factorizationFrequency = 0; // 0 = default formula
   int logLevel = 0;
+  // ClpSimplex::setDualRowPivotAlgorithm (src/ClpSimplex.cpp:4985): 0 ClpDualRowSteepest (default),
+  // 1 ClpDualRowDantzig (src/ClpDualRowDantzig.cpp:56 pivotRow: largest primal infeasibility)
+  int dualRowPivot = 0;
   int batch = 16;                 // iterations enqueued per host synchronisation
   int refreshDualsEvery = 0, refreshPrimalsEvery = 0; // experiments: recompute from scratch inside a cycle
   bool timing = false;
@@ -81,6 +84,16 @@ public:
 
   // ---- solve (ClpSimplex::dual) ----
   int dual();
+  // Hot start for branch-and-bound style callers (ClpSimplexDual::fastDual, src/ClpSimplexDual.cpp:7241;
+  // strongBranching :6965): with hotStart set, a dual() that follows a solve of the SAME model whose
+  // bounds were changed through chgColumnLower/Upper / chgRowLower/Upper (Clp_chgColumnLower ...,
+  // src/Clp_C_Interface.h:150-156) keeps the device-resident factors, eta file, weights, duals and
+  // status: it only re-imposes the bounds, moves nonbasic variables to them, recomputes x_B through
+  // the existing factors and iterates -- no upload, no refactorization at the start.
+  bool hotStart = false;
+  void chgBounds(const double *columnLower, const double *columnUpper, const double *rowLower,
+                 const double *rowUpper); // NULL = unchanged
+  bool lastSolveWasHot = false;
   int problemStatus = -1;
   int numberIterations = 0, numberRefactorizations = 0;
   double objectiveValue = 0.0, sumPrimalInfeasibilities = 0.0;
@@ -147,6 +160,9 @@ private:
   DeviceModel d{};
   cudaStream_t stream = nullptr;
   bool deviceReady = false;
+  bool factorsValid = false; // a factorization of the current device basis exists
+  void boundsToWorking();    // hLower/hUpper -> wLower/wUpper with the scale factors in force
+  int hotPrepare();
   long long readySignature = -1;
   int trivialSolve(); // m == 0 or n == 0 (a presolved model can be empty): host only
   bool haveUserStatus = false;

@@ -41,7 +41,7 @@ __global__ void chuzr_kernel(DeviceModel d)
   for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < d.m; p += gridDim.x * blockDim.x) {
     const int seq = d.pivotVariable[p];
     if (!d.flagged[p])
-      best = max(best, chuzr_key(d.sol[seq], d.lower[seq], d.upper[seq], d.weights[p], tol, p));
+      best = max(best, chuzr_key(d.sol[seq], d.lower[seq], d.upper[seq], d.dantzig ? 1.0 : d.weights[p], tol, p));
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1)
@@ -403,8 +403,8 @@ __global__ void __launch_bounds__(256) iteration_update_kernel(DeviceModel d, in
           x += d.rhs3[(size_t)2 * d.m + p];
         x -= st->thetaPrimal * a;
         d.sol[seq] = x;
-        double w = d.weights[p];
-        if (a != 0.0) {
+        double w = d.dantzig ? 1.0 : d.weights[p];
+        if (a != 0.0 && !d.dantzig) {
           // w_i += (a_i/a_r) * ((a_i/a_r) * w_r - 2 tau_i)   clipped at DEVEX_TRY_NORM
           const double ratio = a / alphaR;
           w += ratio * (ratio * st->rhoNorm2 - 2.0 * d.rhs3[(size_t)d.m + p]);
@@ -416,7 +416,10 @@ __global__ void __launch_bounds__(256) iteration_update_kernel(DeviceModel d, in
       } else {
         double w = st->rhoNorm2 / (alphaR * alphaR);
         w = w < kDevexTryNorm ? kDevexTryNorm : w;
-        d.weights[p] = w;
+        if (d.dantzig)
+          w = 1.0;
+        else
+          d.weights[p] = w;
         const int q = st->seqIn; // becomes basic at this position (housekeeping in the tail)
         d.flagged[p] = 0; // a new variable at this position
         best = chuzr_key(d.sol[q] + st->thetaPrimal, d.lowerTrue[q], d.upperTrue[q], w, d.primalTolerance, p);

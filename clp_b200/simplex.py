@@ -182,6 +182,20 @@ class ClpSimplex:
         return self._L.Clpb_readBasis(self._h, str(fileName).encode())
 
     # ---- ClpSimplex::dual ----
+    def chgColumnLower(self, v): self._L.Clpb_chgColumnLower(self._h, _dp(np.ascontiguousarray(v, dtype=np.float64)))
+    def chgColumnUpper(self, v): self._L.Clpb_chgColumnUpper(self._h, _dp(np.ascontiguousarray(v, dtype=np.float64)))
+    def chgRowLower(self, v): self._L.Clpb_chgRowLower(self._h, _dp(np.ascontiguousarray(v, dtype=np.float64)))
+    def chgRowUpper(self, v): self._L.Clpb_chgRowUpper(self._h, _dp(np.ascontiguousarray(v, dtype=np.float64)))
+    def lastSolveWasHot(self): return bool(self._L.Clpb_lastSolveWasHot(self._h))
+
+    def fastDual(self):
+        """ClpSimplexDual::fastDual: dual() that keeps the device-resident factors of the previous solve"""
+        self._set("hotStart", 1)
+        try:
+            return self.dual()
+        finally:
+            self._set("hotStart", 0)
+
     def dual(self, ifValuesPass=0):
         rc = self._L.Clpb_dual(self._h, int(ifValuesPass))
         if rc == _capi.NO_DEVICE:

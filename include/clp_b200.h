@@ -87,6 +87,17 @@ void Clpb_copyinStatus(Clpb_Simplex *model, const unsigned char *statusArray);
    becomes the starting basis of the next Clpb_dual (like Clpb_copyinStatus).  Host only. */
 int Clpb_writeBasis(Clpb_Simplex *model, const char *filename, int writeValues, int formatType);
 int Clpb_readBasis(Clpb_Simplex *model, const char *filename);
+/* Clp_chgRowLower :150, Clp_chgRowUpper :152, Clp_chgColumnLower :154, Clp_chgColumnUpper :156: replace a
+   whole bound vector of the loaded model.  With the key "hotStart" = 1 (Clpb_setParameter) the next
+   Clpb_dual on the same model is the reference's hot start (ClpSimplexDual::fastDual
+   src/ClpSimplexDual.cpp:7241, the inner solve of strongBranching :6965): factors, eta file, weights,
+   duals and status stay on the device, only the bounds are re-imposed and x_B recomputed -- no upload,
+   no refactorization at the start.  Clpb_lastSolveWasHot tells whether the last Clpb_dual took that path. */
+void Clpb_chgColumnLower(Clpb_Simplex *model, const double *columnLower);
+void Clpb_chgColumnUpper(Clpb_Simplex *model, const double *columnUpper);
+void Clpb_chgRowLower(Clpb_Simplex *model, const double *rowLower);
+void Clpb_chgRowUpper(Clpb_Simplex *model, const double *rowUpper);
+int Clpb_lastSolveWasHot(Clpb_Simplex *model);
 /* Clp_dual :346 (ClpSimplex::dual src/ClpSimplex.cpp:5631).  Returns Clp_status :212:
    0 optimal, 1 primal infeasible, 2 dual infeasible, 3 stopped on iterations/time,
    4 stopped due to errors. */

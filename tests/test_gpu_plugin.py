@@ -212,3 +212,54 @@ def test_ft_entry_points_and_replace_column_codes():
         assert rc == 0
         done += 1
     assert done == 8
+
+
+@pytest.mark.parametrize("name", ["UFL-20x60", "TSP-MTZ-40", "staircase-480"])
+def test_dantzig_row_pivot_reaches_the_same_optimum(name):
+    """ClpDualRowDantzig (largest infeasibility) instead of dual steepest edge: another path, same optimum"""
+    import os
+    from conftest import load_golden
+
+    lp = load_golden(name)
+    s = engine(lp, dualRowPivot=1)
+    assert s.dual() == 0
+    assert abs(s.objectiveValue() - lp.known_objective) <= 1e-6 * (1 + abs(lp.known_objective))
+    assert O.kkt_violations(lp, s.primalColumnSolution(), s.primalRowSolution(), s.dualColumnSolution()) == 0
+    w = s.weights()
+    assert np.all(w == 1.0)          # the steepest-edge weights are left alone in this mode
+
+
+def test_hot_start_after_bound_changes_matches_a_cold_solve():
+    """branching-style re-solves: tighten column bounds, fastDual() keeps the device-resident factors
+    (no upload, no refactorization at the start) and must end at the optimum a cold solve of the modified
+    LP finds (cross-checked with the CPU oracle)"""
+    lp = G.random_sparse_lp(400, 4000, 0.02, 77)
+    s = engine(lp)
+    assert s.dual() == 0
+    x = s.primalColumnSolution()
+    frac = np.nonzero((x > 0.05) & (x < 0.95))[0]
+    assert len(frac) >= 6
+    up = lp.col_upper.copy(); lo = lp.col_lower.copy()
+    total_hot = 0
+    for round_, j in enumerate(frac[:6]):
+        if round_ % 2 == 0:
+            up[j] = 0.0          # "down branch"
+            s.chgColumnUpper(up)
+        else:
+            lo[j] = 1.0          # "up branch"
+            s.chgColumnLower(lo)
+        st = s.fastDual()
+        assert s.lastSolveWasHot()
+        total_hot += s.numberIterations()
+        mod = G.LP(lp.name, lp.m, lp.n, lp.col_start, lp.row_index, lp.element, lo.copy(), up.copy(),
+                   lp.objective, lp.row_lower, lp.row_upper)
+        o = O.OracleSimplex(mod)
+        ost = o.dual()
+        assert st == ost
+        if st == 0:
+            assert abs(s.objectiveValue() - o.objective_value) <= 1e-8 * (1 + abs(o.objective_value))
+            assert O.kkt_violations(mod, s.primalColumnSolution(), s.primalRowSolution(), s.dualColumnSolution()) == 0
+    cold = engine(mod)
+    assert cold.dual() == st
+    # the hot re-solves together need far fewer iterations than one cold solve of the last LP
+    assert total_hot < cold.numberIterations()
