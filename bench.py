@@ -328,13 +328,15 @@ def main():
 
     def new_model(**params):
         s = clp_b200.ClpSimplex()
-        s.loadLP(lp)
-        if status is not None and not params.pop("_from_slack", False):
+        model_lp = params.pop("_lp", None)
+        s.loadLP(model_lp if model_lp is not None else lp)
+        if model_lp is None and status is not None and not params.pop("_from_slack", False):
             s.copyinStatus(status)
         params.pop("_from_slack", None)
+        single = params.pop("_single", False)
         for k, v in params.items():
             s.setParameter(k, v)
-        if world > 1:
+        if world > 1 and not single:
             from clp_b200.sharding import broadcast_unique_id
 
             uid = clp_b200.ClpSimplex.ncclUniqueId() if rank == 0 else np.zeros(128, dtype=np.uint8)
@@ -404,6 +406,34 @@ def main():
                                                       "speedup_vs_n1": value / r1["value"] if r1["value"] else None}
             except Exception:
                 pass
+
+    if world > 1:
+        # ---------------- parity of the sharded path inside the scaling run itself: a small LP of the same
+        # family solved (a) by all ranks with every shard forced on (pricing columns, GEMV rows, eta panel
+        # rows, inverse columns) and (b) by rank 0 alone on one GPU; all ranks must take the same pivots and
+        # both must end at the planted optimum
+        from clp_b200 import generators as G
+
+        plp = G.random_sparse_lp(1500, 20000, 0.01, 31, name="rand-1500x20000")
+        a = new_model(_lp=plp, shardMinNnzPerRank=0, shardPanel=1)
+        ast = a.dual()
+        mine = {"rank": rank, "status": ast, "objective": a.objectiveValue(), "iterations": a.numberIterations()}
+        everyone = [None] * world
+        dist.all_gather_object(everyone, mine)
+        if rank == 0:
+            b1 = new_model(_lp=plp, _single=True)
+            bst = b1.dual()
+            tol = 1e-8 * (1.0 + abs(plp.known_objective))
+            result["sharded_parity"] = {
+                "workload": plp.name, "ranks": everyone,
+                "ranks_identical": all(e["objective"] == everyone[0]["objective"] and e["iterations"] == everyone[0]["iterations"]
+                                       and e["status"] == everyone[0]["status"] for e in everyone),
+                "single_gpu": {"status": bst, "objective": b1.objectiveValue(), "iterations": b1.numberIterations()},
+                "planted_objective": plp.known_objective,
+                "ok": bool(ast == 0 and bst == 0 and abs(everyone[0]["objective"] - plp.known_objective) <= tol
+                           and abs(b1.objectiveValue() - plp.known_objective) <= tol)}
+            del b1
+        del a
 
     if rank == 0 and world == 1:
         # ---------------- per-kernel timing (CUDA events around single kernels, no graph replay)

@@ -25,3 +25,24 @@ def broadcast_unique_id(uid: np.ndarray, src: int = 0) -> np.ndarray:
         t = t.cuda()
     dist.broadcast(t, src=src)
     return t.cpu().numpy()
+
+
+def round_up8(v: int) -> int:
+    return (v + 7) // 8 * 8
+
+
+def factor_row_range(k: int, rank: int, world: int):
+    """Rows of the nucleus inverse rank `rank` streams (gemv_rows_kernel in solve.cu): contiguous blocks
+    of per_k = roundUp8(ceil(k / world)) rows; k is the CURRENT nucleus size."""
+    per_k = round_up8((k + world - 1) // world)
+    lo = min(k, rank * per_k)
+    return lo, min(k, lo + per_k), per_k
+
+
+def gather_slot(i: int, c: int, k: int, world: int, nrhs: int, per_max: int) -> int:
+    """Index of GEMV result (row i, right-hand side c) in the gathered buffer [rank][rhs][per_max]
+    (gemv_result / btran_scatter_kernel in solve.cu); per_max = roundUp8(ceil(m / world)) is fixed for the
+    whole solve so that the all-gather size does not depend on the nucleus size."""
+    per_k = round_up8((k + world - 1) // world)
+    rk = i // per_k
+    return (rk * nrhs + c) * per_max + (i - rk * per_k)

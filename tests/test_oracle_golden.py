@@ -464,3 +464,50 @@ print("ok", rank)
         out, err = p.communicate(timeout=120)
         assert p.returncode == 0, err
         assert "ok" in out
+
+
+def test_two_rank_row_sharded_gemv_protocol():
+    """world_size=2 over gloo: the row-sharded FTRAN GEMV of the multi-GPU path -- every rank computes its
+    block of rows of y = Ninv b for three right-hand sides into its chunk of the [rank][rhs][perMax] buffer,
+    ONE all-gather of fixed-size chunks completes it, and gather_slot() finds every entry (the index math
+    of gemv_rows_kernel / gemv_result in solve.cu restated in clp_b200/sharding.py), for nucleus sizes that
+    are not multiples of anything."""
+    code = r"""
+import os, sys
+sys.path.insert(0, %r)
+import numpy as np, torch, torch.distributed as dist
+from clp_b200.sharding import factor_row_range, gather_slot, round_up8
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%%s" %% os.environ["PORT"],
+                        rank=int(os.environ["RANK"]), world_size=2)
+rank, world = dist.get_rank(), 2
+m, nrhs = 203, 3
+per_max = round_up8((m + world - 1) // world)
+rng = np.random.default_rng(11)
+for k in (1, 7, 8, 9, 100, 101, 203):
+    Ninv = rng.standard_normal((k, k)); b = rng.standard_normal((nrhs, k))
+    lo, hi, per_k = factor_row_range(k, rank, world)
+    assert per_k <= per_max
+    chunk = np.zeros(nrhs * per_max)
+    for c in range(nrhs):
+        chunk[c * per_max: c * per_max + (hi - lo)] = Ninv[lo:hi] @ b[c]
+    parts = [torch.zeros(nrhs * per_max, dtype=torch.float64) for _ in range(world)]
+    dist.all_gather(parts, torch.from_numpy(chunk))
+    gathered = np.concatenate([p.numpy() for p in parts])
+    for c in range(nrhs):
+        y = np.array([gathered[gather_slot(i, c, k, world, nrhs, per_max)] for i in range(k)])
+        assert np.array_equal(y, np.concatenate([Ninv[:min(k, per_k)] @ b[c], Ninv[min(k, per_k):] @ b[c]]))
+dist.destroy_process_group()
+print("ok", rank)
+""" % ROOT
+    import socket
+
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), PORT=str(port))
+        procs.append(subprocess.Popen([sys.executable, "-c", code], env=env, stdout=subprocess.PIPE,
+                                      stderr=subprocess.PIPE, text=True))
+    for p in procs:
+        out, err = p.communicate(timeout=120)
+        assert p.returncode == 0, err
+        assert "ok" in out
