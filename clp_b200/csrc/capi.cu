@@ -224,6 +224,14 @@ int Clpb_setParameter(Clpb_Simplex *model, const char *key, double value)
     e.useRowPass = value != 0.0;
   else if (k == "pfiApplyVariant")
     clpb::g_pfiApplyVariant = (int)value;
+  else if (k == "priceIdx16")
+    clpb::g_priceIdx16 = (int)value;
+  else if (k == "gemvVariantF")
+    clpb::g_gemvVariantF = (int)value;
+  else if (k == "gemvVariantB")
+    clpb::g_gemvVariantB = (int)value;
+  else if (k == "gemvGridMul")
+    clpb::g_gemvGridMul = std::max(1, (int)value);
   else if (k == "objectiveOffset")
     e.objectiveOffset = value;
   else if (k == "scaling")

@@ -295,6 +295,15 @@ int Engine::setupDevice()
   CUDA_OK(cudaMemset(p, 0, sizeof(int) * (nnz + 16)));
   CUDA_OK(cudaMemcpy(p, hRow.data(), sizeof(int) * nnz, cudaMemcpyHostToDevice));
   d.rowIdx = p;
+  d.rowIdx16 = nullptr;
+  if (m <= 65535) {
+    std::vector<unsigned short> r16((size_t)nnz + 32, 0);
+    for (long long e = 0; e < nnz; e++)
+      r16[e] = (unsigned short)hRow[e];
+    unsigned short *p16 = dalloc<unsigned short>(nnz + 32);
+    CUDA_OK(cudaMemcpy(p16, r16.data(), sizeof(unsigned short) * (nnz + 32), cudaMemcpyHostToDevice));
+    d.rowIdx16 = p16;
+  }
   q = dalloc<double>(nnz + 16);
   CUDA_OK(cudaMemset(q, 0, sizeof(double) * (nnz + 16)));
   CUDA_OK(cudaMemcpy(q, wVal.data(), sizeof(double) * nnz, cudaMemcpyHostToDevice));

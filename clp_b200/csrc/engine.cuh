@@ -105,6 +105,7 @@ struct DeviceModel {
   // column copy (CSC) and row copy (CSR) of A
   const int *colStart;
   const int *rowIdx;
+  const unsigned short *rowIdx16; // the same row indices in 16 bits when m <= 65535 (PRICE streams these), else nullptr
   const double *val;
   const int *rowStart;
   const int *colIdx;
@@ -188,6 +189,8 @@ struct KernelTimers {
 };
 extern KernelTimers *g_kernelTimers; // nullptr outside timing mode (engine.cu)
 extern int g_pfiApplyVariant;         // solve.cu
+extern int g_priceIdx16;              // price.cu
+extern int g_gemvVariantF, g_gemvVariantB, g_gemvGridMul; // solve.cu (launch-shape experiments)
 // collectives of a sharded run (host side; set by Engine before it enqueues work)
 struct ShardCtx {
   int W = 1, rank = 0;

@@ -35,7 +35,8 @@ __device__ __forceinline__ void histogram_add(const DeviceModel &d, double a, do
 // entries): 26.6 us = 4.5 TB/s, against 36 us for every variant that stages the CSC tiles through
 // shared memory with cp.async.bulk (TMA) -- those are bound by shared-memory wavefronts (TMA
 // writes + index/value reads + rho gathers), not by HBM.
-template <int THREADS, int CTAS, bool SMEM_RHO>
+// IDX16: row indices are read from the 16-bit copy (m <= 65535): 10 instead of 12 bytes per entry.
+template <int THREADS, int CTAS, bool SMEM_RHO, bool IDX16 = false>
 __global__ void __launch_bounds__(THREADS, CTAS)
     price_ldg_kernel(DeviceModel d, int colBegin, int colEnd)
 {
@@ -50,6 +51,7 @@ __global__ void __launch_bounds__(THREADS, CTAS)
     __syncthreads();
   }
   const int *__restrict__ rowIdx = d.rowIdx;
+  const unsigned short *__restrict__ rowIdx16 = d.rowIdx16;
   const double *__restrict__ val = d.val;
   const int *__restrict__ colStart = d.colStart;
   const unsigned char *__restrict__ status = d.status;
@@ -74,7 +76,7 @@ __global__ void __launch_bounds__(THREADS, CTAS)
     for (int u = 0; u < 4; u++) {
       const int e = b0 + lane + 32 * u;
       const bool p = e < b1;
-      ni[u] = p ? __ldcs(rowIdx + e) : 0;
+      ni[u] = p ? (IDX16 ? (int)__ldcs(rowIdx16 + e) : __ldcs(rowIdx + e)) : 0;
       nv[u] = p ? __ldcs(val + e) : 0.0;
     }
   };
@@ -101,7 +103,7 @@ __global__ void __launch_bounds__(THREADS, CTAS)
     acc0 = fma(cv[2], SMEM_RHO ? srho[ci[2]] : __ldg(rhoG + ci[2]), acc0);
     acc1 = fma(cv[3], SMEM_RHO ? srho[ci[3]] : __ldg(rhoG + ci[3]), acc1);
     for (int e = cb0 + 128 + lane; e < cb1; e += 32) { // columns longer than 128 entries
-      const int r = __ldg(rowIdx + e);
+      const int r = IDX16 ? (int)__ldg(rowIdx16 + e) : __ldg(rowIdx + e);
       acc0 = fma(__ldg(val + e), SMEM_RHO ? srho[r] : __ldg(rhoG + r), acc0);
     }
     const double acc = warp_sum(acc0 + acc1);
@@ -316,6 +318,8 @@ void launch_histogram(const DeviceModel &d, cudaStream_t s)
   histogram_kernel<<<blocks, 256, 0, s>>>(d);
 }
 
+int g_priceIdx16 = 1; // "priceIdx16": 0 forces the 32-bit index stream (A/B)
+
 void launch_price(const DeviceModel &d, int colBegin, int colEnd, bool fuseHist, cudaStream_t s)
 {
   (void)fuseHist; // both kernels leave raw dot products; the histogram is built by the row kernels
@@ -329,6 +333,8 @@ void launch_price(const DeviceModel &d, int colBegin, int colEnd, bool fuseHist,
     cudaFuncSetAttribute(price_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     cudaFuncSetAttribute(price_ldg_kernel<640, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
     cudaFuncSetAttribute(price_ldg_kernel<1024, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+    cudaFuncSetAttribute(price_ldg_kernel<640, 2, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
+    cudaFuncSetAttribute(price_ldg_kernel<1024, 1, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
     attrSet = true;
   }
   static int numSMs = 0;
@@ -357,6 +363,14 @@ void launch_price(const DeviceModel &d, int colBegin, int colEnd, bool fuseHist,
       price_tma_kernel<true><<<gridTma, 1024, tileBytes + rhoBytes, s>>>(d, desc, d.numPriceTiles, descCap);
     else
       price_tma_kernel<false><<<gridTma, 1024, tileBytes, s>>>(d, desc, d.numPriceTiles, descCap);
+  } else if (d.rowIdx16 != nullptr && g_priceIdx16) {
+    // 16-bit row indices (m <= 65535): 10 bytes per entry streamed instead of 12
+    if (rhoBytes <= 112 * 1024)
+      price_ldg_kernel<640, 2, true, true><<<numSMs * 2, 640, rhoBytes, s>>>(d, colBegin, colEnd);
+    else if (rhoBytes <= 224 * 1024)
+      price_ldg_kernel<1024, 1, true, true><<<numSMs, 1024, rhoBytes, s>>>(d, colBegin, colEnd);
+    else
+      price_ldg_kernel<640, 2, false, true><<<numSMs * 2, 640, 0, s>>>(d, colBegin, colEnd);
   } else if (rhoBytes <= 112 * 1024) {
     price_ldg_kernel<640, 2, true><<<numSMs * 2, 640, rhoBytes, s>>>(d, colBegin, colEnd);
   } else if (rhoBytes <= 224 * 1024) {

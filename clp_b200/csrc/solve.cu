@@ -22,6 +22,8 @@ namespace clpb {
 static inline int roundUp8(int v) { return (v + 7) / 8 * 8; }
 
 ShardCtx g_shardCtx;
+// launch-shape experiments (tests/ab_probe.py): rows per CTA pass / 16-byte loads in flight / CTAs per SM
+int g_gemvVariantF = 0, g_gemvVariantB = 0, g_gemvGridMul = 8;
 int g_pfiApplyVariant = 0; // 0: warp per panel row, 1: GEMV-shaped (two rows per CTA); "pfiApplyVariant"
 
 // ---------------------------------------------------------------------------------------
@@ -135,6 +137,56 @@ __global__ void __launch_bounds__(256)
       }
     }
     __syncthreads();
+  }
+}
+
+// Same product with one WARP per row (no block-level reduction, no __syncthreads): lanes stride the row
+// in 16-byte pieces, DEPTH loads per lane in flight.  Launch-shape experiment (gemvVariantF = 7 /
+// gemvVariantB = 6); not sharded.
+template <int NRHS, int DEPTH>
+__global__ void __launch_bounds__(256)
+    gemv_warp_rows_kernel(const FactorDesc *__restrict__ fd, int transposed, const double *__restrict__ x,
+                          double *__restrict__ out, int ostride, const int *__restrict__ outIndex,
+                          const IterState *st, bool checkState)
+{
+  if (checkState && !iter_active(st))
+    return;
+  const int k = fd->k, ldk = fd->ldk;
+  const double *__restrict__ M = transposed ? fd->NinvT : fd->Ninv;
+  const int lane = threadIdx.x & 31;
+  const int half = ldk >> 1;
+  const int warpsTotal = gridDim.x * (blockDim.x >> 5);
+  for (int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < k; i += warpsTotal) {
+    const double2 *row = reinterpret_cast<const double2 *>(M + (size_t)i * ldk);
+    double acc[NRHS];
+#pragma unroll
+    for (int c = 0; c < NRHS; c++)
+      acc[c] = 0.0;
+    for (int j = lane; j < half; j += 32 * DEPTH) {
+      double2 a[DEPTH];
+#pragma unroll
+      for (int u = 0; u < DEPTH; u++)
+        a[u] = j + 32 * u < half ? __ldcs(row + j + 32 * u) : make_double2(0.0, 0.0);
+#pragma unroll
+      for (int u = 0; u < DEPTH; u++) {
+        const int jj = min(j + 32 * u, half - 1);
+#pragma unroll
+        for (int c = 0; c < NRHS; c++) {
+          const double2 xv = __ldg(reinterpret_cast<const double2 *>(x + (size_t)c * ldk) + jj);
+          acc[c] = fma(a[u].x, xv.x, acc[c]);
+          acc[c] = fma(a[u].y, xv.y, acc[c]);
+        }
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < NRHS; c++) {
+      const double v = warp_sum(acc[c]);
+      if (lane == 0) {
+        const int o = outIndex ? outIndex[i] : i;
+        const int os = ostride < 0 ? ldk : ostride;
+        out[(size_t)c * os + o] = v;
+      }
+    }
   }
 }
 
@@ -467,17 +519,35 @@ static void ftran_impl(const DeviceModel &d, double *b, bool applyEtas, bool che
   double *xg = d.ywork + (size_t)3 * roundUp8(maxk);
   if (!pregathered) // the row pass (rowpass.cu) writes xg together with the right-hand sides
     gather_nucleus_kernel<<<gblocks, 256, 0, s>>>(d, b, m, xg, NRHS, checkState);
-  int blocks = maxk < 148 * 8 ? maxk : 148 * 8;
+  int blocks = maxk < 148 * g_gemvGridMul ? maxk : 148 * g_gemvGridMul;
   if (g_kernelTimers && checkState)
     cudaEventRecord(g_kernelTimers->ftranGemv[0], s);
   const bool sharded = d.shardW > 1;
   double *y = sharded ? d.gatherY : d.ywork;
+#define CLPB_GEMV_F(R_, D_)                                                                                   \
+  gemv_rows_kernel<NRHS, R_, D_><<<blocks, 256, 0, s>>>(d.fd, 0, xg, y, -1, nullptr, d.st, checkState, d.shardW, \
+                                                        d.shardRank, d.shardPerK)
   if (NRHS == 1)
-    gemv_rows_kernel<NRHS, 1, 8><<<blocks, 256, 0, s>>>(d.fd, 0, xg, y, -1, nullptr, d.st, checkState,
-                                                        d.shardW, d.shardRank, d.shardPerK);
+    CLPB_GEMV_F(1, 8);
+  else if (g_gemvVariantF == 1)
+    CLPB_GEMV_F(1, 4);
+  else if (g_gemvVariantF == 2)
+    CLPB_GEMV_F(1, 8);
+  else if (g_gemvVariantF == 3)
+    CLPB_GEMV_F(2, 4);
+  else if (g_gemvVariantF == 4)
+    CLPB_GEMV_F(4, 1);
+  else if (g_gemvVariantF == 5)
+    CLPB_GEMV_F(4, 2);
+  else if (g_gemvVariantF == 6)
+    CLPB_GEMV_F(1, 2);
+  else if (g_gemvVariantF == 7 && !sharded)
+    gemv_warp_rows_kernel<NRHS, 4><<<148 * g_gemvGridMul, 256, 0, s>>>(d.fd, 0, xg, y, -1, nullptr, d.st, checkState);
+  else if (g_gemvVariantF == 8 && !sharded)
+    gemv_warp_rows_kernel<NRHS, 8><<<148 * g_gemvGridMul, 256, 0, s>>>(d.fd, 0, xg, y, -1, nullptr, d.st, checkState);
   else
-    gemv_rows_kernel<NRHS, 2, 2><<<blocks, 256, 0, s>>>(d.fd, 0, xg, y, -1, nullptr, d.st, checkState,
-                                                        d.shardW, d.shardRank, d.shardPerK);
+    CLPB_GEMV_F(2, 2);
+#undef CLPB_GEMV_F
   if (g_kernelTimers && checkState)
     cudaEventRecord(g_kernelTimers->ftranGemv[1], s);
   if (sharded)
@@ -688,12 +758,30 @@ static void btran_tail(const DeviceModel &d, double *rhoOut, bool checkState, cu
 
 static void btran_gemv(const DeviceModel &d, double *rhoOut, bool checkState, cudaStream_t s)
 {
-  int blocks = d.m < 148 * 8 ? d.m : 148 * 8;
+  int blocks = d.m < 148 * g_gemvGridMul ? d.m : 148 * g_gemvGridMul;
   if (g_kernelTimers && checkState)
     cudaEventRecord(g_kernelTimers->btranGemv[0], s);
   const bool sharded = d.shardW > 1;
-  gemv_rows_kernel<1, 1, 8><<<blocks, 256, 0, s>>>(d.fd, 1, d.swork, sharded ? d.gatherB : rhoOut, d.m,
-                                                   d.nucRow, d.st, checkState, d.shardW, d.shardRank, d.shardPerK);
+#define CLPB_GEMV_B(R_, D_)                                                                              \
+  gemv_rows_kernel<1, R_, D_><<<blocks, 256, 0, s>>>(d.fd, 1, d.swork, sharded ? d.gatherB : rhoOut, d.m, \
+                                                     d.nucRow, d.st, checkState, d.shardW, d.shardRank, d.shardPerK)
+  if (g_gemvVariantB == 1)
+    CLPB_GEMV_B(1, 4);
+  else if (g_gemvVariantB == 2)
+    CLPB_GEMV_B(2, 4);
+  else if (g_gemvVariantB == 3)
+    CLPB_GEMV_B(2, 8);
+  else if (g_gemvVariantB == 4)
+    CLPB_GEMV_B(4, 4);
+  else if (g_gemvVariantB == 5)
+    CLPB_GEMV_B(4, 2);
+  else if (g_gemvVariantB == 6 && !sharded)
+    gemv_warp_rows_kernel<1, 8><<<148 * g_gemvGridMul, 256, 0, s>>>(d.fd, 1, d.swork, rhoOut, d.m, d.nucRow, d.st, checkState);
+  else if (g_gemvVariantB == 7 && !sharded)
+    gemv_warp_rows_kernel<1, 4><<<148 * g_gemvGridMul, 256, 0, s>>>(d.fd, 1, d.swork, rhoOut, d.m, d.nucRow, d.st, checkState);
+  else
+    CLPB_GEMV_B(1, 8);
+#undef CLPB_GEMV_B
   if (g_kernelTimers && checkState)
     cudaEventRecord(g_kernelTimers->btranGemv[1], s);
   if (sharded) {

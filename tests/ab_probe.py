@@ -18,4 +18,5 @@ for rep in range(2):
         ph = s.phaseTimes(); ns = max(1.0, ph["samples"])
         print(key, v, {k: round(1000.0 * ph[k] / ns, 1) for k in ("btran", "price", "chuzc", "ftran", "update")},
               "sum", round(1000.0 * sum(ph[k] for k in ("chuzr", "btran", "price", "chuzc", "dualUpdate", "ftran", "update")) / ns, 1),
+              "gemv_us", {q: round(1000.0 * ph[q] / ns, 2) for q in ("ftranGemv", "btranGemv", "priceKernel")},
               "refactor_ms", round(ph["refactor"], 1), flush=True)
