@@ -179,6 +179,7 @@ def oracle_sample(lp, status, cores, warm_iters, total_iters=None, seconds=None)
     if status is not None:
         o.set_status(status)
     o.set_option("threads", cores)
+    o.set_option("factorizationFrequency", clp_default_frequency(lp.m))  # the reference's own cadence
     o.set_option("warmupIterations", warm_iters)
     if total_iters is not None:
         o.set_option("maximumIterations", total_iters)

@@ -224,8 +224,10 @@ int Clpb_setParameter(Clpb_Simplex *model, const char *key, double value)
     e.useRowPass = value != 0.0;
   else if (k == "pfiApplyVariant")
     clpb::g_pfiApplyVariant = (int)value;
+  else if (k == "rowPassCtas")
+    clpb::g_rowPassCtas = (int)value;
   else if (k == "priceIdx16")
-    clpb::g_priceIdx16 = (int)value;
+    e.priceIdx16 = value != 0.0;
   else if (k == "gemvVariantF")
     clpb::g_gemvVariantF = (int)value;
   else if (k == "gemvVariantB")

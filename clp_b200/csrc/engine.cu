@@ -264,7 +264,7 @@ int Engine::setupDevice()
   // rebuilds it instead of being silently ignored
   const long long signature = (long long)scalingFlag * 1000003ll + (long long)factorizationFrequency * 101ll +
                               (timing ? 7 : 0) + (long long)worldSize * 13ll + (long long)rank * 17ll +
-                              (usePriceTma ? 3 : 0) + (long long)factorMode * 29ll + (shardActive() ? 31 : 0) + (long long)(shardPanelMode + 1) * 37ll + (long long)dualRowPivot * 41ll;
+                              (usePriceTma ? 3 : 0) + (long long)factorMode * 29ll + (shardActive() ? 31 : 0) + (long long)(shardPanelMode + 1) * 37ll + (long long)dualRowPivot * 41ll + (priceIdx16 ? 43 : 0);
   if (deviceReady && signature == readySignature)
     return 0;
   if (deviceReady)
@@ -296,7 +296,7 @@ int Engine::setupDevice()
   CUDA_OK(cudaMemcpy(p, hRow.data(), sizeof(int) * nnz, cudaMemcpyHostToDevice));
   d.rowIdx = p;
   d.rowIdx16 = nullptr;
-  if (m <= 65535) {
+  if (m <= 65535 && priceIdx16) {
     std::vector<unsigned short> r16((size_t)nnz + 32, 0);
     for (long long e = 0; e < nnz; e++)
       r16[e] = (unsigned short)hRow[e];

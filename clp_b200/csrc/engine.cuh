@@ -190,6 +190,7 @@ struct KernelTimers {
 extern KernelTimers *g_kernelTimers; // nullptr outside timing mode (engine.cu)
 extern int g_pfiApplyVariant;         // solve.cu
 extern int g_priceIdx16;              // price.cu
+extern int g_rowPassCtas;             // rowpass.cu
 extern int g_gemvVariantF, g_gemvVariantB, g_gemvGridMul; // solve.cu (launch-shape experiments)
 // collectives of a sharded run (host side; set by Engine before it enqueues work)
 struct ShardCtx {

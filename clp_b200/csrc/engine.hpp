@@ -49,6 +49,9 @@ public:
   int refreshDualsEvery = 0, refreshPrimalsEvery = 0; // experiments: recompute from scratch inside a cycle
   bool timing = false;
   bool useGraph = true;
+  // 16-bit row indices for PRICE (m <= 65535): 10 instead of 12 bytes per entry.  Measured at C2: no
+  // gain (29.2 vs 29.3 us) -- the kernel is bound by the shared-memory gathers of rho, not by HBM -- so off
+  bool priceIdx16 = false;
   bool usePriceTma = false;       // TMA-staged price kernel (default: LDG-direct kernel, 26% faster)
   // 0 = choose per basis (block-banded nucleus when it pays), 1 = always the dense nucleus inverse,
   // 2 = always block-banded (tests)

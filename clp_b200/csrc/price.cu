@@ -318,7 +318,7 @@ void launch_histogram(const DeviceModel &d, cudaStream_t s)
   histogram_kernel<<<blocks, 256, 0, s>>>(d);
 }
 
-int g_priceIdx16 = 1; // "priceIdx16": 0 forces the 32-bit index stream (A/B)
+int g_priceIdx16 = 1; // use the 16-bit copy when the engine built one ("priceIdx16" = 1 before the first solve)
 
 void launch_price(const DeviceModel &d, int colBegin, int colEnd, bool fuseHist, cudaStream_t s)
 {

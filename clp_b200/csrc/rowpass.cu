@@ -587,6 +587,8 @@ __global__ void __launch_bounds__(1024, 1) row_pass_kernel(DeviceModel d)
 
 // Launch; returns false if the row is too long for the register-resident variant (caller falls
 // back to the separate kernels).
+int g_rowPassCtas = 0;
+
 bool launch_row_pass(const DeviceModel &d, cudaStream_t s)
 {
   static int numSMs = 0;
@@ -597,7 +599,11 @@ bool launch_row_pass(const DeviceModel &d, cudaStream_t s)
     if (numSMs <= 0)
       numSMs = 148;
   }
-  const long gthreads = (long)numSMs * 1024;
+  // "rowPassCtas" (A/B): fewer CTAs make the grid barriers cheaper but every thread owns more entries
+  int ctas = g_rowPassCtas > 0 ? (g_rowPassCtas < numSMs ? g_rowPassCtas : numSMs) : numSMs;
+  if (ctas < kHistBuckets / 1024)
+    ctas = kHistBuckets / 1024;
+  const long gthreads = (long)ctas * 1024;
   const int need = (int)((d.nm + gthreads - 1) / gthreads);
   if (need > 8 || numSMs < kHistBuckets / 1024)
     return false;
@@ -605,13 +611,13 @@ bool launch_row_pass(const DeviceModel &d, cudaStream_t s)
   void *args[] = {&dm};
   cudaError_t rc;
   if (need <= 1)
-    rc = cudaLaunchCooperativeKernel((void *)row_pass_kernel<1>, dim3(numSMs), dim3(1024), args, 0, s);
+    rc = cudaLaunchCooperativeKernel((void *)row_pass_kernel<1>, dim3(ctas), dim3(1024), args, 0, s);
   else if (need <= 2)
-    rc = cudaLaunchCooperativeKernel((void *)row_pass_kernel<2>, dim3(numSMs), dim3(1024), args, 0, s);
+    rc = cudaLaunchCooperativeKernel((void *)row_pass_kernel<2>, dim3(ctas), dim3(1024), args, 0, s);
   else if (need <= 4)
-    rc = cudaLaunchCooperativeKernel((void *)row_pass_kernel<4>, dim3(numSMs), dim3(1024), args, 0, s);
+    rc = cudaLaunchCooperativeKernel((void *)row_pass_kernel<4>, dim3(ctas), dim3(1024), args, 0, s);
   else
-    rc = cudaLaunchCooperativeKernel((void *)row_pass_kernel<8>, dim3(numSMs), dim3(1024), args, 0, s);
+    rc = cudaLaunchCooperativeKernel((void *)row_pass_kernel<8>, dim3(ctas), dim3(1024), args, 0, s);
   return rc == cudaSuccess;
 }
 
