@@ -491,15 +491,16 @@ def main():
                               "refactor_ms_total": ph["refactor"], "basic_structurals_at_start": nb}
         del p
         # ---------------- end to end through the C ABI with host buffers
+        # the problem is uploaded once per solve, so the copies are amortised over the K steps of the call
         t0 = time.perf_counter()
-        e = new_model(batch=args.batch, maximumIterations=min(K, 4) * step_its, factorizationFrequency=cycle)
+        e = new_model(batch=args.batch, maximumIterations=K * step_its, factorizationFrequency=cycle)
         e.dual()
         e.primalColumnSolution(); e.dualRowSolution(); e.statusArray(); e.objectiveValue()
         wall = time.perf_counter() - t0
         result["e2e"] = {"value": e.numberIterations() / wall, "unit": "iterations/s",
-                         "h2d_bytes_per_step": int(h2d / max(1, min(K, 4))), "d2h_bytes_per_step": int(d2h / max(1, min(K, 4))),
+                         "h2d_bytes_per_step": int(h2d / max(1, K)), "d2h_bytes_per_step": int(d2h / max(1, K)),
                          "includes": "Clpb_loadProblem (pageable host arrays -> HBM), basis hand-over, "
-                                     "Clpb_dual for min(K,4) steps, solution read-back", "wall_s": wall,
+                                     "Clpb_dual for K steps, solution read-back", "wall_s": wall,
                          "iterations": e.numberIterations()}
         del e
         # ---------------- wall-to-optimal (the other half of BASELINE.json's metric).  C2 itself approaches
