@@ -258,6 +258,26 @@ bool Engine::shardActive() const
   return (long long)hColStart[n] / worldSize >= shardMinNnzPerRank;
 }
 
+// Refactorization interval for a nucleus of size k under the default policy: the base interval (2x the
+// reference's default), stretched when the modelled cost of a refactorization -- 2k^3 flops at the ~18
+// TFLOP/s the rank-32/128 updates reach, plus ~3.5 us per panel column -- exceeds 35 % of the modelled cost
+// of the iterations of a cycle (two passes over the explicit inverse, one over A, ~110 us of latency-bound
+// kernels, at the ~4.4 TB/s the streams reach).  Capped at 2048 and by a 2 GB eta panel.
+int Engine::cycleFor(int k) const
+{
+  const int base = std::max(8, std::min(2 * defaultFactorizationFrequency(), 2048));
+  if (factorizationFrequency > 0)
+    return std::max(8, std::min(factorizationFrequency, 2048));
+  const double kk = (double)k;
+  const double refactorSeconds = 2.0 * kk * kk * kk / 1.8e13 + kk * 3.5e-6 + 5.0e-3;
+  const double nnz = hColStart.empty() ? 0.0 : (double)hColStart[n];
+  const double iterationSeconds = (16.0 * kk * kk + 12.0 * nnz) / 4.4e12 + 110.0e-6;
+  int cycle = (int)(refactorSeconds / (0.35 * iterationSeconds));
+  const int memoryCap = (int)std::min(2048.0, 2.0e9 / (8.0 * std::max(1, m)));
+  cycle = std::max(base, std::min(cycle, std::max(base, memoryCap)));
+  return cycle;
+}
+
 int Engine::setupDevice()
 {
   // what the device copy was built for: a later scaling() / factorizationFrequency / timing change
@@ -388,9 +408,15 @@ int Engine::setupDevice()
   // measures it) and the row choice degrades.  Twice the reference's own default
   // (ClpSimplex::defaultFactorizationFrequency) keeps the iteration quality of the reference's cadence
   // (profiles/README.md: cycle experiments) at half its refactorization count.
+  // ... except where the refactorization itself is the expensive part (staircase-like LPs whose nucleus is
+  // nearly all of the basis: 0.5 s per refactorization at k = 17 000): cycleFor(k) stretches the interval so
+  // that the modelled refactorization time stays below ~35 % of the modelled iteration time of a cycle.
+  // The model depends on the nucleus size only, so the decision is reproducible and identical on all ranks.
   tmax = factorizationFrequency > 0 ? factorizationFrequency : 2 * defaultFactorizationFrequency();
   tmax = std::max(8, std::min(tmax, 2048));
-  d.tmax = roundUp(tmax, 8);
+  currentCycle = tmax;
+  const int capacity = factorizationFrequency > 0 ? tmax : cycleFor(m);
+  d.tmax = roundUp(capacity, 8);
   d.W = dalloc<double>((size_t)m * d.tmax);
   d.etaPos = dalloc<int>(d.tmax);
   d.etaPrevSame = dalloc<int>(d.tmax);
@@ -836,6 +862,10 @@ int Engine::refactor()
 
 int Engine::refresh()
 {
+  struct CycleUpdate { // the interval in force follows the nucleus size of the factorization just made
+    Engine &e;
+    ~CycleUpdate() { e.currentCycle = std::min(e.cycleFor(e.d.k), e.d.tmax); }
+  } cycleUpdate{*this};
   // keep the recurrence-updated solution: its distance from the recomputed one is the accuracy monitor
   // of the update cycle (ClpSimplexDual::statusOfProblemInDual compares saved and recomputed values the
   // same way, src/ClpSimplexDual.cpp:5170-5195, and shortens the cycle through forceFactorization_)
@@ -1184,7 +1214,6 @@ int Engine::dual()
   int windowStartIteration = 0;
   timedMilliseconds = 0.0;
   timedIterations = 0;
-  const int maxPivots = d.tmax < tmax ? d.tmax : tmax;
   while (problemStatus < 0) {
     if (numberIterations >= maximumIterations) {
       problemStatus = 3;
@@ -1203,7 +1232,7 @@ int Engine::dual()
     }
     // enqueue a batch of iterations; kernels become no-ops once the device sets a stop reason
     fetchState();
-    int room = maxPivots - hState->numEtas;
+    int room = std::min(currentCycle, d.tmax) - hState->numEtas;
     if (room <= 0) {
       if (refresh() != 0) {
         problemStatus = 4;
@@ -1470,7 +1499,7 @@ int Engine::updateColumnTranspose(double *vec)
 int Engine::replaceColumn(int sequenceIn, int pivotRow)
 {
   fetchState();
-  if (hState->numEtas >= tmax)
+  if (hState->numEtas >= std::min(currentCycle, d.tmax))
     return 5; // maximum pivots reached (ClpFactorization.hpp:87)
   if (hState->numEtas >= d.tmax)
     return 3; // no room in the update buffers (:86)
@@ -1736,8 +1765,8 @@ int Engine::replaceColumnChecked(int sequenceIn, int pivotRow, double pivotCheck
 {
   fetchState();
   const int t = hState->numEtas;
-  if (t >= tmax)
-    return 5; // maximum pivots: the update buffers are sized for exactly that many, so
+  if (t >= std::min(currentCycle, d.tmax))
+    return 5; // maximum pivots reached (the update buffers hold at least that many), so
   if (t >= d.tmax)
     return 3; // "no room" (:86) can only be seen if the two limits are ever decoupled
   launch_unpack_column(d, sequenceIn, d.rhs3, stream);

@@ -210,6 +210,7 @@ private:
   void fetchState();
   void downloadSolution();
   int defaultFactorizationFrequency() const;
+  int cycleFor(int k) const;
   void resetStateForRun();
   void buildRowCopy(const std::vector<double> &val, std::vector<int> &rowStart,
                     std::vector<int> &colIdx, std::vector<double> &rval) const;
