@@ -862,9 +862,24 @@ int Engine::refactor()
 
 int Engine::refresh()
 {
-  struct CycleUpdate { // the interval in force follows the nucleus size of the factorization just made
+  struct CycleUpdate {
+    // The interval in force follows the nucleus size of the factorization just made (cost model) and
+    // the accuracy the last cycle actually had: when the recurrence-updated basic values agree with the
+    // recomputed ones to 1e-7 the cycle may run to the capacity of the update buffers (well-conditioned
+    // staircase bases: drift 1e-9, and SHORT cycles cost them iterations), when they drift beyond 1e-5 it
+    // falls back to the base interval.  Both inputs are device results that are identical on every rank.
     Engine &e;
-    ~CycleUpdate() { e.currentCycle = std::min(e.cycleFor(e.d.k), e.d.tmax); }
+    ~CycleUpdate()
+    {
+      int c = e.cycleFor(e.d.k);
+      if (e.factorizationFrequency <= 0 && e.driftMeasured) {
+        if (e.lastPrimalDrift < 1.0e-7)
+          c = e.d.tmax;
+        else if (e.lastPrimalDrift > 1.0e-5)
+          c = std::max(8, std::min(2 * e.defaultFactorizationFrequency(), 2048));
+      }
+      e.currentCycle = std::min(c, e.d.tmax);
+    }
   } cycleUpdate{*this};
   // keep the recurrence-updated solution: its distance from the recomputed one is the accuracy monitor
   // of the update cycle (ClpSimplexDual::statusOfProblemInDual compares saved and recomputed values the
@@ -887,6 +902,7 @@ int Engine::refresh()
     CUDA_OK(cudaMemcpyAsync(&bits, dDrift, sizeof(bits), cudaMemcpyDeviceToHost, stream));
     CUDA_OK(cudaStreamSynchronize(stream));
     memcpy(&lastPrimalDrift, &bits, sizeof(double));
+    driftMeasured = true;
   }
   if (logLevel > 0 && (logLevel > 1 || numberRefactorizations <= 60 || numberRefactorizations % 25 == 0)) {
     // progress line (the reference prints objective / infeasibilities at every refactorization)
@@ -1200,6 +1216,7 @@ int Engine::dual()
   phase = PhaseTimes();
   if (m == 0 || n == 0)
     return trivialSolve();
+  driftMeasured = false;
   lastSolveWasHot = hotStart && deviceReady && factorsValid;
   if ((lastSolveWasHot ? hotPrepare() : startup()) != 0) {
     problemStatus = 4;

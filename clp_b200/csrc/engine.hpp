@@ -176,6 +176,7 @@ private:
   double *dSolOld = nullptr;             // recurrence-updated solution kept across a refresh (drift measure)
   unsigned long long *dDrift = nullptr;
   double lastPrimalDrift = 0.0;          // relative, of the last refresh
+  bool driftMeasured = false;
   int currentCycle = 0;                  // refactorization interval in force (adapted from the drift)
   int *dSrcPos = nullptr, *dCounters = nullptr;
   unsigned char *dFlipFlag = nullptr;
