@@ -3,12 +3,16 @@
 // ClpPresolve::presolvedModel / postsolve (/root/reference/src/ClpPresolve.hpp:40,61) drive a list
 // of CoinPresolveAction objects that live in CoinUtils (not in the reference tree).  This file
 // restates the four elementary ones the driver always applies (src/ClpPresolve.cpp: make_fixed :966,
-// slack_doubleton_action :1141, drop_empty_cols_action :1448, drop_empty_rows_action :1449), iterated
-// to a fixed point:
+// slack_doubleton_action :1141, drop_empty_cols_action :1448, drop_empty_rows_action :1449) and the dual
+// fixing of remove_dual_action (:1158, :1296), iterated to a fixed point:
 //   F  fixed column (l == u)       : removed, row bounds shifted by -a_ij x_j, constant c_j x_j
 //   S  singleton row a_ij x_j      : becomes bounds on x_j, row removed
 //   C  empty column                : set to the bound its cost prefers (unbounded if that is infinite)
 //   R  empty row                   : removed (infeasible if 0 is outside its bounds)
+//   D  dominated column            : the sign restrictions of the row duals (pi_i >= 0 on a row with only a
+//                                    lower bound, <= 0 with only an upper bound, 0 on a free row) already
+//                                    force d_j = c_j - sum a_ij pi_i >= 0 (<= 0): some optimal solution has
+//                                    x_j at its lower (upper) bound, so it is fixed there like an F column
 // postsolve undoes the stack in reverse order on (x, pi, status): a removed row comes back basic with
 // pi = 0, except a singleton row whose implied bound is the one x_j sits on -- then the row takes
 // over (pi_i = d_j / a_ij, d_j = 0, the column becomes basic, the row nonbasic), which keeps the
@@ -87,6 +91,46 @@ int Presolve::presolve(const Engine &src, Engine &dst)
       offset += cost[j] * x;
       colAlive[j] = 0;
       actions.push_back({'F', j, -1, x, 0.0, 0.0, 0.0, 0.0});
+      changed = true;
+    }
+    // ---- D: columns whose reduced cost sign is decided by the row types alone
+    for (int j = 0; j < n; j++) {
+      if (!colAlive[j] || colCount[j] == 0 || !(upper[j] - lower[j] > 0.0))
+        continue;
+      bool canBeNegative = cost[j] < 0.0, canBePositive = cost[j] > 0.0;
+      for (int e = cs[j]; e < cs[j + 1] && !(canBeNegative && canBePositive); e++) {
+        const int i = ri[e];
+        if (!rowAlive[i] || va[e] == 0.0)
+          continue;
+        const bool hasLo = lower[n + i] > -kInf, hasUp = upper[n + i] < kInf;
+        if (hasLo && hasUp) { // equality or range: the dual is free
+          canBeNegative = canBePositive = true;
+        } else if (hasLo) { // pi_i >= 0: the term -a pi is <= 0 for a > 0, >= 0 for a < 0
+          (va[e] > 0.0 ? canBeNegative : canBePositive) = true;
+        } else if (hasUp) { // pi_i <= 0
+          (va[e] > 0.0 ? canBePositive : canBeNegative) = true;
+        } // free row: pi_i = 0
+      }
+      double x;
+      if (!canBeNegative && lower[j] > -kInf)
+        x = lower[j]; // d_j >= 0 whatever the duals are
+      else if (!canBePositive && upper[j] < kInf)
+        x = upper[j]; // d_j <= 0
+      else
+        continue;
+      for (int e = cs[j]; e < cs[j + 1]; e++) {
+        const int i = ri[e];
+        if (!rowAlive[i] || va[e] == 0.0)
+          continue;
+        if (lower[n + i] > -kInf)
+          lower[n + i] -= va[e] * x;
+        if (upper[n + i] < kInf)
+          upper[n + i] -= va[e] * x;
+        rowCount[i]--;
+      }
+      offset += cost[j] * x;
+      colAlive[j] = 0;
+      actions.push_back({'D', j, -1, x, 0.0, 0.0, 0.0, 0.0});
       changed = true;
     }
     // ---- S: singleton rows
@@ -225,6 +269,7 @@ void Presolve::postsolve(const std::vector<double> &xr, const std::vector<double
       solution[ac.col] = ac.value;
       status[ac.col] = isFixed;
       break;
+    case 'D':
     case 'C': {
       solution[ac.col] = ac.value;
       const double lo = orig.hLower[ac.col], up = orig.hUpper[ac.col];

@@ -173,3 +173,54 @@ def test_presolve_infeasibility_is_reported_on_the_original_model():
     s.loadLP(lp)
     assert s.initialSolve() == 1
     assert s.status() == 1 and s.isProvenPrimalInfeasible()
+
+
+def test_dual_fixing_removes_dominated_columns():
+    """remove_dual_action: columns whose reduced-cost sign follows from the row types alone are fixed at
+    the bound that sign prefers; the postsolved solution must be optimal for the ORIGINAL LP (oracle) with
+    a clean KKT audit, and the reduced model must really be smaller"""
+    import scipy.sparse as sp
+
+    rng = np.random.default_rng(12)
+    base = G.random_sparse_lp(60, 300, 0.08, 9)
+    A = base.to_scipy().tocsc()
+    m, n = base.m, base.n
+    # make every row one-sided (>=) so that all row duals are sign restricted, keep the LP feasible
+    row_lower = base.row_lower.copy()
+    row_upper = np.full(m, 1e30)
+    # dominated columns: only positive entries in >= rows and a positive cost -> d_j = c_j - a^T pi can be
+    # anything, so NOT dominated; only NEGATIVE entries and a positive cost -> d_j >= c_j > 0: fixed at lower;
+    # only positive entries and a negative cost -> d_j <= c_j < 0: fixed at upper
+    extra_cols, extra_cost, extra_lo, extra_up = [], [], [], []
+    for t in range(20):
+        rows = rng.choice(m, size=4, replace=False)
+        vals = rng.uniform(0.2, 1.0, size=4)
+        if t % 2 == 0:
+            extra_cols.append(sp.csc_matrix((-vals, (rows, np.zeros(4, dtype=int))), shape=(m, 1)))
+            extra_cost.append(float(rng.uniform(0.1, 1.0)))
+        else:
+            extra_cols.append(sp.csc_matrix((vals, (rows, np.zeros(4, dtype=int))), shape=(m, 1)))
+            extra_cost.append(-float(rng.uniform(0.1, 1.0)))
+        extra_lo.append(0.0)
+        extra_up.append(2.0)
+    A2 = sp.hstack([A] + extra_cols).tocsc()
+    lp = G.LP("dominated", m, n + 20, A2.indptr.astype(np.int32), A2.indices.astype(np.int32), A2.data.astype(float),
+              np.concatenate([base.col_lower, extra_lo]), np.concatenate([base.col_upper, extra_up]),
+              np.concatenate([base.objective, extra_cost]), row_lower, row_upper)
+    o = O.OracleSimplex(lp)
+    assert o.dual() == 0
+    s = clp_b200.ClpSimplex()
+    s.loadLP(lp)
+    st, red = s.presolvedModel()
+    assert st == 0 and red is not None
+    assert red.numberColumns() <= lp.n - 20           # at least the planted dominated columns are gone
+    rlp = red.getProblem()
+    ro = O.OracleSimplex(rlp)
+    assert ro.dual() == 0
+    red.setSolution(ro.column_solution(), ro.row_price(), ro.status())
+    s.postsolve(red)
+    assert abs(s.objectiveValue() - o.objective_value) <= 1e-8 * (1 + abs(o.objective_value))
+    x = s.primalColumnSolution()
+    assert np.all(x[n:][0::2] == 0.0) and np.all(x[n:][1::2] == 2.0)   # where the sign argument puts them
+    assert O.kkt_violations(lp, x, s.primalRowSolution(), s.dualColumnSolution()) == 0
+    assert int((s.statusArray() == 1).sum()) == lp.m
