@@ -221,7 +221,7 @@ private:
 // presolve.cpp -- elementary presolve actions and their postsolve (host only)
 struct Presolve {
   struct Action {
-    char kind;      // 'F' fixed column, 'S' singleton row, 'C' empty column, 'R' empty row, 'D' dominated column
+    char kind;      // 'F' fixed column, 'S' singleton row, 'C' empty column, 'R' empty row, 'D' dominated column, 'g'/'G' column fixed by a forcing row / the row itself
     int col, row;
     double value;   // F/C: the value of the column; S: the coefficient a_ij
     double oldLo, oldUp;         // S: column bounds before the row was folded in

@@ -4,11 +4,14 @@
 // of CoinPresolveAction objects that live in CoinUtils (not in the reference tree).  This file
 // restates the four elementary ones the driver always applies (src/ClpPresolve.cpp: make_fixed :966,
 // slack_doubleton_action :1141, drop_empty_cols_action :1448, drop_empty_rows_action :1449) and the dual
-// fixing of remove_dual_action (:1158, :1296), iterated to a fixed point:
+// fixing of remove_dual_action (:1158, :1296) and forcing_constraint_action (:1182), iterated to a fixed point:
 //   F  fixed column (l == u)       : removed, row bounds shifted by -a_ij x_j, constant c_j x_j
 //   S  singleton row a_ij x_j      : becomes bounds on x_j, row removed
 //   C  empty column                : set to the bound its cost prefers (unbounded if that is infinite)
 //   R  empty row                   : removed (infeasible if 0 is outside its bounds)
+//   G  forcing row                 : the smallest (largest) activity the column bounds allow equals the
+//                                    row's upper (lower) bound: every column of the row sits on the bound
+//                                    that attains it; they are fixed there and the row is removed
 //   D  dominated column            : the sign restrictions of the row duals (pi_i >= 0 on a row with only a
 //                                    lower bound, <= 0 with only an upper bound, 0 on a free row) already
 //                                    force d_j = c_j - sum a_ij pi_i >= 0 (<= 0): some optimal solution has
@@ -91,6 +94,65 @@ int Presolve::presolve(const Engine &src, Engine &dst)
       offset += cost[j] * x;
       colAlive[j] = 0;
       actions.push_back({'F', j, -1, x, 0.0, 0.0, 0.0, 0.0});
+      changed = true;
+    }
+    // ---- G: forcing rows
+    for (int i = 0; i < m; i++) {
+      if (!rowAlive[i] || rowCount[i] < 2)
+        continue;
+      double minAct = 0.0, maxAct = 0.0;
+      bool minFinite = true, maxFinite = true;
+      for (int e = rowStart[i]; e < rowStart[i + 1]; e++) {
+        const int j = colIdx[e];
+        const double a = rval[e];
+        if (!colAlive[j] || a == 0.0)
+          continue;
+        const double lo = lower[j], up = upper[j];
+        if (a > 0.0) {
+          lo > -kInf ? (void)(minAct += a * lo) : (void)(minFinite = false);
+          up < kInf ? (void)(maxAct += a * up) : (void)(maxFinite = false);
+        } else {
+          up < kInf ? (void)(minAct += a * up) : (void)(minFinite = false);
+          lo > -kInf ? (void)(maxAct += a * lo) : (void)(maxFinite = false);
+        }
+      }
+      const double rlo = lower[n + i], rup = upper[n + i];
+      const double tolUp = kFeasTol * (1.0 + std::fabs(rup)), tolLo = kFeasTol * (1.0 + std::fabs(rlo));
+      if ((minFinite && rup < kInf && minAct > rup + 1.0e3 * tolUp) || (maxFinite && rlo > -kInf && maxAct < rlo - 1.0e3 * tolLo))
+        return 1; // the column bounds cannot satisfy the row
+      int side = 0; // +1: activity pinned at the row's upper bound by the minimum, -1: at the lower by the maximum
+      if (minFinite && rup < kInf && std::fabs(minAct - rup) <= tolUp)
+        side = +1;
+      else if (maxFinite && rlo > -kInf && std::fabs(maxAct - rlo) <= tolLo)
+        side = -1;
+      if (side == 0)
+        continue;
+      for (int e = rowStart[i]; e < rowStart[i + 1]; e++) {
+        const int j = colIdx[e];
+        const double a = rval[e];
+        if (!colAlive[j] || a == 0.0)
+          continue;
+        // side +1: a > 0 -> lower bound, a < 0 -> upper bound; side -1: the other way round
+        const bool toLower = (a > 0.0) == (side > 0);
+        const double x = toLower ? lower[j] : upper[j];
+        for (int q = cs[j]; q < cs[j + 1]; q++) {
+          const int r2 = ri[q];
+          if (!rowAlive[r2] || va[q] == 0.0 || r2 == i)
+            continue;
+          if (lower[n + r2] > -kInf)
+            lower[n + r2] -= va[q] * x;
+          if (upper[n + r2] < kInf)
+            upper[n + r2] -= va[q] * x;
+          rowCount[r2]--;
+        }
+        offset += cost[j] * x;
+        colAlive[j] = 0;
+        // value = x, oldLo: 1 if the column went to its lower bound, row = the forcing row
+        actions.push_back({'g', j, i, x, toLower ? 1.0 : 0.0, a, 0.0, 0.0});
+      }
+      rowAlive[i] = 0;
+      rowCount[i] = 0;
+      actions.push_back({'G', -1, i, (double)side, 0.0, 0.0, 0.0, 0.0});
       changed = true;
     }
     // ---- D: columns whose reduced cost sign is decided by the row types alone
@@ -269,6 +331,39 @@ void Presolve::postsolve(const std::vector<double> &xr, const std::vector<double
       solution[ac.col] = ac.value;
       status[ac.col] = isFixed;
       break;
+    case 'G': {
+      // the forced columns of this row are the 'g' actions right below on the stack; their values and
+      // bound sides are known, the row dual is the tightest one that keeps all their reduced costs on
+      // the feasible side (row at upper: pi <= 0, at lower: pi >= 0); if it is nonzero the column that
+      // attains it becomes basic and the row nonbasic at that bound, otherwise the row stays basic
+      const int i = ac.row;
+      const int side = (int)ac.value;
+      for (int b = a - 1; b >= 0 && actions[b].kind == 'g' && actions[b].row == i; b--) {
+        solution[actions[b].col] = actions[b].value;
+        status[actions[b].col] = actions[b].oldLo != 0.0 ? atLowerBound : atUpperBound;
+      }
+      rowPrice[i] = 0.0;
+      status[n + i] = basic;
+      double best = 0.0;
+      int bestCol = -1;
+      for (int b = a - 1; b >= 0 && actions[b].kind == 'g' && actions[b].row == i; b--) {
+        const int j = actions[b].col;
+        const double aij = actions[b].oldUp; // coefficient of the column in the forcing row
+        const double ratio = dj(j) / aij;    // pi_i that makes d_j exactly zero
+        if ((side > 0 && ratio < best) || (side < 0 && ratio > best)) {
+          best = ratio;
+          bestCol = j;
+        }
+      }
+      if (bestCol >= 0) {
+        rowPrice[i] = best;
+        status[bestCol] = basic;
+        status[n + i] = side > 0 ? atUpperBound : atLowerBound;
+      }
+      break;
+    }
+    case 'g':
+      break; // handled by the 'G' entry of its row
     case 'D':
     case 'C': {
       solution[ac.col] = ac.value;

@@ -34,8 +34,8 @@ int Clpb_loadProblem(Clpb_Simplex *model, int numcols, int numrows, const int *s
 /* Clp_readMps :116 (ClpModel::readMps src/ClpModel.cpp:2884) */
 int Clpb_readMps(Clpb_Simplex *model, const char *filename, int keepNames, int ignoreErrors);
 /* ClpPresolve::presolvedModel / postsolve (src/ClpPresolve.hpp:40,61) restricted to the elementary
-   actions (fixed columns, singleton rows, empty columns, empty rows, dual fixing of dominated columns;
-   src/ClpPresolve.cpp:966,1141,1448,1449,1158).  Clpb_presolvedModel returns a NEW model (delete it with Clpb_deleteModel) holding the
+   actions (fixed columns, singleton rows, empty columns, empty rows, dual fixing of dominated columns,
+   forcing rows; src/ClpPresolve.cpp:966,1141,1448,1449,1158,1182).  Clpb_presolvedModel returns a NEW model (delete it with Clpb_deleteModel) holding the
    reduced problem, or NULL with *status = 1 (primal infeasible) / 2 (dual infeasible); the original
    model keeps the postsolve information.  After solving the reduced model, Clpb_postsolve writes
    the solution of the original problem (primal, dual, status, objective) into the original model.

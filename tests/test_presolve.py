@@ -224,3 +224,50 @@ def test_dual_fixing_removes_dominated_columns():
     assert np.all(x[n:][0::2] == 0.0) and np.all(x[n:][1::2] == 2.0)   # where the sign argument puts them
     assert O.kkt_violations(lp, x, s.primalRowSolution(), s.dualColumnSolution()) == 0
     assert int((s.statusArray() == 1).sum()) == lp.m
+
+
+def test_forcing_rows_fix_their_columns():
+    """forcing_constraint_action: rows whose bound equals the extreme activity the column bounds allow pin
+    all their columns; postsolve must give the row the dual that keeps every pinned column dual feasible
+    (and make one of them basic when that dual is nonzero)"""
+    import scipy.sparse as sp
+
+    rng = np.random.default_rng(4)
+    base = G.random_sparse_lp(50, 260, 0.08, 3)
+    A = base.to_scipy().tocsr()
+    m, n = base.m, base.n
+    extra_rows, rl, ru = [], [], []
+    used = set()
+    for t in range(6):
+        cols = [j for j in rng.permutation(n) if j not in used][:3]
+        used.update(cols)
+        coef = rng.choice([-1.5, 0.7, 2.0], size=3)
+        extra_rows.append(sp.csr_matrix((coef, (np.zeros(3, dtype=int), cols)), shape=(1, n)))
+        lo, up = base.col_lower[cols], base.col_upper[cols]
+        min_act = float(np.where(coef > 0, coef * lo, coef * up).sum())
+        max_act = float(np.where(coef > 0, coef * up, coef * lo).sum())
+        if t % 2 == 0:      # activity <= its minimum: pinned at the lower corner
+            rl.append(-1e30); ru.append(min_act)
+        else:               # activity >= its maximum
+            rl.append(max_act); ru.append(1e30)
+    A2 = sp.vstack([A] + extra_rows).tocsc()
+    lp = G.LP("forcing", m + 6, n, A2.indptr.astype(np.int32), A2.indices.astype(np.int32), A2.data.astype(float),
+              base.col_lower, base.col_upper, base.objective,
+              np.concatenate([base.row_lower, rl]), np.concatenate([base.row_upper, ru]))
+    o = O.OracleSimplex(lp)
+    ost = o.dual()
+    s = clp_b200.ClpSimplex()
+    s.loadLP(lp)
+    st, red = s.presolvedModel()
+    if ost != 0:
+        pytest.skip("pinning made this instance infeasible")
+    assert st == 0 and red is not None
+    assert red.numberRows() <= lp.m - 6 and red.numberColumns() <= lp.n - 18
+    rlp = red.getProblem()
+    ro = O.OracleSimplex(rlp)
+    assert ro.dual() == 0
+    red.setSolution(ro.column_solution(), ro.row_price(), ro.status())
+    s.postsolve(red)
+    assert abs(s.objectiveValue() - o.objective_value) <= 1e-8 * (1 + abs(o.objective_value))
+    assert O.kkt_violations(lp, s.primalColumnSolution(), s.primalRowSolution(), s.dualColumnSolution()) == 0
+    assert int((s.statusArray() == 1).sum()) == lp.m
