@@ -511,3 +511,21 @@ print("ok", rank)
         out, err = p.communicate(timeout=120)
         assert p.returncode == 0, err
         assert "ok" in out
+
+
+def test_netlib_afiro_reference_objective():
+    """BASELINE.json configs[0]: Netlib afiro through this repo's MPS reader and the oracle; the value is
+    the reference's own (src/unitTest.cpp:480-486: 28 rows incl. the objective, 32 columns,
+    -4.6475314286e+02 to objValueTol 1e-8)"""
+    import clp_b200
+
+    s = clp_b200.ClpSimplex()
+    assert s.readMps(os.path.join(ROOT, "tests", "golden", "afiro.mps")) == 0
+    assert (s.numberRows() + 1, s.numberColumns(), s.getNumElements()) == (28, 32, 83)
+    lp = s.getProblem()
+    o = O.OracleSimplex(lp)
+    assert o.dual() == 0
+    assert abs(o.objective_value - (-4.6475314286e+02)) <= 1e-8 * (1 + 464.75314286)
+    fx = load_golden("afiro")
+    assert (fx.m, fx.n, fx.nnz) == (lp.m, lp.n, lp.nnz)
+    assert np.array_equal(fx.element, lp.element) and np.array_equal(fx.row_index, lp.row_index)
