@@ -48,6 +48,7 @@ SIGNATURES = {
     "Clpb_chgRowLower": (None, [ctypes.c_void_p, c_double_p]),
     "Clpb_chgRowUpper": (None, [ctypes.c_void_p, c_double_p]),
     "Clpb_lastSolveWasHot": (ctypes.c_int, [ctypes.c_void_p]),
+    "Clpb_refactorizationInterval": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "Clpb_dual": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "Clpb_status": (ctypes.c_int, [ctypes.c_void_p]),
     "Clpb_objectiveValue": (ctypes.c_double, [ctypes.c_void_p]),

@@ -287,6 +287,7 @@ void Clpb_chgColumnUpper(Clpb_Simplex *model, const double *columnUpper) { model
 void Clpb_chgRowLower(Clpb_Simplex *model, const double *rowLower) { model->e.chgBounds(nullptr, nullptr, rowLower, nullptr); }
 void Clpb_chgRowUpper(Clpb_Simplex *model, const double *rowUpper) { model->e.chgBounds(nullptr, nullptr, nullptr, rowUpper); }
 int Clpb_lastSolveWasHot(Clpb_Simplex *model) { return model->e.lastSolveWasHot ? 1 : 0; }
+int Clpb_refactorizationInterval(Clpb_Simplex *model, int nucleusSize) { return model->e.cycleFor(nucleusSize); }
 int Clpb_dual(Clpb_Simplex *model, int)
 {
   return guarded([&] { return model->e.dual(); });

@@ -97,6 +97,7 @@ public:
   void chgBounds(const double *columnLower, const double *columnUpper, const double *rowLower,
                  const double *rowUpper); // NULL = unchanged
   bool lastSolveWasHot = false;
+  int cycleFor(int k) const; // refactorization interval the default policy uses at nucleus size k (host only)
   int problemStatus = -1;
   int numberIterations = 0, numberRefactorizations = 0;
   double objectiveValue = 0.0, sumPrimalInfeasibilities = 0.0;
@@ -211,7 +212,6 @@ private:
   void fetchState();
   void downloadSolution();
   int defaultFactorizationFrequency() const;
-  int cycleFor(int k) const;
   void resetStateForRun();
   void buildRowCopy(const std::vector<double> &val, std::vector<int> &rowStart,
                     std::vector<int> &colIdx, std::vector<double> &rval) const;

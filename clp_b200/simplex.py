@@ -187,6 +187,7 @@ class ClpSimplex:
     def chgRowLower(self, v): self._L.Clpb_chgRowLower(self._h, _dp(np.ascontiguousarray(v, dtype=np.float64)))
     def chgRowUpper(self, v): self._L.Clpb_chgRowUpper(self._h, _dp(np.ascontiguousarray(v, dtype=np.float64)))
     def lastSolveWasHot(self): return bool(self._L.Clpb_lastSolveWasHot(self._h))
+    def refactorizationInterval(self, nucleusSize): return self._L.Clpb_refactorizationInterval(self._h, int(nucleusSize))
 
     def fastDual(self):
         """ClpSimplexDual::fastDual: dual() that keeps the device-resident factors of the previous solve"""

@@ -98,6 +98,11 @@ void Clpb_chgColumnUpper(Clpb_Simplex *model, const double *columnUpper);
 void Clpb_chgRowLower(Clpb_Simplex *model, const double *rowLower);
 void Clpb_chgRowUpper(Clpb_Simplex *model, const double *rowUpper);
 int Clpb_lastSolveWasHot(Clpb_Simplex *model);
+/* ClpFactorization::maximumPivots (src/ClpFactorization.hpp:149) as the default policy sets it for a basis
+   whose structural part ("nucleus") has nucleusSize columns: twice ClpSimplex::defaultFactorizationFrequency
+   (src/ClpSimplex.cpp:11401), stretched when the modelled cost of the dense refactorization outweighs the
+   iterations of a cycle; "factorizationFrequency" > 0 overrides it.  Host only. */
+int Clpb_refactorizationInterval(Clpb_Simplex *model, int nucleusSize);
 /* Clp_dual :346 (ClpSimplex::dual src/ClpSimplex.cpp:5631).  Returns Clp_status :212:
    0 optimal, 1 primal infeasible, 2 dual infeasible, 3 stopped on iterations/time,
    4 stopped due to errors. */

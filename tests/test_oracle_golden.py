@@ -529,3 +529,32 @@ def test_netlib_afiro_reference_objective():
     fx = load_golden("afiro")
     assert (fx.m, fx.n, fx.nnz) == (lp.m, lp.n, lp.nnz)
     assert np.array_equal(fx.element, lp.element) and np.array_equal(fx.row_index, lp.row_index)
+
+
+def test_default_refactorization_interval_policy():
+    """host-only: the default interval is twice ClpSimplex::defaultFactorizationFrequency
+    (src/ClpSimplex.cpp:11401-11431) and is stretched only where the dense refactorization of a large
+    nucleus would dominate a cycle (staircase-like bases); an explicit factorizationFrequency wins"""
+    import clp_b200
+    from bench import clp_default_frequency, default_cycle
+
+    for m, n, dens in ((1000, 10000, 0.01), (10000, 100000, 0.01)):
+        lp = G.random_sparse_lp(m, n, dens, 1) if m < 5000 else None
+        if lp is None:   # sizes only: an LP with the right dimensions and nnz is enough for the model
+            lp = G.LP("dims", m, n, np.arange(0, 100 * n + 1, 100, dtype=np.int32), np.zeros(100 * n, dtype=np.int32),
+                      np.ones(100 * n), np.zeros(n), np.ones(n), np.zeros(n), np.zeros(m), np.ones(m))
+        s = clp_b200.ClpSimplex(); s.loadLP(lp)
+        base = 2 * clp_default_frequency(m)
+        assert default_cycle(m) == base
+        assert s.refactorizationInterval(0) == base
+        assert s.refactorizationInterval(m // 2) == base          # C2's nucleus: the base interval
+        assert base <= s.refactorizationInterval(m) <= 2048
+        s.setFactorizationFrequency(123)
+        assert s.refactorizationInterval(m) == 123
+    # staircase shape (m = n = 20 000, 4e5 nonzeros): the interval grows with the nucleus
+    m = n = 20000
+    lp = G.LP("dims", m, n, np.arange(0, 20 * n + 1, 20, dtype=np.int32), np.zeros(20 * n, dtype=np.int32),
+              np.ones(20 * n), np.zeros(n), np.ones(n), np.zeros(n), np.zeros(m), np.ones(m))
+    s = clp_b200.ClpSimplex(); s.loadLP(lp)
+    vals = [s.refactorizationInterval(k) for k in (2000, 8000, 12000, 17000, 20000)]
+    assert vals[0] == 2 * clp_default_frequency(m) and vals == sorted(vals) and vals[-1] > 2 * vals[0]
